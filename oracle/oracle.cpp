@@ -1,0 +1,247 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see jsnum.hpp header).  PARITY UNPINNED.
+//
+// oracle.cpp — C API over the restatement so Python tests / bench.py's cpu_baseline can drive it
+// through ctypes.  The product (cpu_raymarcher_b200/) never links or loads this library.
+// The worker entry it mirrors: src/workers/raymarchWorker.ts:33-92 (build scene + accel per job,
+// set camera, run the chosen algorithm over rows [yStart, yEnd)).
+#include <cstring>
+#include <deque>
+#include <thread>
+
+#include "march.hpp"
+
+using namespace orc;
+
+struct orc_scene {
+    Scene scene;
+};
+
+static Primitive prim_from_flat(int type, const float* m, const double* prm) {
+    Primitive p;
+    p.type = type;
+    for (int i = 0; i < 16; ++i) p.transform.e[i] = m[i];
+    if (type == SPHERE) p.radius = prm[0];
+    else if (type == BOX) p.halfSize = glm::v3_from(prm[0], prm[1], prm[2]);
+    else {
+        p.majorRadius = prm[0];
+        p.minorRadius = prm[1];
+    }
+    return p;
+}
+
+extern "C" {
+
+orc_scene* orc_scene_new(void) { return new orc_scene(); }
+void orc_scene_free(orc_scene* s) { delete s; }
+void orc_set_length_mode(int use_hypot) { glm::length_uses_hypot() = use_hypot != 0; }
+
+int orc_scene_load_preset(orc_scene* s, int idx) {
+    std::vector<Primitive> prims;
+    if (!makePreset(idx, prims)) return -1;
+    s->scene.setObjects(std::move(prims));
+    return 0;
+}
+void orc_scene_load_synthetic(orc_scene* s, int n, uint32_t seed) {
+    std::vector<Primitive> prims;
+    makeSyntheticSpheres(n, seed, prims);
+    s->scene.setObjects(std::move(prims));
+}
+void orc_scene_set_prims(orc_scene* s, int n, const uint8_t* type, const float* w2l, const double* params) {
+    std::vector<Primitive> prims;
+    for (int i = 0; i < n; ++i) prims.push_back(prim_from_flat(type[i], w2l + 16 * i, params + 4 * i));
+    s->scene.setObjects(std::move(prims));
+}
+int orc_scene_n_prims(orc_scene* s) { return (int)s->scene.objects.size(); }
+void orc_scene_get_prims(orc_scene* s, uint8_t* type, float* w2l, double* params) {
+    for (size_t i = 0; i < s->scene.objects.size(); ++i) {
+        const Primitive& p = s->scene.objects[i];
+        type[i] = (uint8_t)p.type;
+        std::memcpy(w2l + 16 * i, p.transform.e, 16 * sizeof(float));
+        double* q = params + 4 * i;
+        q[0] = q[1] = q[2] = q[3] = 0;
+        if (p.type == SPHERE) q[0] = p.radius;
+        else if (p.type == BOX) {
+            q[0] = p.halfSize[0];
+            q[1] = p.halfSize[1];
+            q[2] = p.halfSize[2];
+        } else {
+            q[0] = p.majorRadius;
+            q[1] = p.minorRadius;
+        }
+    }
+}
+void orc_scene_build_accel(orc_scene* s, int kind) { s->scene.buildAccel(kind); }
+void orc_scene_set_camera(orc_scene* s, double pitch, double yaw) { s->scene.camera.setAngles(pitch, yaw); }
+// raymarcher.ts:62-67 : rot3 = mat3.fromMat4(camera.getRotationMatrix()), origin = camera.getPosition()
+void orc_scene_get_camera(orc_scene* s, float* rot3, float* origin) {
+    mat4 r;
+    s->scene.camera.getRotationMatrix(r);
+    mat3 m3;
+    glm::m3_from_mat4(m3, r);
+    std::memcpy(rot3, m3.e, sizeof(m3.e));
+    vec3 o = glm::v3_create();
+    s->scene.camera.getPosition(o);
+    std::memcpy(origin, o.e, sizeof(o.e));
+}
+// main.ts:438-441 : analytics auto-rotate (yaw += 0.015 before each frame)
+void orc_scene_rotate_camera(orc_scene* s, double dpitch, double dyaw) { s->scene.camera.rotateCamera(dpitch, dyaw); }
+void orc_scene_get_angles(orc_scene* s, double* out) {
+    out[0] = s->scene.camera.pitch;
+    out[1] = s->scene.camera.yaw;
+}
+
+// ---- flatten the pointer trees (pre-order for the BVH, FIFO/8-consecutive-children for the octree)
+static void bvh_count(const BVHNode* n, int& nodes, int& leafPrims) {
+    nodes++;
+    if (n->isLeaf()) leafPrims += (int)n->primitives.size();
+    if (n->left) bvh_count(n->left.get(), nodes, leafPrims);
+    if (n->right) bvh_count(n->right.get(), nodes, leafPrims);
+}
+int orc_bvh_counts(orc_scene* s, int* nNodes, int* nLeafPrims) {
+    if (!s->scene.bvh) return -1;
+    *nNodes = 0;
+    *nLeafPrims = 0;
+    bvh_count(s->scene.bvh->root.get(), *nNodes, *nLeafPrims);
+    return 0;
+}
+static int bvh_flat(const BVHNode* n, float* bounds, int32_t* links, int32_t* leafPrims, int& nextNode, int& nextPrim) {
+    int me = nextNode++;
+    for (int k = 0; k < 3; ++k) {
+        bounds[6 * me + k] = n->bounds.min.e[k];
+        bounds[6 * me + 3 + k] = n->bounds.max.e[k];
+    }
+    links[4 * me + 2] = nextPrim;
+    links[4 * me + 3] = 0;
+    if (n->isLeaf()) {
+        links[4 * me + 3] = (int)n->primitives.size();
+        for (auto* p : n->primitives) leafPrims[nextPrim++] = p->index;
+    }
+    links[4 * me + 0] = n->left ? bvh_flat(n->left.get(), bounds, links, leafPrims, nextNode, nextPrim) : -1;
+    links[4 * me + 1] = n->right ? bvh_flat(n->right.get(), bounds, links, leafPrims, nextNode, nextPrim) : -1;
+    return me;
+}
+void orc_bvh_flatten(orc_scene* s, float* bounds, int32_t* links, int32_t* leafPrims) {
+    int nn = 0, np = 0;
+    bvh_flat(s->scene.bvh->root.get(), bounds, links, leafPrims, nn, np);
+}
+int orc_octree_counts(orc_scene* s, int* nNodes, int* nLeafPrims) {
+    if (!s->scene.octree) return -1;
+    int nodes = 0, prims = 0;
+    std::deque<const OctreeNode*> q{s->scene.octree->root.get()};
+    while (!q.empty()) {
+        const OctreeNode* n = q.front();
+        q.pop_front();
+        nodes++;
+        prims += (int)n->primitives.size();
+        for (auto& c : n->children) q.push_back(c.get());
+    }
+    *nNodes = nodes;
+    *nLeafPrims = prims;
+    return 0;
+}
+// links: 3 per node = first_child (-1 for leaf), prim_first, prim_count
+void orc_octree_flatten(orc_scene* s, float* bounds, int32_t* links, uint8_t* level, uint8_t* isEmpty, double* minDist,
+                        int32_t* leafPrims) {
+    std::deque<const OctreeNode*> q{s->scene.octree->root.get()};
+    int me = 0, nextSlot = 1, nextPrim = 0;
+    while (!q.empty()) {
+        const OctreeNode* n = q.front();
+        q.pop_front();
+        for (int k = 0; k < 3; ++k) {
+            bounds[6 * me + k] = n->bounds.min.e[k];
+            bounds[6 * me + 3 + k] = n->bounds.max.e[k];
+        }
+        level[me] = (uint8_t)n->level;
+        isEmpty[me] = n->isEmpty ? 1 : 0;
+        minDist[me] = n->minDistance;
+        links[3 * me + 1] = nextPrim;
+        links[3 * me + 2] = (int)n->primitives.size();
+        for (auto* p : n->primitives) leafPrims[nextPrim++] = p->index;
+        if (n->hasChildren) {
+            links[3 * me + 0] = nextSlot;
+            nextSlot += 8;
+            for (auto& c : n->children) q.push_back(c.get());
+        } else {
+            links[3 * me + 0] = -1;
+        }
+        me++;
+    }
+}
+
+// ---- render (raymarchWorker.ts:33-92 minus the scene construction, which the caller did above)
+void orc_render(orc_scene* s, int algo, double stepSize, double overshoot, int width, int height, int yStart, int yEnd,
+                uint8_t* depth, uint8_t* normal, uint16_t* sdf, uint16_t* iters, double* depthF64, uint32_t* sdfFull,
+                uint32_t* itersFull, int nthreads) {
+    MarchParams mp;
+    mp.algo = algo;
+    mp.stepSize = stepSize;
+    mp.overshootFactor = overshoot;
+    Raymarcher rm(s->scene, mp);
+    if (nthreads <= 1) {
+        rm.runRows(width, height, yStart, yEnd, 0, 1, depth, normal, sdf, iters, depthF64, sdfFull, itersFull);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t]() {
+            rm.runRows(width, height, yStart, yEnd, t, nthreads, depth, normal, sdf, iters, depthF64, sdfFull, itersFull);
+        });
+    for (auto& t : th) t.join();
+}
+
+void orc_shade(int shader, uint8_t* rgba, const uint8_t* depth, const uint8_t* normal, const uint16_t* sdf,
+               const uint16_t* iters, int w, int h) {
+    size_t n = (size_t)w * h;
+    switch (shader) {
+        case SH_PHONG: shadePhong(rgba, depth, normal, n); break;
+        case SH_SDF_HEAT: shadeHeat(rgba, sdf, n); break;
+        case SH_ITER_HEAT: shadeHeat(rgba, iters, n); break;
+        default: shadeNormal(rgba, normal, n); break;
+    }
+}
+// out = {total SDF calls, max, min, total iterations}  (main.ts:527-543)
+void orc_stats(const uint16_t* sdf, const uint16_t* iters, size_t n, double* out) {
+    FrameStats st = frameStats(sdf, iters, n);
+    out[0] = st.totalSDFCalls;
+    out[1] = st.maxSDFCalls;
+    out[2] = st.minSDFCalls;
+    out[3] = st.totalIterations;
+}
+
+// ---- unit probes for tests
+double orc_hypot3(double a, double b, double c) { return js::hypot3(a, b, c); }
+int orc_to_u8(double x) { return js::to_u8_clamp(x); }
+double orc_min2(double a, double b) { return js::min2(a, b); }
+double orc_max2(double a, double b) { return js::max2(a, b); }
+int orc_mat4_invert(const float* in, float* out) {
+    mat4 a, o = glm::m4_create();
+    std::memcpy(a.e, in, sizeof(a.e));
+    bool ok = glm::m4_invert(o, a);
+    std::memcpy(out, o.e, sizeof(o.e));
+    return ok ? 0 : -1;
+}
+void orc_get_transform(double x, double y, double z, const float* rot_or_null, float* out) {
+    vec3 r;
+    if (rot_or_null) r = vec3{{rot_or_null[0], rot_or_null[1], rot_or_null[2]}};
+    mat4 m = getTransform(x, y, z, rot_or_null ? &r : nullptr);
+    std::memcpy(out, m.e, sizeof(m.e));
+}
+double orc_prim_sdf(orc_scene* s, int prim, const float* p) {
+    vec3 v{{p[0], p[1], p[2]}};
+    return s->scene.objects[prim].sdf(v);
+}
+double orc_scene_distance(orc_scene* s, const float* p, uint32_t* count) {
+    vec3 v{{p[0], p[1], p[2]}};
+    uint32_t c = 0;
+    double d = s->scene.getDistance(v, c);
+    *count = c;
+    return d;
+}
+double orc_mulberry32(uint32_t seed, int nth) {
+    Mulberry32 r(seed);
+    double v = 0;
+    for (int i = 0; i <= nth; ++i) v = r.next();
+    return v;
+}
+
+}  // extern "C"
