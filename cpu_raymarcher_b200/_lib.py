@@ -1,0 +1,104 @@
+"""ctypes binding of librm_b200.so (include/rm.h).  The library is the product; if it is missing this
+module raises — there is no Python/CPU fallback for the raymarch path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librm_b200.so")
+
+RM_OK = 0
+RM_ERR_ARG, RM_ERR_UNSUPPORTED_PRIMITIVE, RM_ERR_CUDA, RM_ERR_STATE, RM_ERR_NOMEM = -1, -2, -3, -4, -5
+RM_F_VALIDATE_FP64, RM_F_LENGTH_SQRT = 1, 2
+STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_ARG", -2: "RM_ERR_UNSUPPORTED_PRIMITIVE", -3: "RM_ERR_CUDA",
+                -4: "RM_ERR_STATE", -5: "RM_ERR_NOMEM"}
+
+ALGORITHMS = {"sphere-tracer": 0, "fixed-step": 1, "adaptive-step": 2, "adaptive-step-v2": 3, "adaptive-step-v3": 4}
+ACCELS = {"None": 0, "Octree": 1, "BVH": 2}
+SHADERS = {None: -1, "none": -1, "normal": 0, "phong": 1, "sdf-heatmap": 2, "iteration-heatmap": 3}
+
+
+class RmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("left", C.c_int32), ("right", C.c_int32),
+                ("prim_first", C.c_int32), ("prim_count", C.c_int32)]
+
+
+class OctreeNode(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("first_child", C.c_int32), ("prim_first", C.c_int32),
+                ("prim_count", C.c_int32), ("level", C.c_uint8), ("is_empty", C.c_uint8), ("pad_", C.c_uint8 * 2),
+                ("min_distance", C.c_double)]
+
+
+class Scene(C.Structure):
+    _fields_ = [("n_prims", C.c_int32), ("type", C.c_void_p), ("world_to_local", C.c_void_p), ("params", C.c_void_p),
+                ("accel_kind", C.c_int32), ("n_nodes", C.c_int32), ("nodes", C.c_void_p), ("n_leaf_prims", C.c_int32),
+                ("leaf_prim_index", C.c_void_p)]
+
+
+class Request(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("y_start", C.c_int32), ("y_end", C.c_int32),
+                ("time", C.c_double), ("rot3", C.c_float * 9), ("origin", C.c_float * 3), ("algorithm", C.c_int32),
+                ("step_size", C.c_double), ("overshoot_factor", C.c_double), ("shader", C.c_int32),
+                ("shader_analytics", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("normal", C.c_void_p), ("sdf_eval", C.c_void_p), ("iters", C.c_void_p),
+                ("rgba", C.c_void_p), ("rgba_analytics", C.c_void_p), ("depth_f32", C.c_void_p),
+                ("sdf_eval_u32", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_pixels", C.c_uint64), ("sum_sdf", C.c_uint64), ("sum_iters", C.c_uint64), ("max_sdf", C.c_uint32),
+                ("min_sdf", C.c_uint32), ("max_iters", C.c_uint32), ("min_iters", C.c_uint32),
+                ("sum_sdf_full", C.c_uint64), ("sum_iters_full", C.c_uint64), ("evals_by_type", C.c_uint64 * 3),
+                ("n_hit", C.c_uint64), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
+                ("device", C.c_int32)]
+
+
+# every symbol include/rm.h declares
+EXPORTS = ["rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_upload_scene",
+           "rm_build_bvh", "rm_build_octree", "rm_render", "rm_render_device", "rm_stats", "rm_shade", "rm_alloc",
+           "rm_free", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C cpu_raymarcher_b200/csrc). There is no CPU fallback for the raymarch path.")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint
+        L.rm_abi_version.restype = C.c_int
+        L.rm_device_count.restype = C.c_int
+        L.rm_create.argtypes = [C.POINTER(vp), C.c_int, u32]
+        L.rm_destroy.argtypes = [vp]
+        L.rm_destroy.restype = None
+        L.rm_last_error.argtypes = [vp]
+        L.rm_last_error.restype = C.c_char_p
+        L.rm_upload_scene.argtypes = [vp, C.POINTER(Scene)]
+        L.rm_build_bvh.argtypes = [i32, vp, vp, vp, u32, vp, C.POINTER(i32), vp, C.POINTER(i32)]
+        L.rm_build_octree.argtypes = [i32, vp, vp, vp, u32, vp, C.POINTER(i32), vp, C.POINTER(i32)]
+        L.rm_render.argtypes = [vp, C.POINTER(Request), C.POINTER(Result)]
+        L.rm_render_device.argtypes = [vp, C.POINTER(Request), C.POINTER(Result), vp]
+        L.rm_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.rm_shade.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32]
+        L.rm_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.rm_free.argtypes = [vp, vp]
+        L.rm_ipc_export.argtypes = [vp, vp, vp]
+        L.rm_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+        L.rm_ipc_close.argtypes = [vp, vp]
+        L.rm_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+        L.rm_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+        _LIB = L
+    return _LIB

@@ -1,0 +1,580 @@
+// rm_api.cu — the C ABI declared in include/rm.h: context, scene upload, render, stats, shade, IPC.
+//
+// One rm_ctx = one CUDA device + one stream.  The scene (primitive arrays, packed fast-path records,
+// flattened BVH / octree) is uploaded once and stays resident in HBM; a render call only ships the
+// ~140-byte request and brings back the band's planes.  There is no CPU fallback anywhere in this
+// file: if the CUDA runtime reports no device, rm_create fails with RM_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rm_host.h"
+#include "rm_types.h"
+
+using namespace rm;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+}  // namespace
+
+struct rm_ctx {
+    int device = 0;
+    unsigned flags = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    std::string err;
+    // scene
+    bool has_scene = false;
+    DevScene scene{};
+    std::vector<void*> scene_allocs;
+    // per-launch stats
+    DevStats* d_stats = nullptr;
+    DevStats* h_stats = nullptr;  // pinned
+    rm_stats_t last{};
+    // band staging for rm_render (device planes + pinned host mirror)
+    DevBuf d_frame, h_frame;
+    // user allocations (rm_alloc)
+    std::vector<void*> user_allocs;
+};
+
+namespace {
+
+int fail(rm_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+#define CU(c, call)                                                                             \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) return fail(c, RM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+void free_scene(rm_ctx* c) {
+    for (void* p : c->scene_allocs) cudaFree(p);
+    c->scene_allocs.clear();
+    c->has_scene = false;
+    std::memset(&c->scene, 0, sizeof(c->scene));
+}
+
+template <class T>
+int upload(rm_ctx* c, const T* host, size_t n, const T** dev_out) {
+    *dev_out = nullptr;
+    if (n == 0) return RM_OK;
+    void* d = nullptr;
+    CU(c, cudaMalloc(&d, n * sizeof(T)));
+    c->scene_allocs.push_back(d);
+    CU(c, cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dev_out = (const T*)d;
+    return RM_OK;
+}
+
+int ensure(rm_ctx* c, DevBuf& b, size_t bytes, bool pinned_host) {
+    if (b.cap >= bytes) return RM_OK;
+    if (b.p) {
+        if (pinned_host) cudaFreeHost(b.p);
+        else cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 8 + 256;
+    if (pinned_host) CU(c, cudaMallocHost(&b.p, cap));
+    else CU(c, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return RM_OK;
+}
+
+bool is_translation_sphere(uint8_t type, const float* m) {
+    if (type != RM_PRIM_SPHERE) return false;
+    static const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    for (int i = 0; i < 12; ++i)
+        if (m[i] != I[i]) return false;  // -0 == 0
+    return m[15] == 1.f;
+}
+bool is_affine(const float* m) { return m[3] == 0.f && m[7] == 0.f && m[11] == 0.f && m[15] == 1.f; }
+
+int validate_request(rm_ctx* c, const rm_request* rq) {
+    if (!rq) return fail(c, RM_ERR_ARG, "request is null");
+    if (rq->width <= 0 || rq->height <= 0) return fail(c, RM_ERR_ARG, "bad frame size %dx%d", rq->width, rq->height);
+    if (rq->y_start < 0 || rq->y_end > rq->height) return fail(c, RM_ERR_ARG, "band [%d,%d) outside frame height %d", rq->y_start, rq->y_end, rq->height);
+    if (rq->algorithm < 0 || rq->algorithm > RM_ALG_ADAPTIVE_STEP_V3) return fail(c, RM_ERR_ARG, "bad algorithm %d", rq->algorithm);
+    if (rq->shader < RM_SHADER_NONE || rq->shader > RM_SHADER_ITERATION_HEATMAP) return fail(c, RM_ERR_ARG, "bad shader %d", rq->shader);
+    if (rq->shader_analytics < RM_SHADER_NONE || rq->shader_analytics > RM_SHADER_ITERATION_HEATMAP)
+        return fail(c, RM_ERR_ARG, "bad analytics shader %d", rq->shader_analytics);
+    return RM_OK;
+}
+
+// Enqueue the render of one band into device planes; read the stats back; fill c->last.
+int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, cudaStream_t stream) {
+    auto w0 = std::chrono::steady_clock::now();
+    if (!c->has_scene) return fail(c, RM_ERR_STATE, "rm_render before rm_upload_scene");
+    int rc = validate_request(c, rq);
+    if (rc) return rc;
+    if (!out || !out->depth || !out->normal || !out->sdf_eval || !out->iters)
+        return fail(c, RM_ERR_ARG, "result planes depth/normal/sdf_eval/iters are required");
+    const int bandH = rq->y_end > rq->y_start ? rq->y_end - rq->y_start : 0;  // Math.max(0, yEnd - yStart)
+    CU(c, cudaSetDevice(c->device));
+
+    RenderParams P{};
+    P.scene = c->scene;
+    P.width = rq->width;
+    P.height = rq->height;
+    P.y_start = rq->y_start;
+    P.y_end = rq->y_start + bandH;
+    std::memcpy(P.rot3, rq->rot3, sizeof(P.rot3));
+    std::memcpy(P.origin, rq->origin, sizeof(P.origin));
+    P.algorithm = rq->algorithm;
+    P.step_size = rq->step_size;
+    P.overshoot = rq->overshoot_factor;
+    P.shader = rq->shader;
+    P.shader2 = rq->shader_analytics;
+    P.length_sqrt = (c->flags & RM_F_LENGTH_SQRT) ? 1 : 0;
+    P.tiles_x = (rq->width + kTileW - 1) / kTileW;
+    P.n_tiles = P.tiles_x * ((bandH + kTileH - 1) / kTileH);
+    P.depth = out->depth;
+    P.normal = out->normal;
+    P.sdf = out->sdf_eval;
+    P.iters = out->iters;
+    P.rgba = (rq->shader != RM_SHADER_NONE) ? out->rgba : nullptr;
+    P.rgba2 = (rq->shader_analytics != RM_SHADER_NONE) ? out->rgba_analytics : nullptr;
+    P.depth_f32 = out->depth_f32;
+    P.sdf_u32 = out->sdf_eval_u32;
+    P.stats = c->d_stats;
+
+    DevStats init{};
+    init.min_sdf = 0xffffffffu;
+    init.min_iters = 0xffffffffu;
+    *c->h_stats = init;
+    CU(c, cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(DevStats), cudaMemcpyHostToDevice, stream));
+    int launches = 0;
+    CU(c, cudaEventRecord(c->ev0, stream));
+    if (P.n_tiles > 0) {
+        int e = (c->flags & RM_F_VALIDATE_FP64) ? launch_render_val(P, c->n_sms, stream) : launch_render_fast(P, c->n_sms, stream);
+        if (e != 0) return fail(c, RM_ERR_CUDA, "render launch: %s", cudaGetErrorString((cudaError_t)e));
+        launches = 1;
+    }
+    CU(c, cudaEventRecord(c->ev1, stream));
+    CU(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, stream));
+    CU(c, cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+
+    const DevStats& s = *c->h_stats;
+    rm_stats_t& L = c->last;
+    std::memset(&L, 0, sizeof(L));
+    L.n_pixels = (uint64_t)rq->width * (uint64_t)bandH;
+    L.sum_sdf = s.sum_sdf;
+    L.sum_iters = s.sum_iters;
+    L.max_sdf = s.max_sdf;
+    L.min_sdf = s.min_sdf;
+    L.max_iters = s.max_iters;
+    L.min_iters = s.min_iters;
+    L.sum_sdf_full = s.sum_sdf_full;
+    L.sum_iters_full = s.sum_iters_full;
+    L.evals_by_type[0] = s.evals_sphere;
+    L.evals_by_type[1] = s.evals_box;
+    L.evals_by_type[2] = s.evals_torus;
+    L.n_hit = s.n_hit;
+    L.kernel_ms = ms;
+    L.n_launches = launches;
+    L.device = c->device;
+    L.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return RM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rm_abi_version(void) { return RM_ABI_VERSION; }
+
+int rm_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        return RM_ERR_CUDA;
+    }
+    return n;
+}
+
+int rm_create(rm_ctx** out, int device, unsigned flags) {
+    if (!out) return fail(nullptr, RM_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(nullptr, RM_ERR_CUDA, "no CUDA device available (%s); librm_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(nullptr, RM_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    rm_ctx* c = new (std::nothrow) rm_ctx();
+    if (!c) return fail(nullptr, RM_ERR_NOMEM, "out of memory");
+    c->device = device;
+    c->flags = flags;
+#define CUC(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e2 = (call);                                                                         \
+        if (e2 != cudaSuccess) {                                                                         \
+            int rc_ = fail(nullptr, RM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2));               \
+            rm_destroy(c);                                                                               \
+            return rc_;                                                                                  \
+        }                                                                                                \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    c->n_sms = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev0));
+    CUC(cudaEventCreate(&c->ev1));
+    CUC(cudaMalloc((void**)&c->d_stats, sizeof(DevStats)));
+    CUC(cudaMallocHost((void**)&c->h_stats, sizeof(DevStats)));
+#undef CUC
+    *out = c;
+    return RM_OK;
+}
+
+void rm_destroy(rm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    for (void* p : c->user_allocs) cudaFree(p);
+    if (c->d_frame.p) cudaFree(c->d_frame.p);
+    if (c->h_frame.p) cudaFreeHost(c->h_frame.p);
+    if (c->d_stats) cudaFree(c->d_stats);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* rm_last_error(rm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int rm_build_bvh(int32_t n, const uint8_t* type, const float* w2l, const double* params, unsigned flags, rm_bvh_node* nodes,
+                 int32_t* n_nodes, int32_t* leaf, int32_t* n_leaf) {
+    if (n < 0 || (n > 0 && (!type || !w2l || !params)) || !n_nodes || !n_leaf) return RM_ERR_ARG;
+    std::vector<PrimGeom> geom;
+    compute_prim_geometry(n, type, w2l, params, flags, geom);
+    std::vector<rm_bvh_node> nn;
+    std::vector<int32_t> lp;
+    build_bvh(geom, nn, lp);
+    if (nodes) {
+        if (*n_nodes < (int32_t)nn.size() || *n_leaf < (int32_t)lp.size() || (!leaf && !lp.empty())) return RM_ERR_ARG;
+        std::memcpy(nodes, nn.data(), nn.size() * sizeof(rm_bvh_node));
+        if (!lp.empty()) std::memcpy(leaf, lp.data(), lp.size() * sizeof(int32_t));
+    }
+    *n_nodes = (int32_t)nn.size();
+    *n_leaf = (int32_t)lp.size();
+    return RM_OK;
+}
+
+int rm_build_octree(int32_t n, const uint8_t* type, const float* w2l, const double* params, unsigned flags,
+                    rm_octree_node* nodes, int32_t* n_nodes, int32_t* leaf, int32_t* n_leaf) {
+    if (n < 0 || (n > 0 && (!type || !w2l || !params)) || !n_nodes || !n_leaf) return RM_ERR_ARG;
+    std::vector<PrimGeom> geom;
+    compute_prim_geometry(n, type, w2l, params, flags, geom);
+    std::vector<rm_octree_node> nn;
+    std::vector<int32_t> lp;
+    build_octree(geom, nn, lp);
+    if (nodes) {
+        if (*n_nodes < (int32_t)nn.size() || *n_leaf < (int32_t)lp.size() || (!leaf && !lp.empty())) return RM_ERR_ARG;
+        std::memcpy(nodes, nn.data(), nn.size() * sizeof(rm_octree_node));
+        if (!lp.empty()) std::memcpy(leaf, lp.data(), lp.size() * sizeof(int32_t));
+    }
+    *n_nodes = (int32_t)nn.size();
+    *n_leaf = (int32_t)lp.size();
+    return RM_OK;
+}
+
+int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!s) return fail(c, RM_ERR_ARG, "scene is null");
+    const int32_t n = s->n_prims;
+    if (n < 0 || (n > 0 && (!s->type || !s->world_to_local || !s->params))) return fail(c, RM_ERR_ARG, "bad primitive arrays");
+    if (s->accel_kind < RM_ACCEL_NONE || s->accel_kind > RM_ACCEL_BVH) return fail(c, RM_ERR_ARG, "bad accel_kind %d", s->accel_kind);
+    // Only sphere / box / torus with hard-min union are on the path: reject the rest loudly.
+    bool allTS = n > 0;
+    uint32_t hist[3] = {0, 0, 0};
+    for (int32_t i = 0; i < n; ++i) {
+        if (s->type[i] > RM_PRIM_TORUS)
+            return fail(c, RM_ERR_UNSUPPORTED_PRIMITIVE, "primitive %d has type %d: only sphere/box/torus are supported (no CPU fallback)", i, (int)s->type[i]);
+        hist[s->type[i]]++;
+        const float* m = s->world_to_local + 16 * (size_t)i;
+        for (int k = 0; k < 16; ++k)
+            if (!std::isfinite(m[k])) return fail(c, RM_ERR_ARG, "primitive %d: non-finite transform", i);
+        if (!(c->flags & RM_F_VALIDATE_FP64) && !is_affine(m))
+            return fail(c, RM_ERR_UNSUPPORTED_PRIMITIVE, "primitive %d: projective world->local is only supported by the validation build", i);
+        allTS = allTS && is_translation_sphere(s->type[i], m);
+    }
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    free_scene(c);
+
+    DevScene ds{};
+    ds.n_prims = n;
+    ds.accel_kind = s->accel_kind;
+    ds.prim_kind = allTS ? PK_TSPHERE : PK_GENERAL;
+    std::memcpy(ds.type_hist, hist, sizeof(hist));
+    int rc;
+    if ((rc = upload(c, s->type, (size_t)n, &ds.type))) return rc;
+    if ((rc = upload(c, s->world_to_local, (size_t)n * 16, &ds.w2l))) return rc;
+    if ((rc = upload(c, s->params, (size_t)n * 4, &ds.params))) return rc;
+
+    // fast-path packed records
+    std::vector<float4> rec;
+    if (allTS) {
+        rec.resize((size_t)n);
+        for (int32_t i = 0; i < n; ++i) {
+            const float* m = s->world_to_local + 16 * (size_t)i;
+            rec[(size_t)i] = make_float4(m[12], m[13], m[14], (float)s->params[4 * (size_t)i]);
+        }
+    } else {
+        rec.resize((size_t)n * 4);
+        for (int32_t i = 0; i < n; ++i) {
+            const float* m = s->world_to_local + 16 * (size_t)i;
+            const double* q = s->params + 4 * (size_t)i;
+            rec[4 * (size_t)i + 0] = make_float4(m[0], m[4], m[8], m[12]);
+            rec[4 * (size_t)i + 1] = make_float4(m[1], m[5], m[9], m[13]);
+            rec[4 * (size_t)i + 2] = make_float4(m[2], m[6], m[10], m[14]);
+            int t = s->type[i];
+            float tf;
+            std::memcpy(&tf, &t, sizeof(tf));
+            rec[4 * (size_t)i + 3] = make_float4((float)q[0], (float)q[1], (float)q[2], tf);
+        }
+    }
+    if ((rc = upload(c, rec.data(), rec.size(), &ds.rec))) return rc;
+
+    // acceleration structure: host-supplied or built natively
+    std::vector<rm_bvh_node> bvh;
+    std::vector<rm_octree_node> oct;
+    std::vector<int32_t> leaf;
+    if (s->accel_kind != RM_ACCEL_NONE) {
+        if (s->nodes) {
+            if (s->n_nodes <= 0 || s->n_leaf_prims < 0 || (s->n_leaf_prims > 0 && !s->leaf_prim_index))
+                return fail(c, RM_ERR_ARG, "bad acceleration-structure arrays");
+            leaf.assign(s->leaf_prim_index, s->leaf_prim_index + s->n_leaf_prims);
+            if (s->accel_kind == RM_ACCEL_BVH) bvh.assign((const rm_bvh_node*)s->nodes, (const rm_bvh_node*)s->nodes + s->n_nodes);
+            else oct.assign((const rm_octree_node*)s->nodes, (const rm_octree_node*)s->nodes + s->n_nodes);
+        } else {
+            std::vector<PrimGeom> geom;
+            compute_prim_geometry(n, s->type, s->world_to_local, s->params, c->flags, geom);
+            if (s->accel_kind == RM_ACCEL_BVH) build_bvh(geom, bvh, leaf);
+            else build_octree(geom, oct, leaf);
+        }
+        // structural validation (indices in range) so a bad host structure cannot fault the GPU
+        const int32_t nn = (int32_t)(s->accel_kind == RM_ACCEL_BVH ? bvh.size() : oct.size());
+        for (int32_t v : leaf)
+            if (v < 0 || v >= n) return fail(c, RM_ERR_ARG, "leaf primitive index %d out of range", v);
+        if (s->accel_kind == RM_ACCEL_BVH) {
+            for (const rm_bvh_node& nd : bvh) {
+                if (nd.left >= nn || nd.right >= nn || nd.left < -1 || nd.right < -1) return fail(c, RM_ERR_ARG, "BVH child index out of range");
+                if (nd.prim_count < 0 || nd.prim_first < 0 || (size_t)nd.prim_first + (size_t)nd.prim_count > leaf.size())
+                    return fail(c, RM_ERR_ARG, "BVH leaf range out of bounds");
+            }
+        } else {
+            for (const rm_octree_node& nd : oct) {
+                if (nd.first_child >= 0 && nd.first_child + 8 > nn) return fail(c, RM_ERR_ARG, "octree child index out of range");
+                if (nd.prim_count < 0 || nd.prim_first < 0 || (size_t)nd.prim_first + (size_t)nd.prim_count > leaf.size())
+                    return fail(c, RM_ERR_ARG, "octree leaf range out of bounds");
+            }
+        }
+        ds.n_nodes = nn;
+        if ((rc = upload(c, bvh.data(), bvh.size(), &ds.bvh))) return rc;
+        if ((rc = upload(c, oct.data(), oct.size(), &ds.oct))) return rc;
+        if ((rc = upload(c, leaf.data(), leaf.size(), &ds.leaf_prims))) return rc;
+    }
+    CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+    c->scene = ds;
+    c->has_scene = true;
+    return RM_OK;
+}
+
+int rm_render_device(rm_ctx* c, const rm_request* rq, const rm_result* out, void* cuda_stream) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return render_device_locked(c, rq, out, cuda_stream ? (cudaStream_t)cuda_stream : c->stream);
+}
+
+int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto w0 = std::chrono::steady_clock::now();
+    int rc = validate_request(c, rq);
+    if (rc) return rc;
+    if (!out || !out->depth || !out->normal || !out->sdf_eval || !out->iters)
+        return fail(c, RM_ERR_ARG, "result planes depth/normal/sdf_eval/iters are required");
+    const int bandH = rq->y_end > rq->y_start ? rq->y_end - rq->y_start : 0;
+    const size_t np = (size_t)rq->width * (size_t)bandH;
+    CU(c, cudaSetDevice(c->device));
+    // plane layout inside one staging block (16-byte aligned sections)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const bool wantRgba = rq->shader != RM_SHADER_NONE && out->rgba, wantRgba2 = rq->shader_analytics != RM_SHADER_NONE && out->rgba_analytics;
+    size_t off = 0;
+    const size_t oDepth = off; off += al(np);
+    const size_t oNormal = off; off += al(3 * np);
+    const size_t oSdf = off; off += al(2 * np);
+    const size_t oIters = off; off += al(2 * np);
+    const size_t oRgba = off; off += wantRgba ? al(4 * np) : 0;
+    const size_t oRgba2 = off; off += wantRgba2 ? al(4 * np) : 0;
+    const size_t oDf = off; off += out->depth_f32 ? al(4 * np) : 0;
+    const size_t oSu = off; off += out->sdf_eval_u32 ? al(4 * np) : 0;
+    const size_t total = off;
+    if ((rc = ensure(c, c->d_frame, total + 256, false))) return rc;
+    if ((rc = ensure(c, c->h_frame, total + 256, true))) return rc;
+    uint8_t* d = (uint8_t*)c->d_frame.p;
+    rm_result dev{};
+    dev.depth = d + oDepth;
+    dev.normal = d + oNormal;
+    dev.sdf_eval = (uint16_t*)(d + oSdf);
+    dev.iters = (uint16_t*)(d + oIters);
+    dev.rgba = wantRgba ? d + oRgba : nullptr;
+    dev.rgba_analytics = wantRgba2 ? d + oRgba2 : nullptr;
+    dev.depth_f32 = out->depth_f32 ? (float*)(d + oDf) : nullptr;
+    dev.sdf_eval_u32 = out->sdf_eval_u32 ? (uint32_t*)(d + oSu) : nullptr;
+    rc = render_device_locked(c, rq, &dev, c->stream);
+    if (rc) return rc;
+    if (np > 0) {
+        // one D2H of the whole staging block into pinned memory, then scatter to the caller's planes
+        CU(c, cudaMemcpyAsync(c->h_frame.p, d, total, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        const uint8_t* h = (const uint8_t*)c->h_frame.p;
+        std::memcpy(out->depth, h + oDepth, np);
+        std::memcpy(out->normal, h + oNormal, 3 * np);
+        std::memcpy(out->sdf_eval, h + oSdf, 2 * np);
+        std::memcpy(out->iters, h + oIters, 2 * np);
+        if (wantRgba) std::memcpy(out->rgba, h + oRgba, 4 * np);
+        if (wantRgba2) std::memcpy(out->rgba_analytics, h + oRgba2, 4 * np);
+        if (out->depth_f32) std::memcpy(out->depth_f32, h + oDf, 4 * np);
+        if (out->sdf_eval_u32) std::memcpy(out->sdf_eval_u32, h + oSu, 4 * np);
+    }
+    c->last.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return RM_OK;
+}
+
+int rm_stats(rm_ctx* c, rm_stats_t* out) {
+    if (!c || !out) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = c->last;
+    return RM_OK;
+}
+
+int rm_shade(rm_ctx* c, int32_t shader, uint8_t* rgba, const uint8_t* depth, const uint8_t* normal, const uint16_t* sdf,
+             const uint16_t* iters, int32_t width, int32_t height) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!rgba || !depth || !normal || !sdf || !iters || width <= 0 || height <= 0) return fail(c, RM_ERR_ARG, "bad shade arguments");
+    if (shader < RM_SHADER_NORMAL || shader > RM_SHADER_ITERATION_HEATMAP) return fail(c, RM_ERR_ARG, "bad shader %d", shader);
+    CU(c, cudaSetDevice(c->device));
+    const size_t np = (size_t)width * height;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oD = 0, oN = al(np), oS = oN + al(3 * np), oI = oS + al(2 * np), oR = oI + al(2 * np), total = oR + al(4 * np);
+    int rc;
+    if ((rc = ensure(c, c->d_frame, total, false))) return rc;
+    uint8_t* d = (uint8_t*)c->d_frame.p;
+    CU(c, cudaMemcpyAsync(d + oD, depth, np, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + oN, normal, 3 * np, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + oS, sdf, 2 * np, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + oI, iters, 2 * np, cudaMemcpyHostToDevice, c->stream));
+    ShadeParams sp{};
+    sp.shader = shader;
+    sp.n_pixels = (int32_t)np;
+    sp.depth = d + oD;
+    sp.normal = d + oN;
+    sp.sdf = (const uint16_t*)(d + oS);
+    sp.iters = (const uint16_t*)(d + oI);
+    sp.rgba = d + oR;
+    int e = (c->flags & RM_F_VALIDATE_FP64) ? launch_shade_val(sp, c->stream) : launch_shade_fast(sp, c->stream);
+    if (e != 0) return fail(c, RM_ERR_CUDA, "shade launch: %s", cudaGetErrorString((cudaError_t)e));
+    CU(c, cudaMemcpyAsync(rgba, d + oR, 4 * np, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RM_OK;
+}
+
+int rm_alloc(rm_ctx* c, size_t bytes, void** dev_ptr) {
+    if (!c || !dev_ptr) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU(c, cudaMalloc(&p, bytes ? bytes : 1));
+    c->user_allocs.push_back(p);
+    *dev_ptr = p;
+    return RM_OK;
+}
+int rm_free(rm_ctx* c, void* dev_ptr) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (size_t i = 0; i < c->user_allocs.size(); ++i)
+        if (c->user_allocs[i] == dev_ptr) {
+            CU(c, cudaSetDevice(c->device));
+            CU(c, cudaFree(dev_ptr));
+            c->user_allocs.erase(c->user_allocs.begin() + (long)i);
+            return RM_OK;
+        }
+    return fail(c, RM_ERR_ARG, "pointer was not allocated by rm_alloc on this context");
+}
+int rm_ipc_export(rm_ctx* c, void* dev_ptr, uint8_t handle[64]) {
+    if (!c || !dev_ptr || !handle) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(c, cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle, &h, 64);
+    return RM_OK;
+}
+int rm_ipc_open(rm_ctx* c, const uint8_t handle[64], void** dev_ptr) {
+    if (!c || !dev_ptr || !handle) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(c, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RM_OK;
+}
+int rm_ipc_close(rm_ctx* c, void* dev_ptr) {
+    if (!c || !dev_ptr) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaIpcCloseMemHandle(dev_ptr));
+    return RM_OK;
+}
+int rm_memcpy_d2h(rm_ctx* c, void* host, const void* dev, size_t bytes) {
+    if (!c || (!host && bytes) || (!dev && bytes)) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RM_OK;
+}
+int rm_memcpy_h2d(rm_ctx* c, void* dev, const void* host, size_t bytes) {
+    if (!c || (!host && bytes) || (!dev && bytes)) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return RM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// rm_build.cpp — native host builders for the flattened BVH / octree (compiled -ffp-contract=off).
+//
+// Result-identical to the reference's builders but with sane complexity: the reference re-inverts
+// every primitive's mat4 inside its sort comparator and per tree level (bvh.ts:66-70,84-85;
+// boundingBox.ts:133-154) and rebuilds per job per frame (raymarchWorker.ts:37-38).  Here the world
+// position and padded box of every primitive are computed once; the rest is index shuffling.
+//   BVH    : src/acceleration_structures/bvh.ts:29-92     (median split, stable sort, depth<=20, leaf<=2)
+//   Octree : src/acceleration_structures/octree.ts:36-118 (fixed +-10 root from scene.ts:81-85, z-y-x
+//            children, closed-interval assignment, depth<=6, leaf<=4) and :149-191 (minDistance)
+// Arithmetic model: JS doubles, f32 stores.  This is product code and does
+// not share sources with oracle/.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "rm_host.h"
+
+namespace rm {
+
+static inline float f32(double x) { return (float)x; }
+
+// V8 Math.hypot (three arguments).
+static double hypot3(double a, double b, double c) {
+    double v[3] = {a, b, c}, av[3] = {0, 0, 0};
+    bool nan = false;
+    double mx = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (std::isnan(v[i])) nan = true;
+        else {
+            av[i] = std::fabs(v[i]);
+            if (av[i] > mx) mx = av[i];
+        }
+    }
+    if (mx == std::numeric_limits<double>::infinity()) return mx;
+    if (nan) return std::numeric_limits<double>::quiet_NaN();
+    if (mx == 0) return 0;
+    double sum = 0, comp = 0;
+    for (int i = 0; i < 3; ++i) {
+        double n = av[i] / mx;
+        double summand = (n * n) - comp;
+        double prelim = sum + summand;
+        comp = (prelim - sum) - summand;
+        sum = prelim;
+    }
+    return std::sqrt(sum) * mx;
+}
+
+// gl-matrix mat4.invert on f32 storage (double arithmetic, f32 stores).  false when det == 0.
+static bool mat4_invert(const float* a, float* out) {
+    double a00 = a[0], a01 = a[1], a02 = a[2], a03 = a[3], a10 = a[4], a11 = a[5], a12 = a[6], a13 = a[7];
+    double a20 = a[8], a21 = a[9], a22 = a[10], a23 = a[11], a30 = a[12], a31 = a[13], a32 = a[14], a33 = a[15];
+    double b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10;
+    double b03 = a01 * a12 - a02 * a11, b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12;
+    double b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30, b08 = a20 * a33 - a23 * a30;
+    double b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
+    double det = b00 * b11 - b01 * b10 + b02 * b09 + b03 * b08 - b04 * b07 + b05 * b06;
+    if (det == 0.0 || std::isnan(det)) return false;
+    det = 1.0 / det;
+    out[0] = f32((a11 * b11 - a12 * b10 + a13 * b09) * det);
+    out[1] = f32((a02 * b10 - a01 * b11 - a03 * b09) * det);
+    out[2] = f32((a31 * b05 - a32 * b04 + a33 * b03) * det);
+    out[3] = f32((a22 * b04 - a21 * b05 - a23 * b03) * det);
+    out[4] = f32((a12 * b08 - a10 * b11 - a13 * b07) * det);
+    out[5] = f32((a00 * b11 - a02 * b08 + a03 * b07) * det);
+    out[6] = f32((a32 * b02 - a30 * b05 - a33 * b01) * det);
+    out[7] = f32((a20 * b05 - a22 * b02 + a23 * b01) * det);
+    out[8] = f32((a10 * b10 - a11 * b08 + a13 * b06) * det);
+    out[9] = f32((a01 * b08 - a00 * b10 - a03 * b06) * det);
+    out[10] = f32((a30 * b04 - a31 * b02 + a33 * b00) * det);
+    out[11] = f32((a21 * b02 - a20 * b04 - a23 * b00) * det);
+    out[12] = f32((a11 * b07 - a10 * b09 - a12 * b06) * det);
+    out[13] = f32((a00 * b09 - a01 * b07 + a02 * b06) * det);
+    out[14] = f32((a31 * b01 - a30 * b03 - a32 * b00) * det);
+    out[15] = f32((a20 * b03 - a21 * b01 + a22 * b00) * det);
+    return true;
+}
+
+void compute_prim_geometry(int32_t n, const uint8_t* type, const float* w2l, const double* params, unsigned flags,
+                           std::vector<PrimGeom>& out) {
+    out.resize((size_t)n);
+    const bool lengthSqrt = (flags & RM_F_LENGTH_SQRT) != 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const float* m = w2l + 16 * (size_t)i;
+        float inv[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // mat4.create(); untouched if singular
+        bool ok = mat4_invert(m, inv);
+        PrimGeom& g = out[(size_t)i];
+        // Primitive.getWorldPosition (primitive.ts:20-30)
+        g.world[0] = inv[12];
+        g.world[1] = inv[13];
+        g.world[2] = inv[14];
+        // getLocalBoundingRadius (sphere.ts:16, box.ts:32-34, torus.ts:27-29)
+        const double* q = params + 4 * (size_t)i;
+        double localRadius;
+        if (type[i] == RM_PRIM_SPHERE) localRadius = q[0];
+        else if (type[i] == RM_PRIM_BOX) {
+            double hx = (double)f32(q[0]), hy = (double)f32(q[1]), hz = (double)f32(q[2]);
+            localRadius = lengthSqrt ? std::sqrt(hx * hx + hy * hy + hz * hz) : hypot3(hx, hy, hz);
+        } else localRadius = q[0] + q[1];
+        // BoundingBox.fromPrimitive (boundingBox.ts:133-154)
+        const float* s = ok ? inv : m;
+        double scaleX = hypot3(s[0], s[1], s[2]);
+        double scaleY = hypot3(s[4], s[5], s[6]);
+        double scaleZ = hypot3(s[8], s[9], s[10]);
+        double maxScale = std::max(std::max(scaleX, scaleY), scaleZ);
+        if (std::isnan(scaleX) || std::isnan(scaleY) || std::isnan(scaleZ)) maxScale = std::numeric_limits<double>::quiet_NaN();
+        double r = localRadius * maxScale * 1.5;
+        for (int k = 0; k < 3; ++k) {
+            g.bmin[k] = f32((double)g.world[k] - r);
+            g.bmax[k] = f32((double)g.world[k] + r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ BVH
+namespace {
+struct BvhBuilder {
+    const std::vector<PrimGeom>& geom;
+    std::vector<rm_bvh_node>& nodes;
+    std::vector<int32_t>& leafPrims;
+    const int maxDepth = 20, maxPrimsPerNode = 2;  // bvh.ts:32-33
+
+    void bounds_of(const std::vector<int32_t>& prims, float* bmin, float* bmax) const {  // computeBounds
+        if (prims.empty()) {
+            for (int k = 0; k < 3; ++k) bmin[k] = bmax[k] = 0.f;
+            return;
+        }
+        for (int k = 0; k < 3; ++k) {
+            bmin[k] = geom[(size_t)prims[0]].bmin[k];
+            bmax[k] = geom[(size_t)prims[0]].bmax[k];
+        }
+        for (size_t i = 1; i < prims.size(); ++i)
+            for (int k = 0; k < 3; ++k) {
+                bmin[k] = std::min(bmin[k], geom[(size_t)prims[i]].bmin[k]);
+                bmax[k] = std::max(bmax[k], geom[(size_t)prims[i]].bmax[k]);
+            }
+    }
+    int32_t build(std::vector<int32_t>& prims, const float* bmin, const float* bmax, int depth) {
+        int32_t me = (int32_t)nodes.size();
+        nodes.emplace_back();
+        {
+            rm_bvh_node& nd = nodes[(size_t)me];
+            for (int k = 0; k < 3; ++k) {
+                nd.bmin[k] = bmin[k];
+                nd.bmax[k] = bmax[k];
+            }
+            nd.left = nd.right = -1;
+            nd.prim_first = (int32_t)leafPrims.size();
+            nd.prim_count = 0;
+        }
+        auto make_leaf = [&]() {
+            nodes[(size_t)me].prim_count = (int32_t)prims.size();
+            leafPrims.insert(leafPrims.end(), prims.begin(), prims.end());
+        };
+        if (depth >= maxDepth || (int)prims.size() <= maxPrimsPerNode) {
+            make_leaf();
+            return me;
+        }
+        // longest axis of the f32 size vector (bvh.ts:57-63)
+        float size[3];
+        for (int k = 0; k < 3; ++k) size[k] = f32((double)bmax[k] - (double)bmin[k]);
+        int axis = 0;
+        if (size[1] > size[0]) axis = 1;
+        if (size[2] > size[axis]) axis = 2;
+        std::vector<int32_t> sorted(prims);
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int32_t a, int32_t b) {
+            return geom[(size_t)a].world[axis] < geom[(size_t)b].world[axis];
+        });
+        size_t mid = sorted.size() / 2;
+        std::vector<int32_t> leftStuff(sorted.begin(), sorted.begin() + (long)mid);
+        std::vector<int32_t> rightStuff(sorted.begin() + (long)mid, sorted.end());
+        if (leftStuff.empty() || rightStuff.empty()) {
+            make_leaf();
+            return me;
+        }
+        float lmin[3], lmax[3], rmin[3], rmax[3];
+        bounds_of(leftStuff, lmin, lmax);
+        bounds_of(rightStuff, rmin, rmax);
+        std::vector<int32_t>().swap(sorted);
+        int32_t l = build(leftStuff, lmin, lmax, depth + 1);
+        nodes[(size_t)me].left = l;
+        int32_t r = build(rightStuff, rmin, rmax, depth + 1);
+        nodes[(size_t)me].right = r;
+        return me;
+    }
+};
+}  // namespace
+
+void build_bvh(const std::vector<PrimGeom>& geom, std::vector<rm_bvh_node>& nodes, std::vector<int32_t>& leafPrims) {
+    nodes.clear();
+    leafPrims.clear();
+    std::vector<int32_t> all(geom.size());
+    for (size_t i = 0; i < geom.size(); ++i) all[i] = (int32_t)i;
+    BvhBuilder b{geom, nodes, leafPrims};
+    float bmin[3], bmax[3];
+    b.bounds_of(all, bmin, bmax);
+    b.build(all, bmin, bmax, 0);
+}
+
+// --------------------------------------------------------------------------------------- octree
+static double box_distance(const float* amin, const float* amax, const float* bmin, const float* bmax) {  // distanceToBox
+    double d[3];
+    for (int k = 0; k < 3; ++k) {
+        d[k] = 0;
+        if (amax[k] < bmin[k]) d[k] = (double)bmin[k] - (double)amax[k];
+        else if (bmax[k] < amin[k]) d[k] = (double)amin[k] - (double)bmax[k];
+    }
+    return hypot3(d[0], d[1], d[2]);
+}
+
+void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>& nodes, std::vector<int32_t>& leafPrims) {
+    const int maxDepth = 6, maxPrimsPerNode = 4;  // octree.ts:39-40
+    nodes.clear();
+    leafPrims.clear();
+    struct Pending {
+        int32_t node;
+        std::vector<int32_t> prims;
+    };
+    std::deque<Pending> q;
+    nodes.emplace_back();
+    {
+        rm_octree_node& root = nodes[0];
+        std::memset(&root, 0, sizeof(root));
+        for (int k = 0; k < 3; ++k) {  // scene.ts:81-85
+            root.bmin[k] = -10.f;
+            root.bmax[k] = 10.f;
+        }
+        root.level = 0;
+        std::vector<int32_t> all(geom.size());
+        for (size_t i = 0; i < geom.size(); ++i) all[i] = (int32_t)i;
+        q.push_back({0, std::move(all)});
+    }
+    while (!q.empty()) {
+        Pending cur = std::move(q.front());
+        q.pop_front();
+        const int32_t me = cur.node;
+        const int depth = nodes[(size_t)me].level;
+        nodes[(size_t)me].prim_first = (int32_t)leafPrims.size();
+        nodes[(size_t)me].prim_count = 0;
+        nodes[(size_t)me].first_child = -1;
+        nodes[(size_t)me].is_empty = 1;
+        nodes[(size_t)me].min_distance = 0;
+        if (depth >= maxDepth || (int)cur.prims.size() <= maxPrimsPerNode) {
+            nodes[(size_t)me].prim_count = (int32_t)cur.prims.size();
+            leafPrims.insert(leafPrims.end(), cur.prims.begin(), cur.prims.end());
+            continue;
+        }
+        float bmin[3], bmax[3], c[3];
+        for (int k = 0; k < 3; ++k) {
+            bmin[k] = nodes[(size_t)me].bmin[k];
+            bmax[k] = nodes[(size_t)me].bmax[k];
+            c[k] = f32(((double)bmin[k] + (double)bmax[k]) / 2);  // BoundingBox.center (boundingBox.ts:108-114)
+        }
+        const int32_t first = (int32_t)nodes.size();
+        nodes[(size_t)me].first_child = first;
+        nodes.resize(nodes.size() + 8);
+        std::vector<int32_t> childPrims[8];
+        for (int i = 0; i < 8; ++i) {
+            rm_octree_node& ch = nodes[(size_t)(first + i)];
+            std::memset(&ch, 0, sizeof(ch));
+            const int xs = i & 1, ys = (i >> 1) & 1, zs = (i >> 2) & 1;  // z,y,x nesting (octree.ts:69-88)
+            ch.bmin[0] = xs ? c[0] : bmin[0];
+            ch.bmax[0] = xs ? bmax[0] : c[0];
+            ch.bmin[1] = ys ? c[1] : bmin[1];
+            ch.bmax[1] = ys ? bmax[1] : c[1];
+            ch.bmin[2] = zs ? c[2] : bmin[2];
+            ch.bmax[2] = zs ? bmax[2] : c[2];
+            ch.level = (uint8_t)(depth + 1);
+            ch.first_child = -1;
+            ch.is_empty = 1;
+        }
+        for (int32_t p : cur.prims) {
+            const PrimGeom& g = geom[(size_t)p];
+            for (int i = 0; i < 8; ++i) {
+                const rm_octree_node& ch = nodes[(size_t)(first + i)];
+                bool hit = ch.bmin[0] <= g.bmax[0] && ch.bmax[0] >= g.bmin[0] && ch.bmin[1] <= g.bmax[1] &&
+                           ch.bmax[1] >= g.bmin[1] && ch.bmin[2] <= g.bmax[2] && ch.bmax[2] >= g.bmin[2];
+                if (hit) childPrims[i].push_back(p);
+            }
+        }
+        for (int i = 0; i < 8; ++i) q.push_back({first + i, std::move(childPrims[i])});
+    }
+    // computeMinDistances (octree.ts:149-191): bottom-up "subtree has primitives", then the
+    // conservative distance of every empty node to the nearest primitive box.
+    const size_t nn = nodes.size();
+    std::vector<uint8_t> hasPrims(nn, 0);
+    for (size_t i = nn; i-- > 0;) {
+        if (nodes[i].first_child < 0) hasPrims[i] = nodes[i].prim_count > 0;
+        else {
+            uint8_t any = 0;
+            for (int k = 0; k < 8; ++k) any |= hasPrims[(size_t)nodes[i].first_child + k];
+            hasPrims[i] = any;
+        }
+        nodes[i].is_empty = hasPrims[i] ? 0 : 1;
+    }
+    std::vector<size_t> empties;
+    for (size_t i = 0; i < nn; ++i)
+        if (nodes[i].is_empty) empties.push_back(i);
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t e = lo; e < hi; ++e) {
+            rm_octree_node& nd = nodes[empties[e]];
+            double minD = std::numeric_limits<double>::infinity();
+            for (const PrimGeom& g : geom) {
+                double d = box_distance(nd.bmin, nd.bmax, g.bmin, g.bmax);
+                if (d < minD) minD = d;
+            }
+            nd.min_distance = (minD != std::numeric_limits<double>::infinity()) ? std::max(0.0, minD) : 0.0;
+        }
+    };
+    const size_t total = empties.size() * geom.size();
+    unsigned nt = total > (1u << 22) ? std::max(1u, std::thread::hardware_concurrency()) : 1u;
+    if (nt <= 1) {
+        work(0, empties.size());
+    } else {
+        std::vector<std::thread> th;
+        size_t per = (empties.size() + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            size_t lo = std::min(empties.size(), t * per), hi = std::min(empties.size(), lo + per);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+    }
+}
+
+}  // namespace rm

@@ -1,0 +1,55 @@
+// rm_launch.cuh — host-side launcher shared by the two kernel translation units.
+// Included with RM_NUM (numeric policy) and RM_SUFFIX (val / fast) defined.
+#pragma once
+#include <algorithm>
+
+#include "rm_device.cuh"
+
+namespace rm {
+
+template <class NP, int ACCEL, int PK>
+static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
+    auto kern = render_kernel<NP, ACCEL, PK>;
+    static int blocksPerSM = 0;  // per instantiation
+    if (blocksPerSM == 0) {
+        int b = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, 128, 0);
+        if (e != cudaSuccess) return (int)e;
+        blocksPerSM = std::max(b, 1);
+    }
+    // persistent grid: a multiple of the SM count, never more warps than there are tiles
+    long long warpsWanted = p.n_tiles;
+    int maxBlocks = n_sms * blocksPerSM;
+    int blocks = (int)std::min<long long>(maxBlocks, (warpsWanted + 3) / 4);
+    if (blocks < 1) blocks = 1;
+    kern<<<blocks, 128, 0, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <class NP>
+static int launch_render_t(const RenderParams& p, int n_sms, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int ak = p.scene.accel_kind;
+    const int pk = NP::kExact ? PK_GENERAL : p.scene.prim_kind;
+    if (pk == PK_TSPHERE) {
+        if constexpr (!NP::kExact) {
+            if (ak == RM_ACCEL_NONE) return launch_one<NP, RM_ACCEL_NONE, PK_TSPHERE>(p, n_sms, stream);
+            if (ak == RM_ACCEL_OCTREE) return launch_one<NP, RM_ACCEL_OCTREE, PK_TSPHERE>(p, n_sms, stream);
+            return launch_one<NP, RM_ACCEL_BVH, PK_TSPHERE>(p, n_sms, stream);
+        }
+    }
+    if (ak == RM_ACCEL_NONE) return launch_one<NP, RM_ACCEL_NONE, PK_GENERAL>(p, n_sms, stream);
+    if (ak == RM_ACCEL_OCTREE) return launch_one<NP, RM_ACCEL_OCTREE, PK_GENERAL>(p, n_sms, stream);
+    return launch_one<NP, RM_ACCEL_BVH, PK_GENERAL>(p, n_sms, stream);
+}
+
+template <class NP>
+static int launch_shade_t(const ShadeParams& p, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (p.n_pixels <= 0) return 0;
+    int blocks = (p.n_pixels + 255) / 256;
+    shade_kernel<NP><<<blocks, 256, 0, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace rm

@@ -1,0 +1,90 @@
+// rm_types.h — structures shared between the host side of librm_b200.so and its sm_100a kernels.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/rm.h"
+
+namespace rm {
+
+constexpr int kTileW = 8;   // image tile handed to a warp by the atomic work queue: 8 x 4 = 32 pixels
+constexpr int kTileH = 4;
+constexpr int kMaxStepsSphere = 100;  // sphereTracer.ts:3, adaptiveStepV2.ts:3, adaptiveStepV3.ts:3
+constexpr int kMaxStepsFixed = 200;   // fixedStep.ts:3, adaptiveStep.ts:3
+constexpr int kOctreeMaxDepth = 6;    // octree.ts:39
+constexpr int kBvhStack = 64;         // BVH depth <= 20 (bvh.ts:32): DFS stack needs <= 2*20+1 entries
+
+// Primitive-set specialisation chosen at upload time.
+enum PrimKind {
+    PK_GENERAL = 0,  // any mix of sphere/box/torus with a general affine world->local
+    PK_TSPHERE = 1   // every primitive is a sphere whose world->local is a pure translation
+};
+
+// Device-resident scene (all pointers are device pointers).
+struct DevScene {
+    int32_t n_prims;
+    int32_t accel_kind;
+    int32_t prim_kind;
+    int32_t n_nodes;
+    // exact inputs (validation kernels read these)
+    const uint8_t* type;   // [n]
+    const float* w2l;      // [16n] column-major
+    const double* params;  // [4n]
+    // fast-path packed records
+    const float4* rec;   // PK_GENERAL: 4 x float4 per prim (3 affine rows + params/type); PK_TSPHERE: 1 x float4 (tx,ty,tz,r)
+    // acceleration structure
+    const rm_bvh_node* bvh;
+    const rm_octree_node* oct;
+    const int32_t* leaf_prims;
+    uint32_t type_hist[3];  // number of sphere / box / torus primitives in the scene
+};
+
+// Per-launch statistics accumulated by the render kernel's epilogue (one atomic set per warp).
+struct DevStats {
+    unsigned long long sum_sdf, sum_iters;            // on the u16-wrapped per-pixel values
+    unsigned long long sum_sdf_full, sum_iters_full;  // un-wrapped
+    unsigned long long evals_sphere, evals_box, evals_torus;
+    unsigned long long n_hit;
+    unsigned int max_sdf, min_sdf, max_iters, min_iters;
+    unsigned int queue;  // atomic tile counter of the persistent-CTA work queue
+    unsigned int pad_;
+};
+
+struct RenderParams {
+    DevScene scene;
+    int32_t width, height, y_start, y_end;
+    float rot3[9];
+    float origin[3];
+    int32_t algorithm;
+    double step_size, overshoot;
+    int32_t shader, shader2;
+    int32_t length_sqrt;  // validation: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot
+    int32_t n_tiles, tiles_x;
+    // outputs (device pointers; optional ones may be null)
+    uint8_t* depth;
+    uint8_t* normal;
+    uint16_t* sdf;
+    uint16_t* iters;
+    uint8_t* rgba;
+    uint8_t* rgba2;
+    float* depth_f32;
+    uint32_t* sdf_u32;
+    DevStats* stats;
+};
+
+struct ShadeParams {
+    int32_t shader;
+    int32_t n_pixels;
+    const uint8_t* depth;
+    const uint8_t* normal;
+    const uint16_t* sdf;
+    const uint16_t* iters;
+    uint8_t* rgba;
+};
+
+// Launchers implemented in rm_kernels_val.cu / rm_kernels_fast.cu.  Return a cudaError_t as int.
+int launch_render_val(const RenderParams& p, int n_sms, void* stream);
+int launch_render_fast(const RenderParams& p, int n_sms, void* stream);
+int launch_shade_val(const ShadeParams& p, void* stream);
+int launch_shade_fast(const ShadeParams& p, void* stream);
+
+}  // namespace rm

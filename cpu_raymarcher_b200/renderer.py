@@ -1,0 +1,195 @@
+"""Thin object wrapper over the C ABI: one Context = one rm_ctx (one B200, one stream)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import ACCELS, ALGORITHMS, SHADERS, RmError
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+@dataclass
+class Frame:
+    """The worker `Result` (raymarchWorker.ts:24-31) plus the optional extension planes."""
+    yStart: int
+    yEnd: int
+    depth: np.ndarray
+    normal: np.ndarray
+    sdfEval: np.ndarray
+    iters: np.ndarray
+    rgba: np.ndarray | None = None
+    rgba_analytics: np.ndarray | None = None
+    depth_f32: np.ndarray | None = None
+    sdf_u32: np.ndarray | None = None
+
+
+def build_bvh(types, w2l, params, flags: int = 0):
+    """rm_build_bvh: native BVH builder, result-identical to bvh.ts:29-92.  No GPU needed."""
+    L = _lib.lib()
+    types = np.ascontiguousarray(types, np.uint8)
+    w2l = np.ascontiguousarray(w2l, np.float32)
+    params = np.ascontiguousarray(params, np.float64)
+    nn, nl = C.c_int32(0), C.c_int32(0)
+    rc = L.rm_build_bvh(len(types), _ptr(types), _ptr(w2l), _ptr(params), flags, None, C.byref(nn), None, C.byref(nl))
+    if rc:
+        raise RmError(rc, "rm_build_bvh")
+    nodes = (_lib.BvhNode * max(nn.value, 1))()
+    leaf = np.zeros(max(nl.value, 1), np.int32)
+    rc = L.rm_build_bvh(len(types), _ptr(types), _ptr(w2l), _ptr(params), flags, nodes, C.byref(nn), _ptr(leaf), C.byref(nl))
+    if rc:
+        raise RmError(rc, "rm_build_bvh")
+    return nodes, nn.value, leaf[: nl.value]
+
+
+def build_octree(types, w2l, params, flags: int = 0):
+    """rm_build_octree: native octree builder, result-identical to octree.ts:36-118,149-191."""
+    L = _lib.lib()
+    types = np.ascontiguousarray(types, np.uint8)
+    w2l = np.ascontiguousarray(w2l, np.float32)
+    params = np.ascontiguousarray(params, np.float64)
+    nn, nl = C.c_int32(0), C.c_int32(0)
+    rc = L.rm_build_octree(len(types), _ptr(types), _ptr(w2l), _ptr(params), flags, None, C.byref(nn), None, C.byref(nl))
+    if rc:
+        raise RmError(rc, "rm_build_octree")
+    nodes = (_lib.OctreeNode * max(nn.value, 1))()
+    leaf = np.zeros(max(nl.value, 1), np.int32)
+    rc = L.rm_build_octree(len(types), _ptr(types), _ptr(w2l), _ptr(params), flags, nodes, C.byref(nn), _ptr(leaf), C.byref(nl))
+    if rc:
+        raise RmError(rc, "rm_build_octree")
+    return nodes, nn.value, leaf[: nl.value]
+
+
+class Context:
+    def __init__(self, device: int = 0, validate_fp64: bool = False, length_sqrt: bool = False):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.flags = (_lib.RM_F_VALIDATE_FP64 if validate_fp64 else 0) | (_lib.RM_F_LENGTH_SQRT if length_sqrt else 0)
+        rc = self._L.rm_create(C.byref(self._h), device, self.flags)
+        if rc:
+            raise RmError(rc, (self._L.rm_last_error(None) or b"").decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise RmError(rc, (self._L.rm_last_error(self._h) or b"").decode())
+
+    # ---- scene ----
+    def upload_scene(self, types, w2l, params, accel="None", nodes=None, n_nodes=0, leaf=None):
+        types = np.ascontiguousarray(types, np.uint8)
+        w2l = np.ascontiguousarray(w2l, np.float32)
+        params = np.ascontiguousarray(params, np.float64)
+        s = _lib.Scene()
+        s.n_prims = len(types)
+        s.type, s.world_to_local, s.params = _ptr(types), _ptr(w2l), _ptr(params)
+        s.accel_kind = ACCELS[accel] if isinstance(accel, str) else int(accel)
+        if nodes is not None:
+            leaf = np.ascontiguousarray(leaf, np.int32)
+            s.n_nodes = n_nodes
+            s.nodes = C.cast(nodes, C.c_void_p)
+            s.n_leaf_prims = len(leaf)
+            s.leaf_prim_index = _ptr(leaf)
+        self._check(self._L.rm_upload_scene(self._h, C.byref(s)))
+        self.n_prims = len(types)
+
+    # ---- render ----
+    @staticmethod
+    def make_request(width, height, rot3, origin, algorithm="sphere-tracer", y_start=0, y_end=None, step_size=0.1,
+                     overshoot=1.2, shader=None, shader_analytics=None, time=0.0) -> _lib.Request:
+        rq = _lib.Request()
+        rq.width, rq.height = width, height
+        rq.y_start, rq.y_end = y_start, (height if y_end is None else y_end)
+        rq.time = time
+        rq.rot3 = (C.c_float * 9)(*[float(v) for v in rot3])
+        rq.origin = (C.c_float * 3)(*[float(v) for v in origin])
+        rq.algorithm = ALGORITHMS.get(algorithm, 0) if isinstance(algorithm, str) else int(algorithm)
+        rq.step_size, rq.overshoot_factor = step_size, overshoot
+        rq.shader = SHADERS[shader] if not isinstance(shader, int) else shader
+        rq.shader_analytics = SHADERS[shader_analytics] if not isinstance(shader_analytics, int) else shader_analytics
+        return rq
+
+    def render(self, rq: _lib.Request, extras: bool = False) -> Frame:
+        """rm_render: host buffers out (the worker path)."""
+        th = max(0, rq.y_end - rq.y_start)
+        n = th * rq.width
+        f = Frame(rq.y_start, rq.y_end, np.zeros(n, np.uint8), np.zeros(3 * n, np.uint8), np.zeros(n, np.uint16),
+                  np.zeros(n, np.uint16))
+        res = _lib.Result()
+        res.depth, res.normal, res.sdf_eval, res.iters = _ptr(f.depth), _ptr(f.normal), _ptr(f.sdfEval), _ptr(f.iters)
+        if rq.shader >= 0:
+            f.rgba = np.zeros(4 * n, np.uint8)
+            res.rgba = _ptr(f.rgba)
+        if rq.shader_analytics >= 0:
+            f.rgba_analytics = np.zeros(4 * n, np.uint8)
+            res.rgba_analytics = _ptr(f.rgba_analytics)
+        if extras:
+            f.depth_f32 = np.zeros(n, np.float32)
+            f.sdf_u32 = np.zeros(n, np.uint32)
+            res.depth_f32, res.sdf_eval_u32 = _ptr(f.depth_f32), _ptr(f.sdf_u32)
+        self._check(self._L.rm_render(self._h, C.byref(rq), C.byref(res)))
+        return f
+
+    def render_device(self, rq: _lib.Request, res: _lib.Result, stream: int | None = None):
+        """rm_render_device: planes are device pointers (e.g. torch tensors' data_ptr())."""
+        self._check(self._L.rm_render_device(self._h, C.byref(rq), C.byref(res), stream))
+
+    def stats(self) -> dict:
+        st = _lib.Stats()
+        self._check(self._L.rm_stats(self._h, C.byref(st)))
+        d = {k: getattr(st, k) for k, _ in _lib.Stats._fields_ if k != "evals_by_type"}
+        d["evals_by_type"] = list(st.evals_by_type)
+        return d
+
+    def shade(self, shader, depth, normal, sdf, iters, width, height) -> np.ndarray:
+        out = np.zeros(4 * width * height, np.uint8)
+        sid = SHADERS[shader] if isinstance(shader, str) else int(shader)
+        self._check(self._L.rm_shade(self._h, sid, _ptr(out), _ptr(np.ascontiguousarray(depth, np.uint8)),
+                                     _ptr(np.ascontiguousarray(normal, np.uint8)),
+                                     _ptr(np.ascontiguousarray(sdf, np.uint16)),
+                                     _ptr(np.ascontiguousarray(iters, np.uint16)), width, height))
+        return out
+
+    # ---- multi-GPU plumbing ----
+    def alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._L.rm_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr: int):
+        self._check(self._L.rm_free(self._h, ptr))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self._L.rm_ipc_export(self._h, ptr, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self._L.rm_ipc_open(self._h, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self._check(self._L.rm_ipc_close(self._h, ptr))
+
+    def memcpy_d2h(self, host: np.ndarray, dev_ptr: int):
+        self._check(self._L.rm_memcpy_d2h(self._h, _ptr(host), dev_ptr, host.nbytes))
+
+    def memcpy_h2d(self, dev_ptr: int, host: np.ndarray):
+        self._check(self._L.rm_memcpy_h2d(self._h, dev_ptr, _ptr(host), host.nbytes))

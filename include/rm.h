@@ -1,0 +1,196 @@
+/* rm.h — C ABI of the B200-native raymarch hot path (librm_b200.so).
+ *
+ * This is the drop-in boundary for vxlerian/cpu-raymarcher's per-pixel raymarch path.  The
+ * reference has no FFI; the seam its controller (src/main.ts) programs against is the Web-Worker
+ * message contract of src/workers/raymarchWorker.ts:
+ *     Job    (raymarchWorker.ts:10-22)  -> rm_request  (+ host-computed camera basis, see below)
+ *     Result (raymarchWorker.ts:24-31)  -> rm_result   (same four arrays, same dtypes, tile-local)
+ *     `new Scene(accel); scene.loadPreset(i)` (raymarchWorker.ts:37-38) -> rm_upload_scene
+ *     diagnostics loop of main.ts:527-548                                -> rm_stats
+ *     ShadingModel.shade (src/util/shading_models/shadingModel.ts:8-16)  -> rm_shade / rm_request.shader
+ * A Node N-API addon (addon/rm_napi.cc) or any other host binds exactly these entry points; see
+ * INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions: plain pointers and sizes only; every function returns RM_OK (0) or a negative
+ * rm_status; nothing throws or aborts; there is NO CPU fallback — without a CUDA device every
+ * compute entry point fails with RM_ERR_CUDA.  All host pointers are borrowed for the duration of
+ * the call only (rm_upload_scene copies).
+ */
+#ifndef RM_H
+#define RM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RM_ABI_VERSION 1
+
+typedef struct rm_ctx rm_ctx; /* opaque: one CUDA device, its stream, device-resident scene + frame buffers */
+
+typedef enum rm_status {
+    RM_OK = 0,
+    RM_ERR_ARG = -1,                   /* null pointer, bad size, bad enum */
+    RM_ERR_UNSUPPORTED_PRIMITIVE = -2, /* operator trees / mandelbulb (reference components outside the path) */
+    RM_ERR_CUDA = -3,                  /* no device, launch or copy failure (message in rm_last_error) */
+    RM_ERR_STATE = -4,                 /* e.g. rm_render before rm_upload_scene */
+    RM_ERR_NOMEM = -5
+} rm_status;
+
+/* rm_create flags */
+#define RM_F_VALIDATE_FP64 1u /* fp64, non-fused, JS-number-exact validation kernels (bit-exact counters/hit mask) */
+#define RM_F_LENGTH_SQRT 2u   /* validation only: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot (gl-matrix caveat) */
+
+/* src/util/primitives/{sphere,box,torus}.ts */
+typedef enum rm_prim_type { RM_PRIM_SPHERE = 0, RM_PRIM_BOX = 1, RM_PRIM_TORUS = 2 } rm_prim_type;
+/* Scene.accelerationStructure: "None" | "Octree" | "BVH"  (src/util/scene.ts:20,32-36) */
+typedef enum rm_accel_kind { RM_ACCEL_NONE = 0, RM_ACCEL_OCTREE = 1, RM_ACCEL_BVH = 2 } rm_accel_kind;
+/* Job.algorithm (raymarchWorker.ts:49-68); unknown strings map to the sphere tracer on the host side */
+typedef enum rm_algorithm {
+    RM_ALG_SPHERE_TRACER = 0,    /* src/cpu_algorithms/sphereTracer.ts   */
+    RM_ALG_FIXED_STEP = 1,       /* src/cpu_algorithms/fixedStep.ts      */
+    RM_ALG_ADAPTIVE_STEP = 2,    /* src/cpu_algorithms/adaptiveStep.ts   */
+    RM_ALG_ADAPTIVE_STEP_V2 = 3, /* src/cpu_algorithms/adaptiveStepV2.ts */
+    RM_ALG_ADAPTIVE_STEP_V3 = 4  /* src/cpu_algorithms/adaptiveStepV3.ts */
+} rm_algorithm;
+/* createShadingModelFromValue (src/main.ts:33-45) */
+typedef enum rm_shader {
+    RM_SHADER_NONE = -1,
+    RM_SHADER_NORMAL = 0,           /* normalModel.ts      */
+    RM_SHADER_PHONG = 1,            /* phongModel.ts       */
+    RM_SHADER_SDF_HEATMAP = 2,      /* SDFHeatmap.ts       */
+    RM_SHADER_ITERATION_HEATMAP = 3 /* IterationHeatmap.ts */
+} rm_shader;
+
+/* Flattened BVH node (src/acceleration_structures/bvh.ts:6-22).  Pre-order, root = 0, left subtree
+ * directly after its parent.  Internal nodes: prim_count = 0.  Leaves: left = right = -1 and
+ * leaf_prim_index[prim_first .. prim_first+prim_count) lists scene primitive indices in the
+ * reference's node.primitives order. */
+typedef struct rm_bvh_node {
+    float bmin[3], bmax[3];
+    int32_t left, right;
+    int32_t prim_first, prim_count;
+} rm_bvh_node;
+
+/* Flattened octree node (src/acceleration_structures/octree.ts:6-26).  Root = 0; the 8 children of
+ * a node are consecutive at first_child .. first_child+7 in the reference's z,y,x order
+ * (octree.ts:69-88); first_child = -1 for leaves. */
+typedef struct rm_octree_node {
+    float bmin[3], bmax[3];
+    int32_t first_child;
+    int32_t prim_first, prim_count;
+    uint8_t level, is_empty, pad_[2];
+    double min_distance;
+} rm_octree_node;
+
+/* The scene as Scene.objectSDFs + optional acceleration structure (src/util/scene.ts:12-71). */
+typedef struct rm_scene {
+    int32_t n_prims;
+    const uint8_t* type;         /* [n_prims] rm_prim_type */
+    const float* world_to_local; /* [16*n_prims] column-major mat4, exactly Primitive.transform (primitive.ts:4,10) */
+    const double* params;        /* [4*n_prims] sphere: r | box: hx,hy,hz (f32-valued) | torus: R, r */
+    int32_t accel_kind;          /* rm_accel_kind */
+    /* Optional host-built structure (e.g. walked out of the reference's own BVH/Octree objects).
+     * If accel_kind != NONE and nodes == NULL the library builds it natively with a builder that is
+     * result-identical to bvh.ts:29-92 / octree.ts:36-118,149-191. */
+    int32_t n_nodes;
+    const void* nodes; /* rm_bvh_node[n_nodes] or rm_octree_node[n_nodes] */
+    int32_t n_leaf_prims;
+    const int32_t* leaf_prim_index;
+} rm_scene;
+
+/* One frame-band request = one worker Job (raymarchWorker.ts:10-22).  The host evaluates the camera
+ * (camera.ts:81-88) and passes rot3 = mat3.fromMat4(camera.getRotationMatrix()) and
+ * origin = camera.getPosition() exactly as raymarcher.ts:62-67 obtains them. */
+typedef struct rm_request {
+    int32_t width, height;  /* full frame size */
+    int32_t y_start, y_end; /* rows of this band; outputs are tile-local ((y-y_start)*width + x) */
+    double time;            /* Job.time; unused by sphere/box/torus (primitive.ts:42-44) */
+    float rot3[9];          /* column-major mat3 */
+    float origin[3];
+    int32_t algorithm;       /* rm_algorithm */
+    double step_size;        /* FixedStep ctor (fixedStep.ts:13-16), default 0.1 */
+    double overshoot_factor; /* AdaptiveStepV2/V3 ctor, default 1.2 */
+    int32_t shader;           /* rm_shader for result.rgba           (RM_SHADER_NONE: skip) */
+    int32_t shader_analytics; /* rm_shader for result.rgba_analytics (main.ts:506-518)      */
+} rm_request;
+
+/* Result (raymarchWorker.ts:24-31).  Buffers are CALLER-allocated.  For rm_render they are host
+ * pointers; for rm_render_device they are device pointers on the context's device. */
+typedef struct rm_result {
+    uint8_t* depth;          /* [W*th]   Uint8ClampedArray, world units (raymarcher.ts:106)      */
+    uint8_t* normal;         /* [3*W*th] Uint8ClampedArray (raymarcher.ts:103-105)               */
+    uint16_t* sdf_eval;      /* [W*th]   Uint16Array, wraps mod 65536 (raymarcher.ts:119)        */
+    uint16_t* iters;         /* [W*th]   Uint16Array                                             */
+    uint8_t* rgba;           /* [4*W*th] optional (NULL to skip): request.shader output          */
+    uint8_t* rgba_analytics; /* [4*W*th] optional: request.shader_analytics output               */
+    float* depth_f32;        /* [W*th]   optional extension: unquantised rayMarch return         */
+    uint32_t* sdf_eval_u32;  /* [W*th]   optional extension: un-wrapped SDF-call count           */
+} rm_result;
+
+/* Diagnostics of the last completed rm_render / rm_render_device on this context. */
+typedef struct rm_stats_t {
+    uint64_t n_pixels;
+    /* main.ts:527-548, on the u16-WRAPPED buffers (what the reference's panel shows) */
+    uint64_t sum_sdf, sum_iters;
+    uint32_t max_sdf, min_sdf, max_iters, min_iters;
+    /* un-wrapped totals (throughput accounting: SDF evals/s) */
+    uint64_t sum_sdf_full, sum_iters_full;
+    uint64_t evals_by_type[3]; /* un-wrapped primitive evaluations split sphere/box/torus */
+    uint64_t n_hit;            /* pixels with depth < MAX_DIST */
+    double kernel_ms;          /* CUDA-event time of the render kernel(s) */
+    double wall_ms;            /* host wall time of the whole call */
+    int32_t n_launches;        /* kernels launched by the call */
+    int32_t device;
+} rm_stats_t;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int rm_abi_version(void);
+int rm_device_count(void); /* >= 0, or RM_ERR_CUDA */
+int rm_create(rm_ctx** out, int device, unsigned flags);
+void rm_destroy(rm_ctx* ctx);
+const char* rm_last_error(rm_ctx* ctx); /* ctx may be NULL: error of the last failed rm_create on this thread */
+
+/* ---- scene -------------------------------------------------------------------------------- */
+int rm_upload_scene(rm_ctx* ctx, const rm_scene* scene);
+
+/* Native builders (host side, no GPU needed).  Two-call pattern: pass nodes = NULL to get the
+ * counts, then call again with buffers of that size.  Results are identical (bounds, topology,
+ * leaf order) to the reference's bvh.ts / octree.ts builders on the same primitives. */
+int rm_build_bvh(int32_t n_prims, const uint8_t* type, const float* world_to_local, const double* params,
+                 unsigned flags /* RM_F_LENGTH_SQRT */, rm_bvh_node* nodes, int32_t* n_nodes,
+                 int32_t* leaf_prim_index, int32_t* n_leaf_prims);
+int rm_build_octree(int32_t n_prims, const uint8_t* type, const float* world_to_local, const double* params,
+                    unsigned flags /* RM_F_LENGTH_SQRT */, rm_octree_node* nodes, int32_t* n_nodes,
+                    int32_t* leaf_prim_index, int32_t* n_leaf_prims);
+
+/* ---- render ------------------------------------------------------------------------------- */
+int rm_render(rm_ctx* ctx, const rm_request* rq, const rm_result* host_out);
+/* Same, but outputs are device pointers and nothing is copied to the host.  cuda_stream is a
+ * cudaStream_t (NULL = the context's own stream).  Returns after the kernels are enqueued AND the
+ * stats have been read back (it synchronises the stream). */
+int rm_render_device(rm_ctx* ctx, const rm_request* rq, const rm_result* device_out, void* cuda_stream);
+int rm_stats(rm_ctx* ctx, rm_stats_t* out);
+
+/* ShadingModel.shade on existing (host) buffers: pure per-pixel map of the four quantised planes. */
+int rm_shade(rm_ctx* ctx, int32_t shader, uint8_t* rgba, const uint8_t* depth, const uint8_t* normal,
+             const uint16_t* sdf_eval, const uint16_t* iters, int32_t width, int32_t height);
+
+/* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "multi-GPU") -------------------- */
+/* Device allocation owned by the context (freed by rm_free / rm_destroy). */
+int rm_alloc(rm_ctx* ctx, size_t bytes, void** dev_ptr);
+int rm_free(rm_ctx* ctx, void* dev_ptr);
+/* CUDA-IPC export/import so a band rendered on rank r is stored straight into rank 0's frame over
+ * NVLink by the render kernel itself (fused gather).  handle is 64 bytes. */
+int rm_ipc_export(rm_ctx* ctx, void* dev_ptr, uint8_t handle[64]);
+int rm_ipc_open(rm_ctx* ctx, const uint8_t handle[64], void** dev_ptr);
+int rm_ipc_close(rm_ctx* ctx, void* dev_ptr);
+int rm_memcpy_d2h(rm_ctx* ctx, void* host, const void* dev, size_t bytes);
+int rm_memcpy_h2d(rm_ctx* ctx, void* dev, const void* host, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RM_H */
