@@ -52,7 +52,7 @@ class Request(C.Structure):
 class Result(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("normal", C.c_void_p), ("sdf_eval", C.c_void_p), ("iters", C.c_void_p),
                 ("rgba", C.c_void_p), ("rgba_analytics", C.c_void_p), ("depth_f32", C.c_void_p),
-                ("sdf_eval_u32", C.c_void_p)]
+                ("sdf_eval_u32", C.c_void_p), ("depth_f64", C.c_void_p)]
 
 
 class Stats(C.Structure):

@@ -158,6 +158,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.rgba2 = (rq->shader_analytics != RM_SHADER_NONE) ? out->rgba_analytics : nullptr;
     P.depth_f32 = out->depth_f32;
     P.sdf_u32 = out->sdf_eval_u32;
+    P.depth_f64 = out->depth_f64;
     P.stats = c->d_stats;
 
     DevStats init{};
@@ -440,6 +441,7 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     const size_t oRgba2 = off; off += wantRgba2 ? al(4 * np) : 0;
     const size_t oDf = off; off += out->depth_f32 ? al(4 * np) : 0;
     const size_t oSu = off; off += out->sdf_eval_u32 ? al(4 * np) : 0;
+    const size_t oD64 = off; off += out->depth_f64 ? al(8 * np) : 0;
     const size_t total = off;
     if ((rc = ensure(c, c->d_frame, total + 256, false))) return rc;
     if ((rc = ensure(c, c->h_frame, total + 256, true))) return rc;
@@ -453,6 +455,7 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     dev.rgba_analytics = wantRgba2 ? d + oRgba2 : nullptr;
     dev.depth_f32 = out->depth_f32 ? (float*)(d + oDf) : nullptr;
     dev.sdf_eval_u32 = out->sdf_eval_u32 ? (uint32_t*)(d + oSu) : nullptr;
+    dev.depth_f64 = out->depth_f64 ? (double*)(d + oD64) : nullptr;
     rc = render_device_locked(c, rq, &dev, c->stream);
     if (rc) return rc;
     if (np > 0) {
@@ -468,6 +471,7 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
         if (wantRgba2) std::memcpy(out->rgba_analytics, h + oRgba2, 4 * np);
         if (out->depth_f32) std::memcpy(out->depth_f32, h + oDf, 4 * np);
         if (out->sdf_eval_u32) std::memcpy(out->sdf_eval_u32, h + oSu, 4 * np);
+        if (out->depth_f64) std::memcpy(out->depth_f64, h + oD64, 8 * np);
     }
     c->last.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     return RM_OK;

@@ -16,18 +16,17 @@
 //   * every lane owns one ray and runs it as an explicit state machine
 //     (STEP -> scene-distance query -> consume -> ... -> 4 normal queries -> finalize); lanes whose
 //     ray terminated are found with __ballot_sync and refilled with fresh pixels immediately, so
-//     divergent ray lengths do not idle lanes;
-//     all scene-distance queries of a warp — march steps, normal taps, V3 bridging taps — funnel
-//     through ONE code site;
+//     divergent ray lengths do not idle lanes; all scene-distance queries of a warp — march steps,
+//     normal taps, V3 bridging taps — funnel through ONE code site;
 //   * a query is first resolved through the acceleration structure (few primitives, lane-local);
 //     queries that need every primitive (no acceleration structure, the BVH "empty candidate set"
-//     fallback of scene.ts:173, points outside the octree root) are executed by the dense
-//     all-primitives loop where every lane reads the same primitive record (one broadcast load per
-//     warp per primitive);
-//   * per-pixel outputs are quantised exactly like the reference's typed arrays and the
-//     diagnostics are reduced in the epilogue (warp reduce, one atomic set per warp).
+//     fallback of scene.ts:173, points outside the octree root) run the dense all-primitives loop
+//     in which every lane reads the same primitive record (one broadcast load per warp per primitive);
+//   * per-pixel outputs are quantised exactly like the reference's typed arrays and the diagnostics
+//     are reduced in the epilogue (warp reduce, one atomic set per warp).
 //
-// The file is instantiated twice: NumJS (fp64, -fmad=false, bit-exact) and NumFast (fp32).
+// Instantiated twice over the FIELD model (rm_numeric.cuh): NumJS (fp64, bit-exact) and NumFast (fp32).
+// Control arithmetic is double / non-fused in both.
 #pragma once
 #include "rm_numeric.cuh"
 #include "rm_types.h"
@@ -38,8 +37,8 @@ constexpr unsigned kFull = 0xffffffffu;
 
 enum Phase : int {
     PH_IDLE = 0,
-    PH_NEW,        // pixel assigned, ray not yet initialised
-    PH_STEP,       // at the top of march-loop index i
+    PH_NEW,         // pixel assigned, ray not yet initialised
+    PH_STEP,        // at the top of march-loop index i
     PH_WAIT_MARCH,  // scene-distance query pending: march step
     PH_WAIT_V3B,    // query pending: AdaptiveStepV3 bridging tap (adaptiveStepV3.ts:113-115)
     PH_WAIT_N0,     // query pending: normal taps (raymarcher.ts:124-132)
@@ -49,49 +48,34 @@ enum Phase : int {
     PH_FINAL  // march + normal done: quantise and store
 };
 
-template <class NP>
-struct Vec3 {
-    typename NP::S x, y, z;
-};
-
 // ------------------------------------------------------------------------------------------
 // Primitive SDFs
 // ------------------------------------------------------------------------------------------
 
-// vec3.length (sphere.ts:13, box.ts:26): Math.hypot in gl-matrix 3.x, optionally plain sqrt.
-template <class NP>
-RM_DEV typename NP::S vec_length(typename NP::S x, typename NP::S y, typename NP::S z, int length_sqrt) {
-    if constexpr (NP::kExact) {
-        if (!length_sqrt) return v8_hypot3(x, y, z);
-        return sqrt(x * x + y * y + z * z);
-    } else {
-        return NP::sqrt_(x * x + y * y + z * z);
-    }
-}
-
-// Exact path: Primitive.sdf (primitive.ts:33-39) = f32(transformMat4(p, M)) then localSdf.
+// Exact model: Primitive.sdf (primitive.ts:33-39) = f32(transformMat4(p, M)) then localSdf.
 RM_DEV double prim_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt) {
     const float* m = sc.w2l + 16 * (size_t)j;
     double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7];
     double m8 = m[8], m9 = m[9], m10 = m[10], m11 = m[11], m12 = m[12], m13 = m[13], m14 = m[14], m15 = m[15];
     double w = m3 * x + m7 * y + m11 * z + m15;
     if (w == 0.0 || w != w) w = 1.0;  // w = w || 1.0
-    double lx = NumJS::vst((m0 * x + m4 * y + m8 * z + m12) / w);
-    double ly = NumJS::vst((m1 * x + m5 * y + m9 * z + m13) / w);
-    double lz = NumJS::vst((m2 * x + m6 * y + m10 * z + m14) / w);
+    double lx = (double)f32r((m0 * x + m4 * y + m8 * z + m12) / w);
+    double ly = (double)f32r((m1 * x + m5 * y + m9 * z + m13) / w);
+    double lz = (double)f32r((m2 * x + m6 * y + m10 * z + m14) / w);
     const double* prm = sc.params + 4 * (size_t)j;
     int type = sc.type[j];
-    if (type == RM_PRIM_SPHERE) {  // sphere.ts:12-14
-        return vec_length<NumJS>(lx, ly, lz, length_sqrt) - prm[0];
+    if (type == RM_PRIM_SPHERE) {  // sphere.ts:12-14 ; vec3.length = Math.hypot (or plain sqrt, RM_F_LENGTH_SQRT)
+        double len = length_sqrt ? sqrt(lx * lx + ly * ly + lz * lz) : v8_hypot3(lx, ly, lz);
+        return len - prm[0];
     } else if (type == RM_PRIM_BOX) {  // box.ts:13-30
-        double q0 = NumJS::vst(fabs(lx) - prm[0]);
-        double q1 = NumJS::vst(fabs(ly) - prm[1]);
-        double q2 = NumJS::vst(fabs(lz) - prm[2]);
-        double o0 = NumJS::vst(jsmax<NumJS>(q0, 0.0));
-        double o1 = NumJS::vst(jsmax<NumJS>(q1, 0.0));
-        double o2 = NumJS::vst(jsmax<NumJS>(q2, 0.0));
-        double outsideDist = vec_length<NumJS>(o0, o1, o2, length_sqrt);
-        double insideDist = jsmin<NumJS>(jsmax<NumJS>(q0, jsmax<NumJS>(q1, q2)), 0.0);
+        double q0 = (double)f32r(fabs(lx) - prm[0]);
+        double q1 = (double)f32r(fabs(ly) - prm[1]);
+        double q2 = (double)f32r(fabs(lz) - prm[2]);
+        double o0 = (double)f32r(jsmax(q0, 0.0));
+        double o1 = (double)f32r(jsmax(q1, 0.0));
+        double o2 = (double)f32r(jsmax(q2, 0.0));
+        double outsideDist = length_sqrt ? sqrt(o0 * o0 + o1 * o1 + o2 * o2) : v8_hypot3(o0, o1, o2);
+        double insideDist = jsmin(jsmax(q0, jsmax(q1, q2)), 0.0);
         return outsideDist + insideDist;
     } else {  // torus.ts:14-25
         double qx = sqrt(lx * lx + lz * lz) - prm[0];
@@ -100,7 +84,7 @@ RM_DEV double prim_sdf_exact(const DevScene& sc, int j, double x, double y, doub
     }
 }
 
-// Fast path, general affine record: rows of the 3x4 world->local + (p0,p1,p2,type).
+// Fast model, general affine record: rows of the 3x4 world->local + (p0,p1,p2,type).
 RM_DEV float prim_sdf_fast_general(const float4* __restrict__ rec, int j, float x, float y, float z, int& type) {
     const float4 r0 = __ldg(rec + 4 * (size_t)j + 0);
     const float4 r1 = __ldg(rec + 4 * (size_t)j + 1);
@@ -123,28 +107,27 @@ RM_DEV float prim_sdf_fast_general(const float4* __restrict__ rec, int j, float 
         return NumFast::sqrt_(fmaf(qx, qx, ly * ly)) - pr.y;
     }
 }
-// Fast path, translation-only sphere: local = p + t.
+// Fast model, translation-only sphere: local = p + t.
 RM_DEV float prim_sdf_fast_tsphere(const float4* __restrict__ rec, int j, float x, float y, float z) {
     const float4 s = __ldg(rec + j);
     float lx = x + s.x, ly = y + s.y, lz = z + s.z;
     return NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - s.w;
 }
 
-// One primitive evaluation for either numeric model; `evalSphere/evalBox` count by type.
+// One primitive evaluation at the f32 sample point q; nSphere/nBox count evaluations by type.
 template <class NP, int PK>
-RM_DEV typename NP::S prim_sdf(const RenderParams& P, int j, typename NP::S x, typename NP::S y, typename NP::S z,
-                               unsigned& nSphere, unsigned& nBox) {
+RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], unsigned& nSphere, unsigned& nBox) {
     if constexpr (NP::kExact) {
         int type = P.scene.type[j];
         nSphere += (type == RM_PRIM_SPHERE);
         nBox += (type == RM_PRIM_BOX);
-        return prim_sdf_exact(P.scene, j, x, y, z, P.length_sqrt);
+        return prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt);
     } else if constexpr (PK == PK_TSPHERE) {
         nSphere += 1;
-        return prim_sdf_fast_tsphere(P.scene.rec, j, x, y, z);
+        return prim_sdf_fast_tsphere(P.scene.rec, j, q[0], q[1], q[2]);
     } else {
         int type;
-        float d = prim_sdf_fast_general(P.scene.rec, j, x, y, z, type);
+        float d = prim_sdf_fast_general(P.scene.rec, j, q[0], q[1], q[2], type);
         nSphere += (type == RM_PRIM_SPHERE);
         nBox += (type == RM_PRIM_BOX);
         return d;
@@ -154,45 +137,45 @@ RM_DEV typename NP::S prim_sdf(const RenderParams& P, int j, typename NP::S x, t
 // Dense all-primitives evaluation: closest = min over every primitive (scene.ts:183-189), starting
 // from MAX_DIST = 10.  Every lane walks the same primitive index -> broadcast loads.
 template <class NP, int PK>
-RM_DEV typename NP::S scene_all_prims(const RenderParams& P, typename NP::S x, typename NP::S y, typename NP::S z) {
-    typedef typename NP::S S;
-    S closest = (S)10;
+RM_DEV typename NP::F scene_all_prims(const RenderParams& P, const float q[3]) {
+    typedef typename NP::F F;
+    F closest = (F)10;
     const int n = P.scene.n_prims;
-    unsigned dummyA = 0, dummyB = 0;
     if constexpr (NP::kExact) {
-        for (int j = 0; j < n; ++j) closest = jsmin<NP>(prim_sdf<NP, PK>(P, j, x, y, z, dummyA, dummyB), closest);
-    } else {
+        for (int j = 0; j < n; ++j)
+            closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
+    } else if constexpr (PK == PK_TSPHERE) {
 #pragma unroll 4
-        for (int j = 0; j < n; ++j) closest = fminf(prim_sdf<NP, PK>(P, j, x, y, z, dummyA, dummyB), closest);
+        for (int j = 0; j < n; ++j) closest = fminf(prim_sdf_fast_tsphere(P.scene.rec, j, q[0], q[1], q[2]), closest);
+    } else {
+        int type;
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) closest = fminf(prim_sdf_fast_general(P.scene.rec, j, q[0], q[1], q[2], type), closest);
     }
     return closest;
 }
 
 // ------------------------------------------------------------------------------------------
-// Bounding boxes
+// Bounding boxes.  Points and box corners are both float32 VALUES, so containment is exact in float.
 // ------------------------------------------------------------------------------------------
-template <class NP>
-RM_DEV bool box_contains(const float* bmin, const float* bmax, typename NP::S x, typename NP::S y, typename NP::S z) {
-    typedef typename NP::S S;
-    return x >= (S)bmin[0] && x <= (S)bmax[0] && y >= (S)bmin[1] && y <= (S)bmax[1] && z >= (S)bmin[2] && z <= (S)bmax[2];
+RM_DEV bool box_contains(const float* bmin, const float* bmax, const float q[3]) {  // boundingBox.ts:15-21
+    return q[0] >= bmin[0] && q[0] <= bmax[0] && q[1] >= bmin[1] && q[1] <= bmax[1] && q[2] >= bmin[2] && q[2] <= bmax[2];
 }
 
-// BoundingBox.intersectRay (boundingBox.ts:69-105).  No NaN can arise: |d| >= 1e-10 makes invD finite.
-template <class NP>
-RM_DEV bool box_intersect_ray(const float* bmin, const float* bmax, const typename NP::S o[3], const typename NP::S d[3],
-                              typename NP::S& tMinOut, typename NP::S& tMaxOut) {
-    typedef typename NP::S S;
-    S tMin = -NP::inf_(), tMax = NP::inf_();
+// BoundingBox.intersectRay (boundingBox.ts:69-105), doubles.  invD = 1/direction[i] is hoisted out of
+// the per-box loop (same value every time).  No NaN can arise: |d| >= 1e-10 keeps invD finite.
+RM_DEV bool box_intersect_ray(const float* bmin, const float* bmax, const double o[3], const float d[3], const double invD[3],
+                              double& tMinOut, double& tMaxOut) {
+    double tMin = -d_inf(), tMax = d_inf();
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        if (NP::abs_(d[i]) < (S)1e-10) {
-            if (o[i] < (S)bmin[i] || o[i] > (S)bmax[i]) return false;
+        if (fabs((double)d[i]) < 1e-10) {
+            if (o[i] < (double)bmin[i] || o[i] > (double)bmax[i]) return false;
         } else {
-            S invD = (S)1.0 / d[i];
-            S t0 = ((S)bmin[i] - o[i]) * invD;
-            S t1 = ((S)bmax[i] - o[i]) * invD;
+            double t0 = ((double)bmin[i] - o[i]) * invD[i];
+            double t1 = ((double)bmax[i] - o[i]) * invD[i];
             if (t0 > t1) {
-                S tmp = t0;
+                double tmp = t0;
                 t0 = t1;
                 t1 = tmp;
             }
@@ -211,57 +194,56 @@ RM_DEV bool box_intersect_ray(const float* bmin, const float* bmax, const typena
 // ------------------------------------------------------------------------------------------
 template <class NP>
 struct Ray {
-    typedef typename NP::S S;
-    S d[3];           // unit direction (f32-valued)
-    S t;              // totalDist
-    S q[3];           // pending query point (f32-valued)
-    S prevSDF, prevStep;  // V2 / V3
-    S aux0, aux1;     // V3: originalPos / newSDF ; normals: d(p) / -
-    S n0, n1;         // normal accumulators
-    S h[3];           // hit position
-    S depth;          // rayMarch return
-    unsigned sdf, iters;      // un-wrapped counters
-    unsigned nSphere, nBox;   // evaluations by type (torus = sdf - nSphere - nBox)
-    int i;            // march loop index
+    typedef typename NP::F F;
+    float d[3];   // unit direction (f32 values, raymarcher.ts:84-88)
+    float q[3];   // pending query point (f32 values)
+    float h[3];   // hit position (raymarcher.ts:94-95)
+    double t;     // totalDist
+    double prevSDF, prevStep;  // V2 / V3
+    double aux0, aux1;         // V3: originalPos / newSDF
+    double depth;              // rayMarch return
+    F nd;                      // getNormal: d = scene distance at the hit position
+    float n0, n1, n2;          // normal (f32 values)
+    unsigned sdf, iters;       // un-wrapped counters
+    unsigned nSphere, nBox;    // evaluations by type (torus = sdf - nSphere - nBox)
+    int i;                     // march loop index
     int phase;
-    int px, py;       // pixel
-    bool done;        // rayMarch has returned (depth is valid)
-    // BVH interval cursor (bvh.ts:204-240)
-    int cur, nIv;
+    int px, py;  // pixel (x, band-local y)
+    bool done;   // rayMarch has returned (depth is valid)
+    int cur, nIv;  // BVH interval cursor (bvh.ts:204-240)
 };
 
-// BVH per-ray interval list: the cursor advances at most one slot per march-loop index
+// BVH per-ray interval list.  The cursor advances at most one slot per march-loop index
 // (bvh.ts:222-236) and there are at most MAX_STEPS indices, so only the first MAX_STEPS+1 entries of
-// the stably sorted list can ever be read.  We keep exactly those, by bounded stable insertion.
-template <class NP>
+// the stably sorted list can ever be read; exactly those are kept, by bounded stable insertion.
 struct IvList {
-    typename NP::S enter[kMaxStepsFixed + 1];
-    typename NP::S exit_[kMaxStepsFixed + 1];
+    double enter[kMaxStepsFixed + 1];
+    double exit_[kMaxStepsFixed + 1];
 };
 
-// BVH.findRayIntersections + onRayMarchStart (bvh.ts:126-202).  Returns number of kept intervals.
-template <class NP>
-__device__ int bvh_collect(const RenderParams& P, const typename NP::S o[3], const typename NP::S d[3], IvList<NP>& iv,
-                           int cap) {
-    typedef typename NP::S S;
-    const rm_bvh_node* nodes = P.scene.bvh;
+// BVH.findRayIntersections + onRayMarchStart (bvh.ts:126-202).  Returns the number of kept intervals.
+static __device__ __noinline__ int bvh_collect(const rm_bvh_node* __restrict__ nodes, const double o[3], const float d[3], IvList& iv,
+                                        int cap) {
     int stack[kBvhStack];
     int sp = 0;
     stack[sp++] = 0;
     int n = 0;
-    const S tMin = (S)0, tMax = (S)10;
+    double invD[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) invD[i] = 1.0 / (double)d[i];
+    const double tMin = 0.0, tMax = 10.0;
     while (sp > 0) {
         int ni = stack[--sp];
         const rm_bvh_node* nd = nodes + ni;
-        S tEnter, tExit;
-        if (!box_intersect_ray<NP>(nd->bmin, nd->bmax, o, d, tEnter, tExit)) continue;
+        double tEnter, tExit;
+        if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tEnter, tExit)) continue;
         if (tExit < tMin || tEnter > tMax) continue;
-        S cEnter = tEnter > tMin ? tEnter : tMin;
-        S cExit = tExit < tMax ? tExit : tMax;
+        double cEnter = tEnter > tMin ? tEnter : tMin;
+        double cExit = tExit < tMax ? tExit : tMax;
         int left = nd->left, right = nd->right;
         if (left >= 0 || right >= 0) {
             if (left >= 0 && sp < kBvhStack) stack[sp++] = left;
-            if (right >= 0 && sp < kBvhStack) stack[sp++] = right;
+            if (right >= 0 && sp < kBvhStack) stack[sp++] = right;  // popped first (bvh.ts:160-161)
         } else if (nd->prim_count > 0) {
             // stable insertion: after every element with enter <= cEnter (later DFS order sorts later)
             if (n == cap && !(cEnter < iv.enter[n - 1])) continue;
@@ -279,74 +261,69 @@ __device__ int bvh_collect(const RenderParams& P, const typename NP::S o[3], con
     return n;
 }
 
-// BVH.onRayMarchStep (bvh.ts:204-240).  `total` = intervals.length as far as the cursor can tell.
+// BVH.onRayMarchStep (bvh.ts:204-240).
 template <class NP>
-RM_DEV typename NP::S bvh_step(Ray<NP>& r, const IvList<NP>& iv) {
-    typedef typename NP::S S;
-    if (r.cur >= r.nIv) return (S)-1;
-    S e = iv.enter[r.cur];
+RM_DEV double bvh_step(Ray<NP>& r, const IvList& iv) {
+    if (r.cur >= r.nIv) return -1.0;
+    double e = iv.enter[r.cur];
     if (r.t < e) return e - r.t;
     if (r.t > iv.exit_[r.cur]) {
         r.cur++;
         if (r.cur < r.nIv) {
-            S ne = iv.enter[r.cur];
+            double ne = iv.enter[r.cur];
             if (ne > r.t) return ne - r.t;
         } else {
-            return (S)-1;
+            return -1.0;
         }
     }
-    return (S)0;
+    return 0.0;
 }
 
 // Octree.findNode (octree.ts:223-248).  Children tile their parent exactly (shared f32 planes), and
 // "first containing child wins" on shared faces means the low half whenever p <= centre.
-template <class NP>
-RM_DEV int octree_find(const RenderParams& P, typename NP::S x, typename NP::S y, typename NP::S z) {
-    typedef typename NP::S S;
-    const rm_octree_node* nodes = P.scene.oct;
-    if (!box_contains<NP>(nodes[0].bmin, nodes[0].bmax, x, y, z)) return -1;
+RM_DEV int octree_find(const rm_octree_node* __restrict__ nodes, const float q[3]) {
+    if (!box_contains(nodes[0].bmin, nodes[0].bmax, q)) return -1;
     int ni = 0;
     for (int lvl = 0; lvl <= kOctreeMaxDepth; ++lvl) {
         int fc = nodes[ni].first_child;
         if (fc < 0 || nodes[ni].level == kOctreeMaxDepth) return ni;
         const float* c = nodes[fc].bmax;  // child 0 = low octant; its max corner is the parent's centre
-        int ci = (x > (S)c[0] ? 1 : 0) + (y > (S)c[1] ? 2 : 0) + (z > (S)c[2] ? 4 : 0);
+        int ci = (q[0] > c[0] ? 1 : 0) + (q[1] > c[1] ? 2 : 0) + (q[2] > c[2] ? 4 : 0);
         int child = fc + ci;
-        if (!box_contains<NP>(nodes[child].bmin, nodes[child].bmax, x, y, z)) return ni;  // octree.ts:247
+        if (!box_contains(nodes[child].bmin, nodes[child].bmax, q)) return ni;  // octree.ts:247
         ni = child;
     }
     return ni;
 }
 
-// Octree.marchRay (octree.ts:252-278) incl. intersectRayBox (:195-220, f32 tMin/tMax, no parallel guard).
-template <class NP>
-RM_DEV typename NP::S octree_march(const RenderParams& P, const typename NP::S o[3], const Ray<NP>& r,
-                                   const typename NP::S p[3]) {
-    typedef typename NP::S S;
-    int ni = octree_find<NP>(P, p[0], p[1], p[2]);
-    if (ni < 0) return (S)0;
-    const rm_octree_node* nd = P.scene.oct + ni;
-    if (!nd->is_empty) return (S)0;
-    S tMinV[3], tMaxV[3];
+// Octree.marchRay (octree.ts:252-278) incl. intersectRayBox (:195-220: f32 tMin/tMax, no parallel guard,
+// so +-Infinity and NaN flow through Math.max/min exactly as in JS).
+RM_DEV double octree_march(const rm_octree_node* __restrict__ nodes, const double o[3], const float d[3], double t,
+                           const float p[3]) {
+    int ni = octree_find(nodes, p);
+    if (ni < 0) return 0.0;
+    const rm_octree_node* nd = nodes + ni;
+    if (!nd->is_empty) return 0.0;
+    double tMinV[3], tMaxV[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        S invD = (S)1.0 / r.d[i];
-        S t0 = ((S)nd->bmin[i] - o[i]) * invD;
-        S t1 = ((S)nd->bmax[i] - o[i]) * invD;
-        if (invD < (S)0.0) {
-            S tmp = t0;
+        double invD = 1.0 / (double)d[i];
+        double t0 = ((double)nd->bmin[i] - o[i]) * invD;
+        double t1 = ((double)nd->bmax[i] - o[i]) * invD;
+        if (invD < 0.0) {
+            double tmp = t0;
             t0 = t1;
             t1 = tmp;
         }
-        tMinV[i] = NP::vst(t0);
-        tMaxV[i] = NP::vst(t1);
+        tMinV[i] = (double)f32r(t0);
+        tMaxV[i] = (double)f32r(t1);
     }
-    S tEnter = jsmax<NP>(jsmax<NP>(tMinV[0], tMinV[1]), tMinV[2]);
-    S tExit = jsmin<NP>(jsmin<NP>(tMaxV[0], tMaxV[1]), tMaxV[2]);
-    if (tEnter > tExit || tExit < (S)0) return (S)0;
-    S toExit = jsmax<NP>((S)0, tExit - r.t);
-    S step = jsmax<NP>((S)0, jsmin<NP>(toExit, (S)nd->min_distance * (S)0.99));
-    return step > (S)0 ? step + (S)0.001 : (S)0;
+    double tEnter = jsmax(jsmax(tMinV[0], tMinV[1]), tMinV[2]);
+    double tExit = jsmin(jsmin(tMaxV[0], tMaxV[1]), tMaxV[2]);
+    if (tEnter > tExit || tExit < 0.0) return 0.0;
+    double toExit = jsmax(0.0, tExit - t);
+    double step = jsmax(0.0, jsmin(toExit, nd->min_distance * 0.99));
+    return step > 0.0 ? step + 0.001 : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -360,37 +337,37 @@ RM_DEV uchar4 shade_heat(unsigned count_u16) {  // SDFHeatmap.ts:24-29 / Iterati
 }
 template <class NP>
 RM_DEV uchar4 shade_phong(unsigned depth_u8, unsigned n0, unsigned n1, unsigned n2) {  // phongModel.ts:15-73
-    typedef typename NP::S S;
+    typedef typename NP::F F;
     if (depth_u8 >= 255u) return make_uchar4(10, 10, 20, 255);
-    // lightDir = normalize(f32(1,-1,1.5))
-    S ll = (S)1 * (S)1 + (S)-1 * (S)-1 + (S)1.5 * (S)1.5;
-    S linv = (S)1 / NP::sqrt_(ll);
-    if constexpr (!NP::kExact) linv = rsqrtf(ll);
-    S L0 = NP::vst((S)1 * linv), L1 = NP::vst((S)-1 * linv), L2 = NP::vst((S)1.5 * linv);
-    S a0 = NP::vst((S)n0 / (S)127.5 - (S)1.0);
-    S a1 = NP::vst((S)n1 / (S)127.5 - (S)1.0);
-    S a2 = NP::vst((S)n2 / (S)127.5 - (S)1.0);
-    S len = a0 * a0 + a1 * a1 + a2 * a2;
-    if (len > (S)0) len = (S)1 / NP::sqrt_(len);
-    S N0 = NP::vst(a0 * len), N1 = NP::vst(a1 * len), N2 = NP::vst(a2 * len);
-    S ndl = N0 * L0 + N1 * L1 + N2 * L2;
-    S diffuse = jsmax<NP>(ndl, (S)0);
-    S sc = (S)2 * ndl;
-    S r0 = NP::vst(N0 * sc), r1 = NP::vst(N1 * sc), r2 = NP::vst(N2 * sc);
-    r0 = NP::vst(r0 - L0);
-    r1 = NP::vst(r1 - L1);
-    r2 = NP::vst(r2 - L2);
-    S rl = r0 * r0 + r1 * r1 + r2 * r2;
-    if (rl > (S)0) rl = (S)1 / NP::sqrt_(rl);
-    r0 = NP::vst(r0 * rl);
-    r1 = NP::vst(r1 * rl);
-    r2 = NP::vst(r2 * rl);
-    S vdr = (S)0 * r0 + (S)0 * r1 + (S)1 * r2;  // dot(viewDir=(0,0,1), reflectDir)
-    S specular = (S)0.5 * NP::pow32(jsmax<NP>(vdr, (S)0));
-    S intensity = jsmin<NP>((S)0.1 + diffuse + specular, (S)1);
-    S depthFactor = (S)1 - (S)depth_u8 / (S)255;
-    S color = (S)255 * intensity * depthFactor;
-    unsigned char c = to_u8_clamp<NP>(color);
+    // lightDir = normalize(vec3(1,-1,1.5))
+    F ll = (F)1 * (F)1 + (F)-1 * (F)-1 + (F)1.5 * (F)1.5;
+    F linv = NP::rsqrt_(ll);
+    F L0 = NP::st((F)1 * linv), L1 = NP::st((F)-1 * linv), L2 = NP::st((F)1.5 * linv);
+    F a0 = NP::st((F)n0 / (F)127.5 - (F)1.0);
+    F a1 = NP::st((F)n1 / (F)127.5 - (F)1.0);
+    F a2 = NP::st((F)n2 / (F)127.5 - (F)1.0);
+    F len = a0 * a0 + a1 * a1 + a2 * a2;
+    if (len > (F)0) len = NP::rsqrt_(len);
+    F N0 = NP::st(a0 * len), N1 = NP::st(a1 * len), N2 = NP::st(a2 * len);
+    F ndl = N0 * L0 + N1 * L1 + N2 * L2;
+    F diffuse = ndl > (F)0 ? ndl : (F)0;  // Math.max(dot, 0); NaN cannot arise from u8 inputs
+    F sc = (F)2 * ndl;
+    F r0 = NP::st(N0 * sc), r1 = NP::st(N1 * sc), r2 = NP::st(N2 * sc);
+    r0 = NP::st(r0 - L0);
+    r1 = NP::st(r1 - L1);
+    r2 = NP::st(r2 - L2);
+    F rl = r0 * r0 + r1 * r1 + r2 * r2;
+    if (rl > (F)0) rl = NP::rsqrt_(rl);
+    r0 = NP::st(r0 * rl);
+    r1 = NP::st(r1 * rl);
+    r2 = NP::st(r2 * rl);
+    F vdr = (F)0 * r0 + (F)0 * r1 + (F)1 * r2;  // dot(viewDir = (0,0,1), reflectDir)
+    F specular = (F)0.5 * NP::pow32(vdr > (F)0 ? vdr : (F)0);
+    F isum = (F)0.1 + diffuse + specular;
+    F intensity = isum < (F)1 ? isum : (F)1;
+    F depthFactor = (F)1 - (F)depth_u8 / (F)255;
+    F color = (F)255 * intensity * depthFactor;
+    unsigned char c = (unsigned char)to_u8_clamp(color);
     return make_uchar4(c, c, c, 255);
 }
 template <class NP>
@@ -430,22 +407,23 @@ RM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
 
 template <class NP, int ACCEL, int PK>
 __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderParams P) {
-    typedef typename NP::S S;
+    typedef typename NP::F F;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    const S o[3] = {(S)P.origin[0], (S)P.origin[1], (S)P.origin[2]};
-    const S MAX_DIST = (S)10, EPSILON = (S)0.001;
+    const double o[3] = {(double)P.origin[0], (double)P.origin[1], (double)P.origin[2]};
+    const double MAX_DIST = 10.0, EPSILON = 0.001;
     const int alg = P.algorithm;
-    const int maxSteps = (alg == RM_ALG_FIXED_STEP || alg == RM_ALG_ADAPTIVE_STEP) ? kMaxStepsFixed : kMaxStepsSphere;
-    const S stepSize = (S)P.step_size, overshoot = (S)P.overshoot;
+    const bool hitOnly = (alg == RM_ALG_FIXED_STEP || alg == RM_ALG_ADAPTIVE_STEP);  // return hit ? t : MAX_DIST
+    const int maxSteps = hitOnly ? kMaxStepsFixed : kMaxStepsSphere;
+    const double stepSize = P.step_size, overshoot = P.overshoot;
     const int bandH = P.y_end - P.y_start;
 
     Ray<NP> r;
     r.phase = PH_IDLE;
     r.cur = 0;
     r.nIv = 0;
-    IvList<NP> iv;  // only touched when ACCEL == BVH (lives in local memory)
+    IvList iv;  // only touched when ACCEL == BVH (lives in local memory)
     LaneStats st;
 
     // warp-uniform work-queue cursor
@@ -476,16 +454,13 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                 int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
                 int x = tx * kTileW + (k % kTileW);
                 int yl = ty * kTileH + (k / kTileW);
-                if (x < P.width && yl < bandH) {
+                if (x < P.width && yl < bandH) {  // edge tiles: out-of-range pixels are skipped
                     r.px = x;
                     r.py = yl;
                     r.phase = PH_NEW;
                 }
             }
             tilePos += take;
-            // lanes that drew an out-of-range pixel of an edge tile stay idle and try again
-            unsigned took = __ballot_sync(kFull, r.phase == PH_IDLE && rank < take);
-            (void)took;
             idle = __ballot_sync(kFull, r.phase == PH_IDLE);
         }
         if (__ballot_sync(kFull, r.phase != PH_IDLE) == 0u) break;  // queue drained and every ray retired
@@ -493,20 +468,20 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         // ---- (b) ray set-up (raymarcher.ts:73-88 + onRayMarchStart) ----
         if (r.phase == PH_NEW) {
             int y = P.y_start + r.py;
-            S v = ((S)y / (S)P.height - (S)0.5) * (S)2.0;
-            S u = ((S)r.px / (S)P.width - (S)0.5) * (S)2.0;
-            S a0 = NP::vst(u), a1 = NP::vst(v), a2 = (S)-1;
-            S b0 = NP::vst(a0 * (S)P.rot3[0] + a1 * (S)P.rot3[3] + a2 * (S)P.rot3[6]);
-            S b1 = NP::vst(a0 * (S)P.rot3[1] + a1 * (S)P.rot3[4] + a2 * (S)P.rot3[7]);
-            S b2 = NP::vst(a0 * (S)P.rot3[2] + a1 * (S)P.rot3[5] + a2 * (S)P.rot3[8]);
-            S len = b0 * b0 + b1 * b1 + b2 * b2;
-            if (len > (S)0) len = (S)1 / NP::sqrt_(len);
-            r.d[0] = NP::vst(b0 * len);
-            r.d[1] = NP::vst(b1 * len);
-            r.d[2] = NP::vst(b2 * len);
-            r.t = (S)0;
-            r.prevSDF = (S)0;
-            r.prevStep = (S)0;
+            double v = ((double)y / (double)P.height - 0.5) * 2.0;
+            double u = ((double)r.px / (double)P.width - 0.5) * 2.0;
+            double a0 = (double)f32r(u), a1 = (double)f32r(v), a2 = -1.0;
+            double b0 = (double)f32r(a0 * (double)P.rot3[0] + a1 * (double)P.rot3[3] + a2 * (double)P.rot3[6]);
+            double b1 = (double)f32r(a0 * (double)P.rot3[1] + a1 * (double)P.rot3[4] + a2 * (double)P.rot3[7]);
+            double b2 = (double)f32r(a0 * (double)P.rot3[2] + a1 * (double)P.rot3[5] + a2 * (double)P.rot3[8]);
+            double len = b0 * b0 + b1 * b1 + b2 * b2;
+            if (len > 0.0) len = 1.0 / sqrt(len);
+            r.d[0] = f32r(b0 * len);
+            r.d[1] = f32r(b1 * len);
+            r.d[2] = f32r(b2 * len);
+            r.t = 0.0;
+            r.prevSDF = 0.0;
+            r.prevStep = 0.0;
             r.sdf = 0;
             r.iters = 0;
             r.nSphere = 0;
@@ -514,10 +489,10 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             r.i = 0;
             r.done = false;
             r.cur = 0;
+            r.depth = 0.0;
             r.phase = PH_STEP;
-            r.depth = (S)0;
             if constexpr (ACCEL == RM_ACCEL_BVH) {
-                r.nIv = bvh_collect<NP>(P, o, r.d, iv, maxSteps + 1);
+                r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
                 if (r.nIv == 0) {  // {terminate:true} -> return MAX_DIST (sphereTracer.ts:38-40)
                     r.depth = MAX_DIST;
                     r.done = true;
@@ -529,30 +504,29 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         if (r.phase == PH_STEP) {
             while (!r.done) {
                 if (r.i >= maxSteps) {  // loop ran out of indices
-                    bool hitOnly = (alg == RM_ALG_FIXED_STEP || alg == RM_ALG_ADAPTIVE_STEP);
                     r.depth = hitOnly ? MAX_DIST : r.t;
                     r.done = true;
                     break;
                 }
-                S p[3] = {NP::vst(o[0] + r.d[0] * r.t), NP::vst(o[1] + r.d[1] * r.t), NP::vst(o[2] + r.d[2] * r.t)};
+                float p[3] = {f32r(o[0] + (double)r.d[0] * r.t), f32r(o[1] + (double)r.d[1] * r.t),
+                              f32r(o[2] + (double)r.d[2] * r.t)};
                 if constexpr (ACCEL != RM_ACCEL_NONE) {
-                    S skip;
+                    double skip;
                     if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP>(r, iv);
-                    else skip = octree_march<NP>(P, o, r, p);
-                    if (skip == (S)-1) {  // nothing left: `return MAX_DIST`
+                    else skip = octree_march(P.scene.oct, o, r.d, r.t, p);
+                    if (skip == -1.0) {  // nothing left: `return MAX_DIST`
                         r.depth = MAX_DIST;
                         r.done = true;
                         break;
-                    } else if (skip > (S)0) {
+                    } else if (skip > 0.0) {
                         r.t += skip;
                         if (r.t > MAX_DIST) {  // `break` out of the for loop
-                            bool hitOnly = (alg == RM_ALG_FIXED_STEP || alg == RM_ALG_ADAPTIVE_STEP);
                             r.depth = hitOnly ? MAX_DIST : r.t;
                             r.done = true;
                             break;
                         }
-                        r.prevSDF = (S)0;  // adaptiveStepV2.ts:75-76 (harmless for the other loops)
-                        r.prevStep = (S)0;
+                        r.prevSDF = 0.0;  // adaptiveStepV2.ts:75-76 (unused by the other loops)
+                        r.prevStep = 0.0;
                         r.i++;
                         continue;
                     }
@@ -565,14 +539,14 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             }
             if (r.phase == PH_STEP) {
                 // march finished with r.depth: hit position + normal taps (raymarcher.ts:94-102)
-                r.h[0] = NP::vst(o[0] + r.d[0] * r.depth);
-                r.h[1] = NP::vst(o[1] + r.d[1] * r.depth);
-                r.h[2] = NP::vst(o[2] + r.d[2] * r.depth);
+                r.h[0] = f32r(o[0] + (double)r.d[0] * r.depth);
+                r.h[1] = f32r(o[1] + (double)r.d[1] * r.depth);
+                r.h[2] = f32r(o[2] + (double)r.d[2] * r.depth);
                 if (r.depth >= MAX_DIST) {
-                    r.n0 = (S)0;
-                    r.n1 = (S)0;
-                    r.aux1 = (S)0;
-                    r.phase = PH_FINAL;  // finalize marker
+                    r.n0 = 0.f;
+                    r.n1 = 0.f;
+                    r.n2 = 0.f;
+                    r.phase = PH_FINAL;
                 } else {
                     r.q[0] = r.h[0];
                     r.q[1] = r.h[1];
@@ -584,14 +558,14 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
 
         // ---- (d) resolve the pending scene-distance query (scene.ts:144-190) ----
         const bool waiting = (r.phase >= PH_WAIT_MARCH && r.phase <= PH_WAIT_N3);
-        S dist = MAX_DIST;
+        F dist = (F)10;
         unsigned cnt = 0;
         bool needAll = false;
         if (waiting) {
             if constexpr (ACCEL == RM_ACCEL_NONE) {
                 needAll = true;
             } else if constexpr (ACCEL == RM_ACCEL_OCTREE) {
-                int ni = octree_find<NP>(P, r.q[0], r.q[1], r.q[2]);
+                int ni = octree_find(P.scene.oct, r.q);
                 if (ni < 0) {
                     needAll = true;  // outside the octree bounds: full evaluation (scene.ts:166)
                 } else {
@@ -599,13 +573,10 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                     int pc = nd->prim_count;
                     if (pc > 0) {
                         const int32_t* lp = P.scene.leaf_prims + nd->prim_first;
-                        for (int k = 0; k < pc; ++k) {
-                            S s = prim_sdf<NP, PK>(P, lp[k], r.q[0], r.q[1], r.q[2], r.nSphere, r.nBox);
-                            dist = jsmin<NP>(s, dist);
-                        }
+                        for (int k = 0; k < pc; ++k) dist = NP::fmin_(prim_sdf<NP, PK>(P, lp[k], r.q, r.nSphere, r.nBox), dist);
                         cnt = (unsigned)pc;
                     } else if (nd->is_empty) {
-                        dist = jsmin<NP>(dist, (S)nd->min_distance * (S)0.99);
+                        dist = (F)jsmin(10.0, nd->min_distance * 0.99);
                     }
                 }
             } else {  // BVH.getPrimitivesAt (bvh.ts:95-121): every leaf whose box contains p, left before right
@@ -616,15 +587,12 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                 while (sp > 0) {
                     int ni = stack[--sp];
                     const rm_bvh_node* nd = nodes + ni;
-                    if (!box_contains<NP>(nd->bmin, nd->bmax, r.q[0], r.q[1], r.q[2])) continue;
+                    if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
                     int left = nd->left, right = nd->right;
                     if (left < 0 && right < 0) {
                         const int32_t* lp = P.scene.leaf_prims + nd->prim_first;
                         int pc = nd->prim_count;
-                        for (int k = 0; k < pc; ++k) {
-                            S s = prim_sdf<NP, PK>(P, lp[k], r.q[0], r.q[1], r.q[2], r.nSphere, r.nBox);
-                            dist = jsmin<NP>(s, dist);
-                        }
+                        for (int k = 0; k < pc; ++k) dist = NP::fmin_(prim_sdf<NP, PK>(P, lp[k], r.q, r.nSphere, r.nBox), dist);
                         cnt += (unsigned)pc;
                     } else {
                         if (right >= 0 && sp < kBvhStack) stack[sp++] = right;  // popped after left
@@ -636,7 +604,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         }
         // dense all-primitives pass for the lanes that need it
         if (needAll) {
-            dist = scene_all_prims<NP, PK>(P, r.q[0], r.q[1], r.q[2]);
+            dist = scene_all_prims<NP, PK>(P, r.q);
             cnt = (unsigned)P.scene.n_prims;
             r.nSphere += P.scene.type_hist[0];
             r.nBox += P.scene.type_hist[1];
@@ -645,44 +613,32 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         // ---- (e) consume the query result ----
         if (waiting) {
             r.sdf += cnt;
+            const double dd = (double)dist;  // control arithmetic continues in double
             switch (r.phase) {
                 case PH_WAIT_MARCH: {
                     r.phase = PH_STEP;
+                    r.iters++;
                     if (alg == RM_ALG_SPHERE_TRACER) {  // sphereTracer.ts:67-74
-                        r.t += dist;
-                        r.iters++;
-                        if (dist < EPSILON || r.t > MAX_DIST) {
+                        r.t += dd;
+                        if (dd < EPSILON || r.t > MAX_DIST) {
                             r.depth = r.t;
                             r.done = true;
                         } else {
                             r.i++;
                         }
-                    } else if (alg == RM_ALG_FIXED_STEP) {  // fixedStep.ts:75-89
-                        r.iters++;
-                        if (dist < EPSILON) {
+                    } else if (hitOnly) {  // fixedStep.ts:75-89 / adaptiveStep.ts:75-96
+                        if (dd < EPSILON) {
                             r.depth = r.t;
                             r.done = true;
                         } else {
-                            r.t += stepSize;
-                            if (r.t > MAX_DIST) {
-                                r.depth = MAX_DIST;
-                                r.done = true;
+                            double step;
+                            if (alg == RM_ALG_FIXED_STEP) {
+                                step = stepSize;
+                            } else if (dd < 0.1) {  // NEAR_DIST
+                                step = 0.01;        // NEAR_STEP
                             } else {
-                                r.i++;
-                            }
-                        }
-                    } else if (alg == RM_ALG_ADAPTIVE_STEP) {  // adaptiveStep.ts:75-96
-                        r.iters++;
-                        if (dist < EPSILON) {
-                            r.depth = r.t;
-                            r.done = true;
-                        } else {
-                            S step;
-                            if (dist < (S)0.1) {
-                                step = (S)0.01;
-                            } else {
-                                step = (S)0.8 * dist;
-                                const S MIN_STEP = (S)0.1 * (S)0.25, MAX_STEP = (S)0.1 * (S)5.0;
+                                step = 0.8 * dd;  // STEP_SCALE
+                                const double MIN_STEP = 0.1 * 0.25, MAX_STEP = 0.1 * 5.0;
                                 if (step < MIN_STEP) step = MIN_STEP;
                                 if (step > MAX_STEP) step = MAX_STEP;
                             }
@@ -695,19 +651,18 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                             }
                         }
                     } else {  // V2 (adaptiveStepV2.ts:81-116) and V3 (adaptiveStepV3.ts:72-130)
-                        r.iters++;
-                        if (dist < EPSILON || r.t > MAX_DIST) {
+                        if (dd < EPSILON || r.t > MAX_DIST) {
                             r.depth = r.t;
                             r.done = true;
-                        } else if (r.i == 0 || r.prevSDF == (S)0) {
-                            r.t += dist;
-                            r.prevSDF = dist;
-                            r.prevStep = dist;
+                        } else if (r.i == 0 || r.prevSDF == 0.0) {
+                            r.t += dd;
+                            r.prevSDF = dd;
+                            r.prevStep = dd;
                             r.i++;
-                        } else if (r.prevStep <= (r.prevSDF + dist)) {
-                            S step = dist * overshoot;
+                        } else if (r.prevStep <= (r.prevSDF + dd)) {
+                            double step = dd * overshoot;
                             r.t += step;
-                            r.prevSDF = dist;
+                            r.prevSDF = dd;
                             r.prevStep = step;
                             r.i++;
                         } else if (alg == RM_ALG_ADAPTIVE_STEP_V2) {
@@ -716,13 +671,13 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                             r.prevStep = r.prevSDF;
                             r.i++;
                         } else {  // V3: step back, take the bridging tap d3
-                            S originalPos = r.t - r.prevStep;
+                            double originalPos = r.t - r.prevStep;
                             r.t = originalPos + r.prevSDF;
                             r.aux0 = originalPos;
-                            r.aux1 = dist;  // newSDF
-                            r.q[0] = NP::vst(o[0] + r.d[0] * r.t);
-                            r.q[1] = NP::vst(o[1] + r.d[1] * r.t);
-                            r.q[2] = NP::vst(o[2] + r.d[2] * r.t);
+                            r.aux1 = dd;  // newSDF
+                            r.q[0] = f32r(o[0] + (double)r.d[0] * r.t);
+                            r.q[1] = f32r(o[1] + (double)r.d[1] * r.t);
+                            r.q[2] = f32r(o[2] + (double)r.d[2] * r.t);
                             r.phase = PH_WAIT_V3B;
                         }
                     }
@@ -730,7 +685,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                 }
                 case PH_WAIT_V3B: {  // adaptiveStepV3.ts:113-134
                     r.iters++;
-                    S newSDF = r.aux1, d3 = dist;
+                    double newSDF = r.aux1, d3 = dd;
                     if (r.prevSDF + newSDF + d3 >= r.prevStep) {
                         r.t = r.aux0 + r.prevStep + newSDF;
                         r.prevSDF = newSDF;
@@ -745,31 +700,30 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                     break;
                 }
                 case PH_WAIT_N0:  // raymarcher.ts:124-128
-                    r.aux0 = dist;
-                    r.q[0] = NP::vst(r.h[0] - (S)0.01);
-                    r.q[1] = r.h[1];
-                    r.q[2] = r.h[2];
+                    r.nd = dist;
+                    r.q[0] = f32r((double)r.h[0] - 0.01);
                     r.phase = PH_WAIT_N1;
                     break;
                 case PH_WAIT_N1:
-                    r.n0 = NP::vst(r.aux0 - dist);
+                    r.n0 = (float)(r.nd - dist);  // n[0] = d - d(p - e_x): Float32Array store
                     r.q[0] = r.h[0];
-                    r.q[1] = NP::vst(r.h[1] - (S)0.01);
+                    r.q[1] = f32r((double)r.h[1] - 0.01);
                     r.phase = PH_WAIT_N2;
                     break;
                 case PH_WAIT_N2:
-                    r.n1 = NP::vst(r.aux0 - dist);
+                    r.n1 = (float)(r.nd - dist);
                     r.q[1] = r.h[1];
-                    r.q[2] = NP::vst(r.h[2] - (S)0.01);
+                    r.q[2] = f32r((double)r.h[2] - 0.01);
                     r.phase = PH_WAIT_N3;
                     break;
                 default: {  // PH_WAIT_N3: normalise (raymarcher.ts:131-133)
-                    S n2 = NP::vst(r.aux0 - dist);
-                    S len = r.n0 * r.n0 + r.n1 * r.n1 + n2 * n2;
-                    if (len > (S)0) len = (S)1 / NP::sqrt_(len);
-                    r.n0 = NP::vst(r.n0 * len);
-                    r.n1 = NP::vst(r.n1 * len);
-                    r.aux1 = NP::vst(n2 * len);
+                    r.n2 = (float)(r.nd - dist);
+                    F x = (F)r.n0, y = (F)r.n1, z = (F)r.n2;
+                    F len = x * x + y * y + z * z;
+                    if (len > (F)0) len = NP::rsqrt_(len);
+                    r.n0 = (float)(x * len);
+                    r.n1 = (float)(y * len);
+                    r.n2 = (float)(z * len);
                     r.phase = PH_FINAL;
                     break;
                 }
@@ -779,10 +733,10 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         // ---- (f) finalize: quantise, shade, store, accumulate diagnostics (raymarcher.ts:103-106) ----
         if (r.phase == PH_FINAL) {
             size_t idx = (size_t)r.py * P.width + r.px;
-            unsigned nb0 = to_u8_clamp<NP>((r.n0 + (S)1) * (S)0.5 * (S)255);
-            unsigned nb1 = to_u8_clamp<NP>((r.n1 + (S)1) * (S)0.5 * (S)255);
-            unsigned nb2 = to_u8_clamp<NP>((r.aux1 + (S)1) * (S)0.5 * (S)255);
-            unsigned db = to_u8_clamp<NP>(r.depth);
+            unsigned nb0 = to_u8_clamp(((F)r.n0 + (F)1) * (F)0.5 * (F)255);
+            unsigned nb1 = to_u8_clamp(((F)r.n1 + (F)1) * (F)0.5 * (F)255);
+            unsigned nb2 = to_u8_clamp(((F)r.n2 + (F)1) * (F)0.5 * (F)255);
+            unsigned db = to_u8_clamp(r.depth);
             unsigned sdf16 = r.sdf & 0xffffu, it16 = r.iters & 0xffffu;
             P.depth[idx] = (uint8_t)db;
             P.normal[3 * idx + 0] = (uint8_t)nb0;
@@ -793,6 +747,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[idx] = shade_pixel<NP>(P.shader, db, nb0, nb1, nb2, sdf16, it16);
             if (P.rgba2) reinterpret_cast<uchar4*>(P.rgba2)[idx] = shade_pixel<NP>(P.shader2, db, nb0, nb1, nb2, sdf16, it16);
             if (P.depth_f32) P.depth_f32[idx] = (float)r.depth;
+            if (P.depth_f64) P.depth_f64[idx] = r.depth;
             if (P.sdf_u32) P.sdf_u32[idx] = r.sdf;
             st.sum_sdf += sdf16;
             st.sum_iters += it16;

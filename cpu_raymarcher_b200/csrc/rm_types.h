@@ -68,6 +68,7 @@ struct RenderParams {
     uint8_t* rgba2;
     float* depth_f32;
     uint32_t* sdf_u32;
+    double* depth_f64;
     DevStats* stats;
 };
 

@@ -27,6 +27,7 @@ class Frame:
     rgba_analytics: np.ndarray | None = None
     depth_f32: np.ndarray | None = None
     sdf_u32: np.ndarray | None = None
+    depth_f64: np.ndarray | None = None
 
 
 def build_bvh(types, w2l, params, flags: int = 0):
@@ -141,7 +142,8 @@ class Context:
         if extras:
             f.depth_f32 = np.zeros(n, np.float32)
             f.sdf_u32 = np.zeros(n, np.uint32)
-            res.depth_f32, res.sdf_eval_u32 = _ptr(f.depth_f32), _ptr(f.sdf_u32)
+            f.depth_f64 = np.zeros(n, np.float64)
+            res.depth_f32, res.sdf_eval_u32, res.depth_f64 = _ptr(f.depth_f32), _ptr(f.sdf_u32), _ptr(f.depth_f64)
         self._check(self._L.rm_render(self._h, C.byref(rq), C.byref(res)))
         return f
 

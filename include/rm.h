@@ -128,6 +128,7 @@ typedef struct rm_result {
     uint8_t* rgba_analytics; /* [4*W*th] optional: request.shader_analytics output               */
     float* depth_f32;        /* [W*th]   optional extension: unquantised rayMarch return         */
     uint32_t* sdf_eval_u32;  /* [W*th]   optional extension: un-wrapped SDF-call count           */
+    double* depth_f64;       /* [W*th]   optional extension: rayMarch return as a double (exact in the validation build) */
 } rm_result;
 
 /* Diagnostics of the last completed rm_render / rm_render_device on this context. */

@@ -26,9 +26,11 @@ inline bool& length_uses_hypot() {
     return v;
 }
 
+// NOTE: there is deliberately no non-const operator[] returning float&: `v[i] + 1` would then be
+// evaluated in float arithmetic by C++'s promotion rules, whereas JS reads a Float32Array element as
+// a double.  Reads always go through the double-returning accessor; stores go through `.e[i] =`.
 struct vec3 {
     float e[3];
-    float& operator[](int i) { return e[i]; }
     double operator[](int i) const { return (double)e[i]; }  // reads promote exactly
 };
 struct mat3 {
@@ -36,7 +38,6 @@ struct mat3 {
 };
 struct mat4 {
     float e[16];
-    float& operator[](int i) { return e[i]; }
     double operator[](int i) const { return (double)e[i]; }
 };
 

@@ -30,19 +30,20 @@ for preset, syn, accel, alg, pitch, yaw in cases:
     ex = dict(depth=np.array_equal(fv.depth, ref.depth), normal=np.array_equal(fv.normal, ref.normal),
               sdf=np.array_equal(fv.sdfEval, ref.sdfEval), iters=np.array_equal(fv.iters, ref.iters),
               sdf32=np.array_equal(fv.sdf_u32, ref.sdf_full),
-              hit=np.array_equal(fv.depth_f32 < 10, ref.depth_f64.astype(np.float32) < 10),
+              depth64=np.array_equal(fv.depth_f64.view(np.uint64), ref.depth_f64.view(np.uint64)),
+              iters32=np.array_equal(fv.sdf_u32 * 0 + fv.iters, ref.iters),
               phong=np.array_equal(fv.rgba, po.shade("phong", ref.depth, ref.normal, ref.sdfEval, ref.iters, W, H)),
               heat=np.array_equal(fv.rgba_analytics, po.shade("sdf-heatmap", ref.depth, ref.normal, ref.sdfEval, ref.iters, W, H)))
     ff = fast.on_message(job, shader="phong", extras=True)
     kf = fast.stats()["kernel_ms"]
     hit_ref = ref.depth_f64 < 10
-    hit_f = ff.depth_f32 < 10
+    hit_f = ff.depth_f64 < 10
     agree_hit = (hit_ref == hit_f)
     ref_rgb = po.shade("phong", ref.depth, ref.normal, ref.sdfEval, ref.iters, W, H).reshape(-1, 4)[:, :3].astype(int)
     rgb_ok = (np.abs(ff.rgba.reshape(-1, 4)[:, :3].astype(int) - ref_rgb).max(1) <= 1)
     nrm_ok = (np.abs(ff.normal.reshape(-1, 3).astype(int) - ref.normal.reshape(-1, 3).astype(int)).max(1) <= 1)
     both = hit_ref & hit_f
-    rel = np.abs(ff.depth_f32[both] - ref.depth_f64[both]) / np.maximum(np.abs(ref.depth_f64[both]), 1e-9) if both.any() else np.zeros(1)
+    rel = np.abs(ff.depth_f64[both] - ref.depth_f64[both]) / np.maximum(np.abs(ref.depth_f64[both]), 1e-9) if both.any() else np.zeros(1)
     ok_px = agree_hit & rgb_ok & nrm_ok
     allv = all(ex.values())
     fast_frac = ok_px.mean()
