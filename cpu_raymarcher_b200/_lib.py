@@ -46,7 +46,8 @@ class Request(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("y_start", C.c_int32), ("y_end", C.c_int32),
                 ("time", C.c_double), ("rot3", C.c_float * 9), ("origin", C.c_float * 3), ("algorithm", C.c_int32),
                 ("step_size", C.c_double), ("overshoot_factor", C.c_double), ("shader", C.c_int32),
-                ("shader_analytics", C.c_int32)]
+                ("shader_analytics", C.c_int32), ("stripe_rows", C.c_int32), ("stripe_count", C.c_int32),
+                ("stripe_index", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -59,14 +60,14 @@ class Stats(C.Structure):
     _fields_ = [("n_pixels", C.c_uint64), ("sum_sdf", C.c_uint64), ("sum_iters", C.c_uint64), ("max_sdf", C.c_uint32),
                 ("min_sdf", C.c_uint32), ("max_iters", C.c_uint32), ("min_iters", C.c_uint32),
                 ("sum_sdf_full", C.c_uint64), ("sum_iters_full", C.c_uint64), ("evals_by_type", C.c_uint64 * 3),
-                ("n_hit", C.c_uint64), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
+                ("n_hit", C.c_uint64), ("algorithmic_flops", C.c_double), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
                 ("device", C.c_int32)]
 
 
 # every symbol include/rm.h declares
 EXPORTS = ["rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_upload_scene",
            "rm_build_bvh", "rm_build_octree", "rm_render", "rm_render_device", "rm_stats", "rm_shade", "rm_alloc",
-           "rm_free", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
+           "rm_free", "rm_probe_fp32_peak", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
 
 _LIB = None
 
@@ -93,6 +94,7 @@ def lib():
         L.rm_render_device.argtypes = [vp, C.POINTER(Request), C.POINTER(Result), vp]
         L.rm_stats.argtypes = [vp, C.POINTER(Stats)]
         L.rm_shade.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32]
+        L.rm_probe_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.rm_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.rm_free.argtypes = [vp, vp]
         L.rm_ipc_export.argtypes = [vp, vp, vp]

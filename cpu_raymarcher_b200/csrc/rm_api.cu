@@ -120,6 +120,9 @@ int validate_request(rm_ctx* c, const rm_request* rq) {
     if (rq->shader < RM_SHADER_NONE || rq->shader > RM_SHADER_ITERATION_HEATMAP) return fail(c, RM_ERR_ARG, "bad shader %d", rq->shader);
     if (rq->shader_analytics < RM_SHADER_NONE || rq->shader_analytics > RM_SHADER_ITERATION_HEATMAP)
         return fail(c, RM_ERR_ARG, "bad analytics shader %d", rq->shader_analytics);
+    if (rq->stripe_count > 1 && (rq->stripe_rows <= 0 || rq->stripe_rows % kTileH != 0 || rq->stripe_index < 0 || rq->stripe_index >= rq->stripe_count))
+        return fail(c, RM_ERR_ARG, "bad stripe spec rows=%d count=%d index=%d (rows must be a positive multiple of %d)", rq->stripe_rows, rq->stripe_count, rq->stripe_index, kTileH);
+    if (rq->stripe_count < 0) return fail(c, RM_ERR_ARG, "bad stripe_count %d", rq->stripe_count);
     return RM_OK;
 }
 
@@ -149,7 +152,27 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.shader2 = rq->shader_analytics;
     P.length_sqrt = (c->flags & RM_F_LENGTH_SQRT) ? 1 : 0;
     P.tiles_x = (rq->width + kTileW - 1) / kTileW;
-    P.n_tiles = P.tiles_x * ((bandH + kTileH - 1) / kTileH);
+    uint64_t ownedRows = (uint64_t)bandH;
+    if (rq->stripe_count > 1) {
+        P.stripe_rows = rq->stripe_rows;
+        P.stripe_count = rq->stripe_count;
+        P.stripe_index = rq->stripe_index;
+        const int nStripes = (bandH + P.stripe_rows - 1) / P.stripe_rows;
+        const int nOwned = nStripes > P.stripe_index ? (nStripes - P.stripe_index + P.stripe_count - 1) / P.stripe_count : 0;
+        P.tiles_per_stripe = P.tiles_x * (P.stripe_rows / kTileH);
+        P.n_tiles = nOwned * P.tiles_per_stripe;
+        ownedRows = 0;
+        for (int sIdx = P.stripe_index; sIdx < nStripes; sIdx += P.stripe_count) {
+            int y0 = sIdx * P.stripe_rows, y1 = y0 + P.stripe_rows < bandH ? y0 + P.stripe_rows : bandH;
+            ownedRows += (uint64_t)(y1 - y0);
+        }
+    } else {
+        P.stripe_rows = kTileH;
+        P.stripe_count = 1;
+        P.stripe_index = 0;
+        P.tiles_per_stripe = P.tiles_x;
+        P.n_tiles = P.tiles_x * ((bandH + kTileH - 1) / kTileH);
+    }
     P.depth = out->depth;
     P.normal = out->normal;
     P.sdf = out->sdf_eval;
@@ -182,7 +205,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     const DevStats& s = *c->h_stats;
     rm_stats_t& L = c->last;
     std::memset(&L, 0, sizeof(L));
-    L.n_pixels = (uint64_t)rq->width * (uint64_t)bandH;
+    L.n_pixels = (uint64_t)rq->width * ownedRows;
     L.sum_sdf = s.sum_sdf;
     L.sum_iters = s.sum_iters;
     L.max_sdf = s.max_sdf;
@@ -195,6 +218,11 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     L.evals_by_type[1] = s.evals_box;
     L.evals_by_type[2] = s.evals_torus;
     L.n_hit = s.n_hit;
+    {
+        const bool ts = !(c->flags & RM_F_VALIDATE_FP64) && c->scene.prim_kind == PK_TSPHERE;
+        L.algorithmic_flops = ts ? 11.0 * (double)s.evals_sphere
+                                 : 26.0 * (double)s.evals_sphere + 38.0 * (double)s.evals_box + 29.0 * (double)s.evals_torus;
+    }
     L.kernel_ms = ms;
     L.n_launches = launches;
     L.device = c->device;
@@ -513,6 +541,17 @@ int rm_shade(rm_ctx* c, int32_t shader, uint8_t* rgba, const uint8_t* depth, con
     if (e != 0) return fail(c, RM_ERR_CUDA, "shade launch: %s", cudaGetErrorString((cudaError_t)e));
     CU(c, cudaMemcpyAsync(rgba, d + oR, 4 * np, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return RM_OK;
+}
+
+int rm_probe_fp32_peak(rm_ctx* c, double* tflops) {
+    if (!c || !tflops) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->d_frame, (size_t)c->n_sms * 8 * 256 * sizeof(float), false))) return rc;
+    int e = probe_fp32_peak(c->n_sms, c->stream, (float*)c->d_frame.p, tflops);
+    if (e != 0) return fail(c, RM_ERR_CUDA, "fp32 probe: %s", cudaGetErrorString((cudaError_t)e));
     return RM_OK;
 }
 

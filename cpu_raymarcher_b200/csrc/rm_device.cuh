@@ -451,9 +451,11 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             int rank = __popc(idle & lt_mask);
             if (r.phase == PH_IDLE && rank < take) {
                 int k = tilePos + rank;
-                int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+                // tile -> (owned stripe, tile row inside the stripe, tile column); stripes interleave across GPUs
+                int os = tile / P.tiles_per_stripe, rem = tile - os * P.tiles_per_stripe;
+                int tyIn = rem / P.tiles_x, tx = rem - tyIn * P.tiles_x;
                 int x = tx * kTileW + (k % kTileW);
-                int yl = ty * kTileH + (k / kTileW);
+                int yl = (os * P.stripe_count + P.stripe_index) * P.stripe_rows + tyIn * kTileH + (k / kTileW);
                 if (x < P.width && yl < bandH) {  // edge tiles: out-of-range pixels are skipped
                     r.px = x;
                     r.py = yl;

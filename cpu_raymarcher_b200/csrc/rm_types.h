@@ -59,6 +59,7 @@ struct RenderParams {
     int32_t shader, shader2;
     int32_t length_sqrt;  // validation: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot
     int32_t n_tiles, tiles_x;
+    int32_t stripe_rows, stripe_count, stripe_index, tiles_per_stripe;  // row-stripe interleave (multi-GPU)
     // outputs (device pointers; optional ones may be null)
     uint8_t* depth;
     uint8_t* normal;
@@ -87,5 +88,6 @@ int launch_render_val(const RenderParams& p, int n_sms, void* stream);
 int launch_render_fast(const RenderParams& p, int n_sms, void* stream);
 int launch_shade_val(const ShadeParams& p, void* stream);
 int launch_shade_fast(const ShadeParams& p, void* stream);
+int probe_fp32_peak(int n_sms, void* stream, float* scratch, double* tflops);
 
 }  // namespace rm

@@ -1,0 +1,262 @@
+"""Row-stripe sharding of one frame over the GPUs of a box — one process per GPU (torchrun).
+
+The reference's only parallelism is row-band data parallelism over <= 4 web workers with the tiles
+copied into the full-frame buffers on the main thread and the diagnostics summed serially
+(src/main.ts:318-321,444-471,527-543).  Here:
+
+  * scene "broadcast" (each reference worker rebuilds the scene, raymarchWorker.ts:37-38): rank 0 builds
+    the primitive arrays and the flattened BVH/octree once; one NCCL broadcast of the packed blob;
+    every rank uploads it and keeps it resident;
+  * work split: rows are dealt to ranks as interleaved 8-row stripes (a contiguous band per rank —
+    the reference's rule — leaves sky rows on one GPU and dense rows on another);
+  * tile "gather" (main.ts:461-468): FUSED into the render kernel.  Rank 0 owns the full-frame planes;
+    every other rank maps them through CUDA IPC and its render kernel stores its pixels straight into
+    rank 0's HBM over NVLink — no staging buffer, no separate gather collective;
+  * diagnostics "reduce" (main.ts:527-543): each kernel's epilogue leaves 12 words per GPU; one NCCL
+    all-reduce per operator (sum / max / min) combines them.
+
+With world_size == 1 every collective disappears and this is a thin wrapper over rm_render_device.
+`render_band` can be replaced (tests inject a CPU renderer to exercise the partition / merge logic
+under gloo without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+from .renderer import Context
+
+STRIPE_ROWS = 8
+
+
+def stripe_rows_of(rank: int, world: int, height: int, stripe_rows: int = STRIPE_ROWS):
+    """Image rows owned by `rank`: stripes rank, rank+world, ... of `stripe_rows` rows each."""
+    rows = []
+    n_stripes = (height + stripe_rows - 1) // stripe_rows
+    for s in range(rank, n_stripes, world):
+        rows.extend(range(s * stripe_rows, min((s + 1) * stripe_rows, height)))
+    return np.asarray(rows, np.int32)
+
+
+def plane_layout(width: int, height: int):
+    """Byte offsets of the full-frame planes inside one device allocation (256-byte aligned sections)."""
+    n = width * height
+    al = lambda x: (x + 255) & ~255  # noqa: E731
+    off, lay = 0, {}
+    for name, size in (("depth", n), ("normal", 3 * n), ("sdf", 2 * n), ("iters", 2 * n), ("rgba", 4 * n)):
+        lay[name] = off
+        off += al(size)
+    lay["total"] = off
+    return lay
+
+
+def reduce_stats(stats_list):
+    """Combine per-rank diagnostics the way main.ts:527-543 would over the whole frame."""
+    out = dict(stats_list[0])
+    for s in stats_list[1:]:
+        for k in ("n_pixels", "sum_sdf", "sum_iters", "sum_sdf_full", "sum_iters_full", "n_hit", "algorithmic_flops", "n_launches"):
+            out[k] += s[k]
+        for k in ("max_sdf", "max_iters"):
+            out[k] = max(out[k], s[k])
+        for k in ("min_sdf", "min_iters"):
+            out[k] = min(out[k], s[k])
+        out["evals_by_type"] = [a + b for a, b in zip(out["evals_by_type"], s["evals_by_type"])]
+        out["kernel_ms"] = max(out["kernel_ms"], s["kernel_ms"])
+    return out
+
+
+class FrameSharder:
+    def __init__(self, worker, rank: int = 0, world: int = 1, local_rank: int = 0):
+        self.worker = worker
+        self.ctx: Context = worker.ctx
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.frame_ptr = None      # base of the full-frame planes this rank writes into (local on rank 0, peer-mapped elsewhere)
+        self.frame_owned = False
+        self.layout = None
+        self.size = None
+
+    # ------------------------------------------------------------------ scene
+    def setup_scene(self, job: dict):
+        if self.world == 1:
+            self.worker._ensure_scene(int(job.get("scenePresetIndex", 0)), job.get("accelerationStructure", "None"),
+                                      job.get("synthetic"))
+            return
+        import torch
+        import torch.distributed as dist
+        from .renderer import build_bvh, build_octree
+        from .scene import Scene
+
+        accel = job.get("accelerationStructure", "None")
+        accel = accel if accel in ("Octree", "BVH") else "None"
+        dev = torch.device("cuda", self.local_rank)
+        if self.rank == 0:
+            sc = Scene(accel)
+            if job.get("synthetic"):
+                sc.load_synthetic(*job["synthetic"])
+            else:
+                sc.load_preset(int(job.get("scenePresetIndex", 0)))
+            t, m, q = sc.primitives.arrays()
+            parts = [t.tobytes(), m.tobytes(), q.tobytes()]
+            n_nodes = 0
+            if accel != "None":
+                nodes, n_nodes, leaf = (build_bvh if accel == "BVH" else build_octree)(t, m, q, self.ctx.flags)
+                node_size = C.sizeof(_lib.BvhNode if accel == "BVH" else _lib.OctreeNode)
+                parts += [bytes(C.string_at(C.addressof(nodes), n_nodes * node_size)), leaf.tobytes()]
+            hdr = np.array([len(t), n_nodes] + [len(p) for p in parts] + [0] * (6 - len(parts)), np.int64)
+            blob = np.frombuffer(b"".join(parts), np.uint8)
+        else:
+            hdr = np.zeros(8, np.int64)
+            blob = None
+        hdr_t = torch.from_numpy(hdr.copy()).to(dev)
+        dist.broadcast(hdr_t, src=0)
+        hdr = hdr_t.cpu().numpy()
+        total = int(hdr[2:].sum())
+        blob_t = torch.from_numpy(blob.copy()).to(dev) if self.rank == 0 else torch.empty(total, dtype=torch.uint8, device=dev)
+        dist.broadcast(blob_t, src=0)  # NCCL over NVLink: primitives + flattened acceleration structure
+        raw = blob_t.cpu().numpy().tobytes()
+        n, n_nodes = int(hdr[0]), int(hdr[1])
+        sizes = [int(x) for x in hdr[2:] if x > 0]
+        offs = np.cumsum([0] + sizes)
+        t = np.frombuffer(raw[offs[0]:offs[1]], np.uint8)
+        m = np.frombuffer(raw[offs[1]:offs[2]], np.float32).reshape(n, 16)
+        q = np.frombuffer(raw[offs[2]:offs[3]], np.float64).reshape(n, 4)
+        if accel != "None":
+            node_t = _lib.BvhNode if accel == "BVH" else _lib.OctreeNode
+            nodes = (node_t * n_nodes).from_buffer_copy(raw[offs[3]:offs[4]])
+            leaf = np.frombuffer(raw[offs[4]:offs[5]], np.int32)
+            self.ctx.upload_scene(t, m, q, accel, nodes=nodes, n_nodes=n_nodes, leaf=leaf)
+        else:
+            self.ctx.upload_scene(t, m, q, accel)
+        sc = Scene(accel)
+        self.worker.scene = sc
+        self.worker._scene_key = (int(job.get("scenePresetIndex", 0)), job.get("synthetic"), accel)
+
+    # ------------------------------------------------------------------ frame planes
+    def _ensure_frame(self, width: int, height: int):
+        if self.size == (width, height):
+            return
+        self.release()
+        self.layout = plane_layout(width, height)
+        self.size = (width, height)
+        if self.world == 1:
+            self.frame_ptr = self.ctx.alloc(self.layout["total"])
+            self.frame_owned = True
+            return
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.local_rank)
+        if self.rank == 0:
+            self.frame_ptr = self.ctx.alloc(self.layout["total"])
+            self.frame_owned = True
+            handle = np.frombuffer(self.ctx.ipc_export(self.frame_ptr), np.uint8).copy()
+        else:
+            handle = np.zeros(64, np.uint8)
+        h_t = torch.from_numpy(handle).to(dev)
+        dist.broadcast(h_t, src=0)
+        if self.rank != 0:
+            self.frame_ptr = self.ctx.ipc_open(h_t.cpu().numpy().tobytes())  # rank 0's planes, reachable over NVLink
+            self.frame_owned = False
+
+    def release(self):
+        if self.frame_ptr is not None:
+            if self.frame_owned:
+                self.ctx.free(self.frame_ptr)
+            else:
+                self.ctx.ipc_close(self.frame_ptr)
+        self.frame_ptr = None
+
+    def _result(self, shader):
+        lay, base = self.layout, self.frame_ptr
+        res = _lib.Result()
+        res.depth, res.normal = base + lay["depth"], base + lay["normal"]
+        res.sdf_eval, res.iters = base + lay["sdf"], base + lay["iters"]
+        if shader is not None:
+            res.rgba = base + lay["rgba"]
+        return res
+
+    def _request(self, job: dict, shader):
+        scene = self.worker.scene
+        cam = job.get("camera", {})
+        scene.camera.set_angles(float(cam.get("pitch", 0.0)), float(cam.get("yaw", 0.0)))
+        W, H = int(job["width"]), int(job["height"])
+        return Context.make_request(W, H, scene.camera.get_rotation_matrix3(), scene.camera.get_position(),
+                                    algorithm=job.get("algorithm", "sphere-tracer"), y_start=0, y_end=H,
+                                    step_size=float(job.get("stepSize") or 0.1), overshoot=float(job.get("overshootFactor") or 1.2),
+                                    shader=shader, time=float(job.get("time", 0.0)),
+                                    stripes=(STRIPE_ROWS, self.world, self.rank) if self.world > 1 else None)
+
+    # ------------------------------------------------------------------ one frame, device-resident
+    def render_frame(self, job: dict, shader=None) -> dict:
+        """Every rank renders its stripes straight into rank 0's planes; returns frame-level diagnostics."""
+        W, H = int(job["width"]), int(job["height"])
+        self._ensure_frame(W, H)
+        rq = self._request(job, shader)
+        self.ctx.render_device(rq, self._result(shader))  # synchronises this rank's stream
+        st = self.ctx.stats()
+        st["n_prims"] = self.ctx.n_prims
+        if self.world == 1:
+            st["frame_ms"] = st["kernel_ms"]
+            st["kernel_ms_max"] = st["kernel_ms"]
+            return st
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.local_rank)
+        sums = torch.tensor([st["n_pixels"], st["sum_sdf"], st["sum_iters"], st["sum_sdf_full"], st["sum_iters_full"], st["n_hit"],
+                             st["n_launches"]] + list(st["evals_by_type"]), dtype=torch.int64, device=dev)
+        fsum = torch.tensor([st["algorithmic_flops"]], dtype=torch.float64, device=dev)
+        maxs = torch.tensor([st["max_sdf"], st["max_iters"], int(st["kernel_ms"] * 1e6)], dtype=torch.int64, device=dev)
+        mins = torch.tensor([st["min_sdf"], st["min_iters"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mins, op=dist.ReduceOp.MIN)  # also orders every rank's peer stores before rank 0 reads the frame
+        s, mx, mn = sums.tolist(), maxs.tolist(), mins.tolist()
+        st.update(n_pixels=s[0], sum_sdf=s[1], sum_iters=s[2], sum_sdf_full=s[3], sum_iters_full=s[4], n_hit=s[5], n_launches=s[6],
+                  evals_by_type=s[7:10], algorithmic_flops=float(fsum.item()), max_sdf=mx[0], max_iters=mx[1], min_sdf=mn[0],
+                  min_iters=mn[1])
+        st["kernel_ms_max"] = mx[2] / 1e6
+        st["frame_ms"] = st["kernel_ms_max"]  # the gather is fused into the kernel: the slowest rank's kernel is the frame
+        return st
+
+    def download_frame(self, shader=None) -> dict:
+        """Rank 0: copy the assembled full-frame planes to host arrays (the reference's frame buffers, main.ts:324-329)."""
+        W, H = self.size
+        n = W * H
+        out = {"depth": np.empty(n, np.uint8), "normal": np.empty(3 * n, np.uint8), "sdfEval": np.empty(n, np.uint16),
+               "iters": np.empty(n, np.uint16)}
+        if shader is not None:
+            out["rgba"] = np.empty(4 * n, np.uint8)
+        for k, name in (("depth", "depth"), ("normal", "normal"), ("sdfEval", "sdf"), ("iters", "iters"), ("rgba", "rgba")):
+            if k in out:
+                self.ctx.memcpy_d2h(out[k], self.frame_ptr + self.layout[name])
+        return out
+
+    # ------------------------------------------------------------------ end-to-end frames (host buffers)
+    def e2e_frames(self, job: dict, shader, steps: int = 3) -> dict:
+        """The same frame through the reference-facing call with HOST buffers: request in, planes out.
+        world == 1: RaymarchWorker.on_message (rm_render).  world > 1: fused-gather render + rank 0 D2H."""
+        W, H = int(job["width"]), int(job["height"])
+        n = W * H
+        d2h = n * (1 + 3 + 2 + 2 + (4 if shader else 0))
+        h2d = C.sizeof(_lib.Request)
+        if self.world == 1:
+            self.worker.on_message(job, shader=shader)  # warm-up (staging buffers)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.worker.on_message(job, shader=shader)
+            ms = (time.perf_counter() - t0) * 1e3 / steps
+            return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h}
+        import torch.distributed as dist
+        self.render_frame(job, shader)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.render_frame(job, shader)
+            if self.rank == 0:
+                self.download_frame(shader)
+            dist.barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        return {"ms_per_frame": ms, "h2d_bytes": h2d * self.world, "d2h_bytes": d2h}

@@ -112,7 +112,7 @@ class Context:
     # ---- render ----
     @staticmethod
     def make_request(width, height, rot3, origin, algorithm="sphere-tracer", y_start=0, y_end=None, step_size=0.1,
-                     overshoot=1.2, shader=None, shader_analytics=None, time=0.0) -> _lib.Request:
+                     overshoot=1.2, shader=None, shader_analytics=None, time=0.0, stripes=None) -> _lib.Request:
         rq = _lib.Request()
         rq.width, rq.height = width, height
         rq.y_start, rq.y_end = y_start, (height if y_end is None else y_end)
@@ -123,6 +123,8 @@ class Context:
         rq.step_size, rq.overshoot_factor = step_size, overshoot
         rq.shader = SHADERS[shader] if not isinstance(shader, int) else shader
         rq.shader_analytics = SHADERS[shader_analytics] if not isinstance(shader_analytics, int) else shader_analytics
+        if stripes is not None:  # (rows per stripe, number of GPUs, this GPU's index)
+            rq.stripe_rows, rq.stripe_count, rq.stripe_index = stripes
         return rq
 
     def render(self, rq: _lib.Request, extras: bool = False) -> Frame:
@@ -166,6 +168,12 @@ class Context:
                                      _ptr(np.ascontiguousarray(sdf, np.uint16)),
                                      _ptr(np.ascontiguousarray(iters, np.uint16)), width, height))
         return out
+
+    def probe_fp32_peak(self) -> float:
+        """Measured FFMA peak of this device in TFLOP/s (roofline denominator)."""
+        v = C.c_double(0.0)
+        self._check(self._L.rm_probe_fp32_peak(self._h, C.byref(v)))
+        return v.value
 
     # ---- multi-GPU plumbing ----
     def alloc(self, nbytes: int) -> int:

@@ -115,6 +115,11 @@ typedef struct rm_request {
     double overshoot_factor; /* AdaptiveStepV2/V3 ctor, default 1.2 */
     int32_t shader;           /* rm_shader for result.rgba           (RM_SHADER_NONE: skip) */
     int32_t shader_analytics; /* rm_shader for result.rgba_analytics (main.ts:506-518)      */
+    /* Multi-GPU extension (0,0,0 = the plain contiguous band of the reference's partition rule,
+     * main.ts:444-449).  With stripe_count > 1 the call renders only the rows y of [y_start, y_end)
+     * with ((y - y_start) / stripe_rows) % stripe_count == stripe_index; outputs keep the band layout
+     * ((y - y_start) * width + x), untouched rows are left alone.  stripe_rows must be a multiple of 4. */
+    int32_t stripe_rows, stripe_count, stripe_index;
 } rm_request;
 
 /* Result (raymarchWorker.ts:24-31).  Buffers are CALLER-allocated.  For rm_render they are host
@@ -141,6 +146,8 @@ typedef struct rm_stats_t {
     uint64_t sum_sdf_full, sum_iters_full;
     uint64_t evals_by_type[3]; /* un-wrapped primitive evaluations split sphere/box/torus */
     uint64_t n_hit;            /* pixels with depth < MAX_DIST */
+    double algorithmic_flops;  /* sum over evals of the executed variant's FLOP count: general affine sphere 26 / box 38 /
+                                  torus 29; translation-only sphere fast path 11 */
     double kernel_ms;          /* CUDA-event time of the render kernel(s) */
     double wall_ms;            /* host wall time of the whole call */
     int32_t n_launches;        /* kernels launched by the call */
@@ -178,6 +185,10 @@ int rm_stats(rm_ctx* ctx, rm_stats_t* out);
 /* ShadingModel.shade on existing (host) buffers: pure per-pixel map of the four quantised planes. */
 int rm_shade(rm_ctx* ctx, int32_t shader, uint8_t* rgba, const uint8_t* depth, const uint8_t* normal,
              const uint16_t* sdf_eval, const uint16_t* iters, int32_t width, int32_t height);
+
+/* Live microbenchmark of the FP32 (non-tensor) FFMA peak of this device in TFLOP/s: the roofline
+ * denominator of the raymarch path.  Takes ~50 ms. */
+int rm_probe_fp32_peak(rm_ctx* ctx, double* tflops);
 
 /* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "multi-GPU") -------------------- */
 /* Device allocation owned by the context (freed by rm_free / rm_destroy). */

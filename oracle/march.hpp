@@ -304,14 +304,19 @@ struct Raymarcher {
     void runRows(int width, int height, int yStart, int yEnd, int rowBegin, int rowStride, uint8_t* depthBuffer,
                  uint8_t* normalBuffer, uint16_t* sdfBuffer, uint16_t* itersBuffer, double* depthF64,
                  uint32_t* sdfFull, uint32_t* itersFull) const {
+        for (int y = yStart + rowBegin; y < yEnd; y += rowStride)
+            runRow(width, height, y, y - yStart, depthBuffer, normalBuffer, sdfBuffer, itersBuffer, depthF64, sdfFull, itersFull);
+    }
+    // one image row y, written at buffer row localY
+    void runRow(int width, int height, int y, int localY, uint8_t* depthBuffer, uint8_t* normalBuffer, uint16_t* sdfBuffer,
+                uint16_t* itersBuffer, double* depthF64, uint32_t* sdfFull, uint32_t* itersFull) const {
         mat4 rotMat4;
         scene.camera.getRotationMatrix(rotMat4);
         mat3 rotMat3;
         glm::m3_from_mat4(rotMat3, rotMat4);
         vec3 rayOrigin = glm::v3_create();
         scene.camera.getPosition(rayOrigin);
-        for (int y = yStart + rowBegin; y < yEnd; y += rowStride) {
-            int localY = y - yStart;
+        {
             double v = ((double)y / (double)height - 0.5) * 2.0;
             for (int x = 0; x < width; ++x) {
                 size_t idx = (size_t)localY * width + x;

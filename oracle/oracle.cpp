@@ -189,6 +189,26 @@ void orc_render(orc_scene* s, int algo, double stepSize, double overshoot, int w
     for (auto& t : th) t.join();
 }
 
+// Bounded sample for CPU-baseline timing: only the listed image rows, written compactly (row k of the
+// output = image row rows[k]).  Threads take rows round-robin.
+void orc_render_rows(orc_scene* s, int algo, double stepSize, double overshoot, int width, int height, const int* rows,
+                     int nrows, uint8_t* depth, uint8_t* normal, uint16_t* sdf, uint16_t* iters, double* depthF64,
+                     uint32_t* sdfFull, uint32_t* itersFull, int nthreads) {
+    MarchParams mp;
+    mp.algo = algo;
+    mp.stepSize = stepSize;
+    mp.overshootFactor = overshoot;
+    Raymarcher rm(s->scene, mp);
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t]() {
+            for (int k = t; k < nrows; k += nthreads)
+                rm.runRow(width, height, rows[k], k, depth, normal, sdf, iters, depthF64, sdfFull, itersFull);
+        });
+    for (auto& t : th) t.join();
+}
+
 void orc_shade(int shader, uint8_t* rgba, const uint8_t* depth, const uint8_t* normal, const uint16_t* sdf,
                const uint16_t* iters, int w, int h) {
     size_t n = (size_t)w * h;

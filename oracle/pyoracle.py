@@ -51,6 +51,7 @@ def lib():
         L.orc_octree_counts.argtypes = [vp, vp, vp]
         L.orc_octree_flatten.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.orc_render.argtypes = [vp, i32, f64, f64, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_render_rows.argtypes = [vp, i32, f64, f64, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32]
         L.orc_shade.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32]
         L.orc_stats.argtypes = [vp, vp, C.c_size_t, vp]
         L.orc_hypot3.restype = f64
@@ -191,6 +192,20 @@ class OracleScene:
         self._L.orc_render(self._h, algo, step_size, overshoot, width, height, y_start, y_end, _p(f.depth),
                            _p(f.normal), _p(f.sdfEval), _p(f.iters), _p(f.depth_f64), _p(f.sdf_full),
                            _p(f.iters_full), nthreads)
+        return f
+
+    def render_rows(self, width, height, rows, algorithm="sphere-tracer", step_size=0.1, overshoot=1.2,
+                    nthreads=None) -> OracleFrame:
+        """Bounded sample: only image rows `rows` (compact output, row k = image row rows[k])."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        n = len(rows) * width
+        f = OracleFrame(np.zeros(n, np.uint8), np.zeros(n * 3, np.uint8), np.zeros(n, np.uint16),
+                        np.zeros(n, np.uint16), np.zeros(n, np.float64), np.zeros(n, np.uint32),
+                        np.zeros(n, np.uint32))
+        nthreads = nthreads or (os.cpu_count() or 1)
+        self._L.orc_render_rows(self._h, ALGOS.get(algorithm, 0), step_size, overshoot, width, height, _p(rows),
+                                len(rows), _p(f.depth), _p(f.normal), _p(f.sdfEval), _p(f.iters), _p(f.depth_f64),
+                                _p(f.sdf_full), _p(f.iters_full), nthreads)
         return f
 
     def prim_sdf(self, prim: int, p) -> float:

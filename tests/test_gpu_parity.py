@@ -1,0 +1,370 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI (librm_b200.so).
+
+Bars (BASELINE.json north_star):
+  * fp64 validation build: hit mask, per-pixel SDF-call and iteration counters, the quantised depth/normal
+    planes AND the unquantised depth (as raw doubles) are BIT-EXACT against the oracle;
+  * fp32 fast path: >= 99.9 % of pixels agree on the hit mask and are within 1/255 in RGB (normal / Phong),
+    depth relative error <= 1e-4 on >= 99.9 % of hit pixels.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_job
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ALGS = ("sphere-tracer", "fixed-step", "adaptive-step", "adaptive-step-v2", "adaptive-step-v3")
+RGB_TOL = 1          # 1/255
+DEPTH_REL_TOL = 1e-4
+PIXEL_AGREEMENT = 0.999
+
+
+def _oracle_scene(oracle, preset, accel, pitch=0.0, yaw=0.0, synthetic=None):
+    s = oracle.OracleScene()
+    if synthetic:
+        s.load_synthetic(*synthetic)
+    else:
+        s.load_preset(preset)
+    return s.build_accel(accel).set_camera(pitch, yaw)
+
+
+def assert_bit_exact(f, ref, oracle, W, H, shaders=True):
+    assert np.array_equal(f.sdfEval, ref.sdfEval), "SDF-call counters differ"
+    assert np.array_equal(f.iters, ref.iters), "iteration counters differ"
+    assert np.array_equal(f.sdf_u32, ref.sdf_full), "un-wrapped SDF-call counters differ"
+    assert np.array_equal(f.depth_f64 < 10, ref.depth_f64 < 10), "hit mask differs"
+    assert np.array_equal(f.depth_f64.view(np.uint64), ref.depth_f64.view(np.uint64)), "unquantised depth differs"
+    assert np.array_equal(f.depth, ref.depth), "depth bytes differ"
+    assert np.array_equal(f.normal, ref.normal), "normal bytes differ"
+
+
+def fast_agreement(f, ref, oracle, W, H):
+    hit_ref, hit_f = ref.depth_f64 < 10, f.depth_f64 < 10
+    ok = hit_ref == hit_f
+    ok &= np.abs(f.normal.reshape(-1, 3).astype(int) - ref.normal.reshape(-1, 3).astype(int)).max(1) <= RGB_TOL
+    if f.rgba is not None:
+        want = oracle.shade("phong", ref.depth, ref.normal, ref.sdfEval, ref.iters, W, H).reshape(-1, 4)
+        ok &= np.abs(f.rgba.reshape(-1, 4).astype(int) - want.astype(int)).max(1) <= RGB_TOL
+    both = hit_ref & hit_f
+    rel = np.abs(f.depth_f64[both] - ref.depth_f64[both]) / np.maximum(np.abs(ref.depth_f64[both]), 1e-12)
+    depth_ok = float((rel <= DEPTH_REL_TOL).mean()) if both.any() else 1.0
+    return float(ok.mean()), depth_ok
+
+
+# ------------------------------------------------------------------------------------------ validation build
+@pytest.mark.parametrize("accel", ["None", "Octree", "BVH"])
+@pytest.mark.parametrize("alg", ALGS)
+@pytest.mark.parametrize("preset", [0, 2, 3, 5, 8, 9])
+def test_validation_bit_exact_matrix(val_worker, oracle, preset, accel, alg):
+    W, H = 96, 56
+    ref = _oracle_scene(oracle, preset, accel).render(W, H, alg)
+    f = val_worker.on_message(make_job(W, H, preset, accel, alg), extras=True)
+    assert_bit_exact(f, ref, oracle, W, H)
+
+
+@pytest.mark.parametrize("pitch,yaw", [(0.3, 0.7), (-0.6, 2.5), (1.2, 5.0), (0.0, 0.015 * 123)])
+@pytest.mark.parametrize("preset,accel", [(1, "BVH"), (3, "Octree"), (4, "None"), (9, "BVH"), (5, "Octree")])
+def test_validation_bit_exact_rotated_camera(val_worker, oracle, preset, accel, pitch, yaw):
+    W, H = 80, 48
+    ref = _oracle_scene(oracle, preset, accel, pitch, yaw).render(W, H, "sphere-tracer")
+    f = val_worker.on_message(make_job(W, H, preset, accel, "sphere-tracer", pitch, yaw), extras=True)
+    assert_bit_exact(f, ref, oracle, W, H)
+
+
+def test_validation_axis_aligned_rays_nan_path(val_worker, oracle):
+    """Centre column at yaw 0 has dir.x == 0 exactly and octree planes pass through the origin's coordinates:
+    0 * Infinity = NaN flows through Math.max/min in intersectRayBox (octree.ts:200-213).  Even widths hit it."""
+    W, H = 64, 64
+    for preset in (2, 3):
+        ref = _oracle_scene(oracle, preset, "Octree").render(W, H, "sphere-tracer")
+        f = val_worker.on_message(make_job(W, H, preset, "Octree", "sphere-tracer"), extras=True)
+        assert_bit_exact(f, ref, oracle, W, H)
+
+
+@pytest.mark.parametrize("step", [0.01, 0.05, 0.37, 0.5])
+def test_validation_fixed_step_sizes(val_worker, oracle, step):
+    W, H = 64, 40
+    ref = _oracle_scene(oracle, 4, "BVH").render(W, H, "fixed-step", step_size=step)
+    f = val_worker.on_message(make_job(W, H, 4, "BVH", "fixed-step", step=step), extras=True)
+    assert_bit_exact(f, ref, oracle, W, H)
+
+
+@pytest.mark.parametrize("over", [1.0, 1.5, 2.0])
+@pytest.mark.parametrize("alg", ["adaptive-step-v2", "adaptive-step-v3"])
+def test_validation_overshoot_factors(val_worker, oracle, alg, over):
+    W, H = 64, 40
+    ref = _oracle_scene(oracle, 1, "Octree", 0.1, 0.9).render(W, H, alg, overshoot=over)
+    f = val_worker.on_message(make_job(W, H, 1, "Octree", alg, 0.1, 0.9, over=over), extras=True)
+    assert_bit_exact(f, ref, oracle, W, H)
+
+
+@pytest.mark.parametrize("accel", ["BVH", "Octree", "None"])
+def test_validation_synthetic_spheres(val_worker, oracle, accel):
+    """Config-4 generator at a size the oracle finishes quickly: exercises the BVH full-scene fallback
+    (scene.ts:173) and deep interval lists."""
+    W, H = 64, 36
+    syn = (3000, 0x5EED0001)
+    ref = _oracle_scene(oracle, 1, accel, synthetic=syn).render(W, H, "sphere-tracer")
+    f = val_worker.on_message(make_job(W, H, 1, accel, "sphere-tracer", synthetic=syn), extras=True)
+    assert_bit_exact(f, ref, oracle, W, H)
+    if accel == "BVH":
+        assert (ref.sdf_full >= 3000).any(), "expected at least one full-scene fallback"
+
+
+def test_validation_u16_counter_wrap(val_worker, oracle):
+    syn = (70000, 0x5EED0001)
+    W, H = 8, 4
+    ref = _oracle_scene(oracle, 1, "None", synthetic=syn).render(W, H, "sphere-tracer")
+    f = val_worker.on_message(make_job(W, H, 1, "None", "sphere-tracer", synthetic=syn), extras=True)
+    assert_bit_exact(f, ref, oracle, W, H)
+    assert np.all(f.sdf_u32 >= 70000) and np.array_equal(f.sdfEval, (f.sdf_u32 % 65536).astype(np.uint16))
+
+
+def test_validation_mixed_rotated_primitives(oracle):
+    """Boxes / tori / spheres with general rotations built by the Python host mirror (not a preset)."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    pl = sm.PrimitiveList()
+    sm.add_box(pl, 0.3, -0.2, 0.5, (0.4, 0.2, 0.7), rotation=(0.3, 1.1, -0.8))
+    sm.add_torus(pl, -1.0, 0.4, 0.0, 0.8, rotation=(1.0, 0.0, 0.5))
+    sm.add_sphere(pl, 1.0, 1.0, -1.0, 0.3)
+    sm.add_box(pl, -0.6, -0.9, 0.2, (0.1, 0.5, 0.3))
+    sm.add_sphere(pl, 0.0, 0.2, 1.4, 0.25, rotation=(0.1, 0.2, 0.3))
+    t, m, q = pl.arrays()
+    W, H = 72, 48
+    cam = Camera()
+    cam.set_angles(0.2, 0.6)
+    for accel in ("None", "BVH", "Octree"):
+        ref = oracle.OracleScene().set_prims(t, m, q).build_accel(accel).set_camera(0.2, 0.6).render(W, H, "adaptive-step-v3")
+        ctx = rb.Context(0, validate_fp64=True)
+        ctx.upload_scene(t, m, q, accel)
+        rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), "adaptive-step-v3")
+        f = ctx.render(rq, extras=True)
+        assert_bit_exact(f, ref, oracle, W, H)
+        st = ctx.stats()
+        assert sum(st["evals_by_type"]) == int(ref.sdf_full.sum())
+        ctx.close()
+
+
+def test_validation_length_sqrt_flag(oracle):
+    import cpu_raymarcher_b200 as rb
+    W, H = 64, 40
+    oracle.lib().orc_set_length_mode(0)
+    try:
+        ref = _oracle_scene(oracle, 8, "BVH", 0.0, 0.8).render(W, H, "sphere-tracer")
+    finally:
+        oracle.lib().orc_set_length_mode(1)
+    w = rb.RaymarchWorker(0, validate_fp64=True, length_sqrt=True)
+    f = w.on_message(make_job(W, H, 8, "BVH", "sphere-tracer", 0.0, 0.8), extras=True)
+    w.close()
+    assert_bit_exact(f, ref, oracle, W, H)
+
+
+def _golden_cases():
+    with open(os.path.join(GOLDEN, "manifest.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_validation_matches_committed_golden(val_worker, case):
+    g = np.load(os.path.join(GOLDEN, case["name"] + ".npz"))
+    job = make_job(case["W"], case["H"], case["preset"], case["accel"], case["alg"], case["pitch"], case["yaw"],
+                   synthetic=tuple(case["synthetic"]) if case.get("synthetic") else None, step=case["step"], over=case["over"])
+    f = val_worker.on_message(job, shader="phong", shader_analytics="sdf-heatmap", extras=True)
+    for k in ("depth", "normal", "sdfEval", "iters"):
+        assert np.array_equal(getattr(f, k), g[k]), k
+    assert np.array_equal(f.depth_f64.view(np.uint64), g["depth_f64"].view(np.uint64))
+    assert np.array_equal(f.rgba, g["phong"]) and np.array_equal(f.rgba_analytics, g["sdf_heat"])
+
+
+# ------------------------------------------------------------------------------------------ worker contract
+def test_band_partition_invariance_and_ragged_sizes(val_worker, oracle):
+    """main.ts:444-449 partition rule with 4 and 3 workers on sizes that are not multiples of the 8x4 tile."""
+    W, H = 77, 45
+    ref = _oracle_scene(oracle, 3, "BVH", 0.1, 0.3).render(W, H, "sphere-tracer")
+    for workers in (4, 3, 7):
+        rows = -(-H // workers)
+        parts = []
+        for i in range(workers):
+            y0, y1 = min(i * rows, H), min((i + 1) * rows, H)
+            if y0 >= y1:
+                continue
+            f = val_worker.on_message(make_job(W, H, 3, "BVH", "sphere-tracer", 0.1, 0.3, y0, y1))
+            assert (f.yStart, f.yEnd) == (y0, y1) and f.depth.size == W * (y1 - y0)
+            parts.append(f)
+        assert np.array_equal(np.concatenate([p.sdfEval for p in parts]), ref.sdfEval)
+        assert np.array_equal(np.concatenate([p.normal for p in parts]), ref.normal)
+        assert np.array_equal(np.concatenate([p.depth for p in parts]), ref.depth)
+        assert np.array_equal(np.concatenate([p.iters for p in parts]), ref.iters)
+
+
+def test_edge_cases_empty_band_single_pixel_unknown_algorithm(val_worker, oracle):
+    f = val_worker.on_message(make_job(32, 32, 0, "None", "sphere-tracer", y0=10, y1=10))
+    assert f.depth.size == 0 and f.normal.size == 0
+    f = val_worker.on_message(make_job(32, 32, 0, "None", "sphere-tracer", y0=20, y1=5))  # Math.max(0, yEnd - yStart)
+    assert f.depth.size == 0
+    ref = _oracle_scene(oracle, 0, "None").render(1, 1)
+    f = val_worker.on_message(make_job(1, 1, 0), extras=True)
+    assert_bit_exact(f, ref, oracle, 1, 1)
+    ref = _oracle_scene(oracle, 2, "None").render(40, 24, "sphere-tracer")
+    f = val_worker.on_message(make_job(40, 24, 2, "None", "no-such-algorithm"), extras=True)  # default branch: sphere tracer
+    assert_bit_exact(f, ref, oracle, 40, 24)
+
+
+def test_stripe_interleave_extension(oracle):
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import multigpu
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    W, H = 64, 52
+    ref = _oracle_scene(oracle, 3, "Octree").render(W, H)
+    t, m, q = sm.get_preset(3).arrays()
+    ctx = rb.Context(0, validate_fp64=True)
+    ctx.upload_scene(t, m, q, "Octree")
+    cam = Camera()
+    got = np.full(W * H, 0xFFFF, np.uint16)
+    total = 0
+    for rank in range(3):
+        rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), stripes=(8, 3, rank))
+        f = ctx.render(rq)
+        rows = multigpu.stripe_rows_of(rank, 3, H, 8)
+        sel = (rows[:, None] * W + np.arange(W)[None, :]).ravel()
+        got[sel] = f.sdfEval[sel]
+        st = ctx.stats()
+        assert st["n_pixels"] == len(rows) * W
+        total += st["sum_sdf"]
+    assert np.array_equal(got, ref.sdfEval)
+    assert total == int(ref.sdfEval.astype(np.int64).sum())
+    ctx.close()
+
+
+def test_stats_match_main_ts_diagnostics(val_worker, oracle):
+    W, H = 96, 54
+    ref = _oracle_scene(oracle, 3, "BVH").render(W, H, "sphere-tracer")
+    val_worker.on_message(make_job(W, H, 3, "BVH", "sphere-tracer"))
+    st = val_worker.stats()
+    want = oracle.stats(ref.sdfEval, ref.iters)
+    assert st["n_pixels"] == W * H
+    assert st["sum_sdf"] == want["total_sdf"] and st["sum_iters"] == want["total_iters"]
+    assert st["max_sdf"] == want["max_sdf"] and st["min_sdf"] == want["min_sdf"]
+    assert st["sum_sdf_full"] == int(ref.sdf_full.astype(np.int64).sum())
+    assert st["sum_iters_full"] == int(ref.iters_full.astype(np.int64).sum())
+    assert st["n_hit"] == int((ref.depth_f64 < 10).sum())
+    assert st["n_launches"] == 1 and st["kernel_ms"] > 0
+
+
+@pytest.mark.parametrize("shader", ["normal", "phong", "sdf-heatmap", "iteration-heatmap"])
+def test_standalone_shade_entry_bit_exact(val_worker, oracle, shader):
+    W, H = 64, 48
+    ref = _oracle_scene(oracle, 8, "None", 0.2, 0.5).render(W, H)
+    got = val_worker.ctx.shade(shader, ref.depth, ref.normal, ref.sdfEval, ref.iters, W, H)
+    assert np.array_equal(got, oracle.shade(shader, ref.depth, ref.normal, ref.sdfEval, ref.iters, W, H))
+    # all 2^16 counter values and all depth bytes through the heat-map / phong maps
+    if shader in ("sdf-heatmap", "iteration-heatmap"):
+        cnt = np.arange(65536, dtype=np.uint16)
+        z8, z24 = np.zeros(65536, np.uint8), np.zeros(3 * 65536, np.uint8)
+        assert np.array_equal(val_worker.ctx.shade(shader, z8, z24, cnt, cnt, 256, 256), oracle.shade(shader, z8, z24, cnt, cnt, 256, 256))
+
+
+def test_phong_over_random_quantised_inputs(val_worker, fast_worker, oracle):
+    rng = np.random.default_rng(7)
+    n = 256 * 128
+    depth = rng.integers(0, 256, n, dtype=np.uint8)
+    normal = rng.integers(0, 256, 3 * n, dtype=np.uint8)
+    z = np.zeros(n, np.uint16)
+    want = oracle.shade("phong", depth, normal, z, z, 256, 128)
+    assert np.array_equal(val_worker.ctx.shade("phong", depth, normal, z, z, 256, 128), want)
+    fast = fast_worker.ctx.shade("phong", depth, normal, z, z, 256, 128)
+    assert np.abs(fast.astype(int) - want.astype(int)).max() <= RGB_TOL
+
+
+def test_errors_are_reported_not_swallowed():
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import _lib
+    ctx = rb.Context(0)
+    rq = rb.Context.make_request(8, 8, np.eye(3, dtype=np.float32).ravel(), np.zeros(3, np.float32))
+    with pytest.raises(rb.RmError) as ei:
+        ctx.render(rq)
+    assert ei.value.code == _lib.RM_ERR_STATE
+    t = np.array([7], np.uint8)  # not sphere/box/torus: operator trees are outside the path
+    with pytest.raises(rb.RmError) as ei:
+        ctx.upload_scene(t, np.eye(4, dtype=np.float32).reshape(1, 16), np.zeros((1, 4)))
+    assert ei.value.code == _lib.RM_ERR_UNSUPPORTED_PRIMITIVE
+    ctx.upload_scene(np.array([0], np.uint8), np.eye(4, dtype=np.float32).reshape(1, 16), np.array([[1.0, 0, 0, 0]]))
+    rq.y_end = 99
+    with pytest.raises(rb.RmError) as ei:
+        ctx.render(rq)
+    assert ei.value.code == _lib.RM_ERR_ARG
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------ fp32 fast path
+@pytest.mark.parametrize("accel", ["None", "Octree", "BVH"])
+@pytest.mark.parametrize("alg", ALGS)
+@pytest.mark.parametrize("preset", [0, 1, 3, 5, 9])
+def test_fast_path_tolerance_matrix(fast_worker, oracle, preset, accel, alg):
+    W, H = 160, 90
+    ref = _oracle_scene(oracle, preset, accel, 0.1, 0.4).render(W, H, alg)
+    f = fast_worker.on_message(make_job(W, H, preset, accel, alg, 0.1, 0.4), shader="phong", extras=True)
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"pixel agreement {px}"
+    assert dz >= PIXEL_AGREEMENT, f"depth agreement {dz}"
+
+
+@pytest.mark.parametrize("accel", ["BVH", "Octree"])
+def test_fast_path_synthetic_spheres(fast_worker, oracle, accel):
+    W, H = 128, 72
+    syn = (4000, 0x5EED0001)
+    ref = _oracle_scene(oracle, 1, accel, synthetic=syn).render(W, H, "sphere-tracer")
+    f = fast_worker.on_message(make_job(W, H, 1, accel, "sphere-tracer", synthetic=syn), shader="phong", extras=True)
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT and dz >= PIXEL_AGREEMENT, (px, dz)
+    # counters are not part of the fast-path bar, but they should be overwhelmingly identical
+    assert (f.sdfEval == ref.sdfEval).mean() > 0.99
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_1080p_properties(fast_worker):
+    """BASELINE config 2 at its real size: size-independent properties instead of an oracle frame."""
+    W, H = 1920, 1080
+    job = make_job(W, H, 2, "BVH", "sphere-tracer")
+    full = fast_worker.on_message(job, shader="phong", shader_analytics="iteration-heatmap", extras=True)
+    st = fast_worker.stats()
+    assert st["n_pixels"] == W * H
+    # checksum of checksums: epilogue reduction == host reduction of the planes
+    assert st["sum_sdf"] == int(full.sdfEval.astype(np.int64).sum()) and st["sum_iters"] == int(full.iters.astype(np.int64).sum())
+    assert st["max_sdf"] == int(full.sdfEval.max()) and st["min_sdf"] == int(full.sdfEval.min()) == 0  # BVH misses (KAT-3)
+    assert st["n_hit"] == int((full.depth_f64 < 10).sum())
+    # hit pixels: 1-2 leaf primitives per query or 9 on fallback; misses terminated by the BVH have zero counters
+    miss0 = full.sdf_u32 == 0
+    assert np.all(full.depth[miss0] == 10) and np.all(full.iters[miss0] == 0)
+    assert np.all(full.normal.reshape(-1, 3)[miss0] == 128)
+    # tile-partition invariance at full size (4 bands, the reference's rule)
+    rows = -(-H // 4)
+    parts = [fast_worker.on_message(make_job(W, H, 2, "BVH", "sphere-tracer", y0=i * rows, y1=min((i + 1) * rows, H)),
+                                    shader="phong") for i in range(4)]
+    assert np.array_equal(np.concatenate([p.sdfEval for p in parts]), full.sdfEval)
+    assert np.array_equal(np.concatenate([p.rgba for p in parts]), full.rgba)
+    # idempotence
+    again = fast_worker.on_message(job, shader="phong")
+    assert np.array_equal(again.normal, full.normal) and np.array_equal(again.iters, full.iters)
+    # the fused shader output is a pure function of the planes
+    assert np.array_equal(fast_worker.ctx.shade("phong", full.depth, full.normal, full.sdfEval, full.iters, W, H), full.rgba)
+    # left-right mirror symmetry of the scene and camera: hit mask symmetric about the centre column
+    hit = (full.depth_f64 < 10).reshape(H, W)
+    assert (hit[:, 1:] == hit[:, 1:][:, ::-1]).mean() > 0.9995
+
+
+def test_full_size_no_accel_invariant_4k(fast_worker):
+    """No-accel sphere tracer: sdfEval == N * (iters + 4 * hit) holds for every pixel at 3840x2160."""
+    W, H = 3840, 2160
+    f = fast_worker.on_message(make_job(W, H, 4, "None", "sphere-tracer"), extras=True)
+    hit = f.depth_f64 < 10
+    assert np.array_equal(f.sdf_u32, 7 * (f.iters.astype(np.uint32) + 4 * hit))
+    st = fast_worker.stats()
+    assert st["evals_by_type"] == [st["sum_sdf_full"], 0, 0]

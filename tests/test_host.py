@@ -1,0 +1,192 @@
+"""CPU tests of the host side: C-ABI exports, loud failure without a GPU, native builders and the Python
+mirrors of sceneManager.ts / camera.ts against the oracle (independent implementations, bit-exact)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cpu_raymarcher_b200 as rb
+from cpu_raymarcher_b200 import _lib, multigpu
+from cpu_raymarcher_b200 import scene_manager as sm
+from cpu_raymarcher_b200.camera import Camera
+
+from conftest import HAVE_GPU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rm.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|void|const char\*)\s+(rm_[a-z0-9_]+)\s*\(", hdr, re.M))
+    assert declared, "no declarations parsed"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/rm.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert L.rm_abi_version() == 1
+
+
+def test_struct_layouts_match_c_abi():
+    assert C.sizeof(_lib.BvhNode) == 40
+    assert C.sizeof(_lib.OctreeNode) == 48
+    assert _lib.OctreeNode.min_distance.offset == 40
+    assert C.sizeof(_lib.Request) % 8 == 0
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="only meaningful on a machine without a GPU")
+def test_no_gpu_fails_loudly_no_cpu_fallback():
+    with pytest.raises(rb.RmError) as ei:
+        rb.Context()
+    assert ei.value.code == _lib.RM_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cpu_raymarcher_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("not share sources with oracle/", ""), f
+
+
+@pytest.mark.parametrize("idx", sm.SUPPORTED_PRESETS)
+def test_presets_match_oracle_bitwise(oracle, idx):
+    t, m, q = sm.get_preset(idx).arrays()
+    ot, om, oq = oracle.OracleScene().load_preset(idx).get_prims()
+    assert np.array_equal(t, ot)
+    assert np.array_equal(bits(m), bits(om))
+    assert np.array_equal(bits(q), bits(oq))
+
+
+@pytest.mark.parametrize("idx", [6, 10, 11, 12, 13, 14, 15, 16, 17, 18])
+def test_operator_presets_are_rejected(idx):
+    with pytest.raises(sm.UnsupportedPreset):
+        sm.get_preset(idx)
+
+
+def test_synthetic_scene_matches_oracle_bitwise(oracle):
+    t, m, q = sm.synthetic_spheres(5000).arrays()
+    ot, om, oq = oracle.OracleScene().load_synthetic(5000).get_prims()
+    assert np.array_equal(t, ot) and np.array_equal(bits(m), bits(om)) and np.array_equal(bits(q), bits(oq))
+    # first 7 primitives are the reference's "Random Spheres"
+    t1, m1, q1 = sm.get_preset(1).arrays()
+    assert np.array_equal(bits(m[:7]), bits(m1)) and np.array_equal(q[:7], q1)
+    # vectorised transform == scalar transform (incl. the sign of zeros)
+    c = np.array([[0.25, -1.5, 2.0], [-2.4, 0.0, 0.1]])
+    batch = sm.get_transform_batch(c)
+    for k in range(2):
+        assert np.array_equal(bits(np.array(sm.get_transform(*c[k]), np.float32)), bits(batch[k]))
+
+
+@pytest.mark.parametrize("pitch,yaw", [(0, 0), (0.3, 1.1), (-2.0, 5.4), (0.0, 0.015 * 77), (1.2, -3.0)])
+def test_camera_matches_oracle_bitwise(oracle, pitch, yaw):
+    c = Camera()
+    c.set_angles(pitch, yaw)
+    r, o = oracle.OracleScene().set_camera(pitch, yaw).get_camera()
+    assert np.array_equal(bits(r), bits(c.get_rotation_matrix3()))
+    assert np.array_equal(bits(o), bits(c.get_position()))
+
+
+def test_camera_analytics_rotation_accumulates_like_main_ts(oracle):
+    c = Camera()
+    s = oracle.OracleScene()
+    for _ in range(25):  # main.ts:438-441: yaw += 0.015 before every frame
+        c.rotate_camera(0, 0.015)
+        s.rotate_camera(0, 0.015)
+    assert c.get_angles() == s.get_angles()
+    r, o = s.get_camera()
+    assert np.array_equal(bits(r), bits(c.get_rotation_matrix3()))
+
+
+BVH_DT = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("l", "<i4"), ("r", "<i4"), ("pf", "<i4"), ("pc", "<i4")])
+OCT_DT = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("fc", "<i4"), ("pf", "<i4"), ("pc", "<i4"), ("lvl", "u1"), ("emp", "u1"),
+                   ("pad", "u1", 2), ("md", "<f8")])
+
+
+def _scene_cases():
+    return [("preset", i) for i in sm.SUPPORTED_PRESETS] + [("synthetic", 300), ("synthetic", 3000)]
+
+
+@pytest.mark.parametrize("kind,arg", _scene_cases())
+def test_native_bvh_builder_matches_oracle(oracle, kind, arg):
+    if kind == "preset":
+        t, m, q = sm.get_preset(arg).arrays()
+        osc = oracle.OracleScene().load_preset(arg)
+    else:
+        t, m, q = sm.synthetic_spheres(arg).arrays()
+        osc = oracle.OracleScene().load_synthetic(arg)
+    ob, ol, oleaf = osc.build_accel("BVH").bvh_flat()
+    nodes, nn, leaf = rb.build_bvh(t, m, q)
+    a = np.frombuffer(nodes, dtype=BVH_DT, count=nn)
+    assert nn == len(ob)
+    assert np.array_equal(bits(a["bmin"]), bits(ob[:, :3])) and np.array_equal(bits(a["bmax"]), bits(ob[:, 3:]))
+    assert np.array_equal(a["l"], ol[:, 0]) and np.array_equal(a["r"], ol[:, 1])
+    assert np.array_equal(a["pf"], ol[:, 2]) and np.array_equal(a["pc"], ol[:, 3])
+    assert np.array_equal(leaf, oleaf)
+    # every primitive lives in exactly one leaf (so the reference's Set de-duplication never matters)
+    assert sorted(leaf.tolist()) == list(range(len(t)))
+
+
+@pytest.mark.parametrize("kind,arg", _scene_cases())
+def test_native_octree_builder_matches_oracle(oracle, kind, arg):
+    if kind == "preset":
+        t, m, q = sm.get_preset(arg).arrays()
+        osc = oracle.OracleScene().load_preset(arg)
+    else:
+        t, m, q = sm.synthetic_spheres(arg).arrays()
+        osc = oracle.OracleScene().load_synthetic(arg)
+    ob, ol, lvl, emp, mind, oleaf = osc.build_accel("Octree").octree_flat()
+    nodes, nn, leaf = rb.build_octree(t, m, q)
+    a = np.frombuffer(nodes, dtype=OCT_DT, count=nn)
+    assert nn == len(ob)
+    assert np.array_equal(bits(a["bmin"]), bits(ob[:, :3])) and np.array_equal(bits(a["bmax"]), bits(ob[:, 3:]))
+    assert np.array_equal(a["fc"], ol[:, 0]) and np.array_equal(a["pf"], ol[:, 1]) and np.array_equal(a["pc"], ol[:, 2])
+    assert np.array_equal(a["lvl"], lvl) and np.array_equal(a["emp"], emp)
+    assert np.array_equal(bits(a["md"]), bits(mind))
+    assert np.array_equal(leaf, oleaf)
+
+
+def test_builders_handle_empty_and_rotated_scenes(oracle):
+    nodes, nn, leaf = rb.build_bvh(np.zeros(0, np.uint8), np.zeros((0, 16), np.float32), np.zeros((0, 4)))
+    assert nn == 1 and len(leaf) == 0
+    pl = sm.PrimitiveList()
+    sm.add_box(pl, 0.3, -0.2, 0.5, (0.4, 0.2, 0.7), rotation=(0.3, 1.1, -0.8))
+    sm.add_torus(pl, -1.0, 0.4, 0.0, 0.8, rotation=(1.0, 0.0, 0.5))
+    sm.add_sphere(pl, 1.0, 1.0, -1.0, 0.3)
+    sm.add_box(pl, -0.6, -0.9, 0.2, (0.1, 0.5, 0.3))
+    sm.add_sphere(pl, 0.0, 0.2, 1.4, 0.25, rotation=(0.1, 0.2, 0.3))
+    t, m, q = pl.arrays()
+    osc = oracle.OracleScene().set_prims(t, m, q).build_accel("BVH")
+    ob, ol, oleaf = osc.bvh_flat()
+    nodes, nn, leaf = rb.build_bvh(t, m, q)
+    a = np.frombuffer(nodes, dtype=BVH_DT, count=nn)
+    assert np.array_equal(bits(a["bmin"]), bits(ob[:, :3])) and np.array_equal(leaf, oleaf)
+    # transforms with rotation agree with the oracle's getTransform
+    out = np.zeros(16, np.float32)
+    rot = np.array([0.3, 1.1, -0.8], np.float32)
+    oracle.lib().orc_get_transform(0.3, -0.2, 0.5, rot.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(bits(out), bits(m[0]))
+
+
+def test_stripe_partition_covers_every_row_once():
+    for H in (1, 7, 8, 9, 63, 64, 2160):
+        for world in (1, 2, 3, 4, 8):
+            rows = np.concatenate([multigpu.stripe_rows_of(r, world, H) for r in range(world)])
+            assert sorted(rows.tolist()) == list(range(H))
+
+
+def test_plane_layout_is_aligned_and_disjoint():
+    lay = multigpu.plane_layout(1920, 1080)
+    n = 1920 * 1080
+    sizes = dict(depth=n, normal=3 * n, sdf=2 * n, iters=2 * n, rgba=4 * n)
+    spans = sorted((lay[k], lay[k] + sizes[k]) for k in sizes)
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    assert all(lay[k] % 256 == 0 for k in sizes) and lay["total"] >= spans[-1][1]

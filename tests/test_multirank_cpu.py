@@ -1,0 +1,70 @@
+"""world_size-2 gloo test of the N>1 host logic (stripe partition, frame merge, stats reduce) with a CPU band
+renderer injected in place of the GPU kernel.  The renderer here is the oracle — legitimate inside tests/ —
+so the merged 2-rank frame must equal the 1-rank oracle frame bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cpu_raymarcher_b200 import multigpu
+    from oracle import pyoracle as po
+    W, H = 64, 44
+    s = po.OracleScene().load_preset(3).build_accel("Octree").set_camera(0.1, 0.4)
+    rows = multigpu.stripe_rows_of(rank, world, H)
+    f = s.render_rows(W, H, rows, "sphere-tracer", nthreads=2)
+    # "fused gather": every rank contributes its rows to the full frame; gloo all_reduce(SUM) of disjoint rows
+    frame = {k: torch.zeros(H * W * c, dtype=torch.int32) for k, c in (("depth", 1), ("normal", 3), ("sdfEval", 1), ("iters", 1))}
+    for k, c in (("depth", 1), ("normal", 3), ("sdfEval", 1), ("iters", 1)):
+        src = getattr(f, k).astype(np.int32).reshape(len(rows), W * c)
+        dst = frame[k].view(H, W * c)
+        dst[torch.from_numpy(rows.astype(np.int64))] = torch.from_numpy(src)
+        dist.all_reduce(frame[k], op=dist.ReduceOp.SUM)
+    st = po.stats(f.sdfEval, f.iters)
+    local = dict(n_pixels=len(rows) * W, sum_sdf=int(st["total_sdf"]), sum_iters=int(st["total_iters"]), sum_sdf_full=int(f.sdf_full.sum()),
+                 sum_iters_full=int(f.iters_full.sum()), n_hit=int((f.depth_f64 < 10).sum()), algorithmic_flops=0.0, n_launches=1,
+                 max_sdf=int(st["max_sdf"]), min_sdf=int(st["min_sdf"]), max_iters=int(f.iters.max()), min_iters=int(f.iters.min()),
+                 evals_by_type=[int(f.sdf_full.sum()), 0, 0], kernel_ms=1.0 + rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    if rank == 0:
+        q.put(({k: v.numpy() for k, v in frame.items()}, multigpu.reduce_stats(gathered)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_stripe_render_equals_single_rank():
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as po
+    po.lib()  # build before forking
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    frame, st = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    W, H = 64, 44
+    ref = po.OracleScene().load_preset(3).build_accel("Octree").set_camera(0.1, 0.4).render(W, H, "sphere-tracer")
+    assert np.array_equal(frame["depth"], ref.depth.astype(np.int32))
+    assert np.array_equal(frame["normal"], ref.normal.astype(np.int32))
+    assert np.array_equal(frame["sdfEval"], ref.sdfEval.astype(np.int32))
+    assert np.array_equal(frame["iters"], ref.iters.astype(np.int32))
+    full = po.stats(ref.sdfEval, ref.iters)
+    assert st["n_pixels"] == W * H
+    assert st["sum_sdf"] == full["total_sdf"] and st["sum_iters"] == full["total_iters"]
+    assert st["max_sdf"] == full["max_sdf"] and st["min_sdf"] == full["min_sdf"]
+    assert st["kernel_ms"] == 2.0  # max over ranks
