@@ -134,25 +134,83 @@ RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], u
     }
 }
 
-// Dense all-primitives evaluation: closest = min over every primitive (scene.ts:183-189), starting
-// from MAX_DIST = 10.  Every lane walks the same primitive index -> broadcast loads.
-template <class NP, int PK>
-RM_DEV typename NP::F scene_all_prims(const RenderParams& P, const float q[3]) {
-    typedef typename NP::F F;
-    F closest = (F)10;
-    const int n = P.scene.n_prims;
-    if constexpr (NP::kExact) {
-        for (int j = 0; j < n; ++j)
-            closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
-    } else if constexpr (PK == PK_TSPHERE) {
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) closest = fminf(prim_sdf_fast_tsphere(P.scene.rec, j, q[0], q[1], q[2]), closest);
+// fp32 evaluation of primitive j by either fast record layout.
+template <int PK>
+RM_DEV float prim_sdf_f32(const float4* __restrict__ rec, int j, const float q[3]) {
+    if constexpr (PK == PK_TSPHERE) {
+        return prim_sdf_fast_tsphere(rec, j, q[0], q[1], q[2]);
     } else {
         int type;
-#pragma unroll 2
-        for (int j = 0; j < n; ++j) closest = fminf(prim_sdf_fast_general(P.scene.rec, j, q[0], q[1], q[2], type), closest);
+        return prim_sdf_fast_general(rec, j, q[0], q[1], q[2], type);
     }
-    return closest;
+}
+
+// Dense all-primitives evaluation: closest = min over every primitive (scene.ts:183-189), starting
+// from MAX_DIST = 10.  Every lane walks the same primitive index -> broadcast loads.
+//   exact model: the reference's Math.min chain in doubles;
+//   fast model : fp32 SEARCH for the nearest primitive (the FLOP-dominant N-primitive loop), then ONE
+//                fp64 evaluation of that primitive ("f32 search, f64 polish").  The hot loop keeps only
+//                a running min per 32-primitive chunk (1 FMNMX per evaluation); the winning chunk is
+//                re-scanned once to recover the index.
+constexpr int kChunk = 32;
+template <class NP, int PK>
+RM_DEV double scene_all_prims(const RenderParams& P, const float q[3]) {
+    const int n = P.scene.n_prims;
+    if constexpr (NP::kExact) {
+        double closest = 10.0;
+        for (int j = 0; j < n; ++j)
+            closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
+        return closest;
+    } else {
+        const float4* __restrict__ rec = P.scene.rec;
+        float best = 10.f;
+        int bestChunk = -1, bestIdx = -1;
+        int j = 0;
+        for (; j + kChunk <= n; j += kChunk) {
+            float m = prim_sdf_f32<PK>(rec, j, q);
+#pragma unroll 8
+            for (int k = 1; k < kChunk; ++k) m = fminf(m, prim_sdf_f32<PK>(rec, j + k, q));
+            if (m < best) {
+                best = m;
+                bestChunk = j;
+            }
+        }
+        for (; j < n; ++j) {  // tail (and the whole scene when n < 32)
+            float d = prim_sdf_f32<PK>(rec, j, q);
+            if (d < best) {
+                best = d;
+                bestIdx = j;
+                bestChunk = -1;
+            }
+        }
+        if (bestChunk >= 0) {
+            for (int k = 0; k < kChunk; ++k)
+                if (prim_sdf_f32<PK>(rec, bestChunk + k, q) == best) {
+                    bestIdx = bestChunk + k;
+                    break;
+                }
+        }
+        if (bestIdx < 0) return 10.0;  // nothing closer than MAX_DIST
+        return jsmin(prim_sdf_exact(P.scene, bestIdx, (double)q[0], (double)q[1], (double)q[2], 1), 10.0);
+    }
+}
+
+// Candidate-list evaluation (octree leaf / BVH leaf): running (min, argmin) in the field model.
+template <class NP, int PK>
+RM_DEV void leaf_prims(const RenderParams& P, const int32_t* __restrict__ lp, int pc, const float q[3], double& distExact,
+                       float& distF32, int& argmin, unsigned& nSphere, unsigned& nBox) {
+    for (int k = 0; k < pc; ++k) {
+        const int j = lp[k];
+        if constexpr (NP::kExact) {
+            distExact = jsmin(prim_sdf<NP, PK>(P, j, q, nSphere, nBox), distExact);
+        } else {
+            float d = (float)prim_sdf<NP, PK>(P, j, q, nSphere, nBox);
+            if (d < distF32) {
+                distF32 = d;
+                argmin = j;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,7 +252,6 @@ RM_DEV bool box_intersect_ray(const float* bmin, const float* bmax, const double
 // ------------------------------------------------------------------------------------------
 template <class NP>
 struct Ray {
-    typedef typename NP::F F;
     float d[3];   // unit direction (f32 values, raymarcher.ts:84-88)
     float q[3];   // pending query point (f32 values)
     float h[3];   // hit position (raymarcher.ts:94-95)
@@ -202,7 +259,7 @@ struct Ray {
     double prevSDF, prevStep;  // V2 / V3
     double aux0, aux1;         // V3: originalPos / newSDF
     double depth;              // rayMarch return
-    F nd;                      // getNormal: d = scene distance at the hit position
+    double nd;                 // getNormal: d = scene distance at the hit position
     float n0, n1, n2;          // normal (f32 values)
     unsigned sdf, iters;       // un-wrapped counters
     unsigned nSphere, nBox;    // evaluations by type (torus = sdf - nSphere - nBox)
@@ -407,7 +464,6 @@ RM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
 
 template <class NP, int ACCEL, int PK>
 __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderParams P) {
-    typedef typename NP::F F;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -560,9 +616,11 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
 
         // ---- (d) resolve the pending scene-distance query (scene.ts:144-190) ----
         const bool waiting = (r.phase >= PH_WAIT_MARCH && r.phase <= PH_WAIT_N3);
-        F dist = (F)10;
+        double dd = 10.0;      // the query result handed to the control logic
+        float distF = 10.f;    // fast model: running fp32 min over the candidate primitives
+        int argmin = -1;       // fast model: its primitive
         unsigned cnt = 0;
-        bool needAll = false;
+        bool needAll = false, polish = false;
         if (waiting) {
             if constexpr (ACCEL == RM_ACCEL_NONE) {
                 needAll = true;
@@ -574,11 +632,11 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                     const rm_octree_node* nd = P.scene.oct + ni;
                     int pc = nd->prim_count;
                     if (pc > 0) {
-                        const int32_t* lp = P.scene.leaf_prims + nd->prim_first;
-                        for (int k = 0; k < pc; ++k) dist = NP::fmin_(prim_sdf<NP, PK>(P, lp[k], r.q, r.nSphere, r.nBox), dist);
+                        leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
                         cnt = (unsigned)pc;
+                        polish = true;
                     } else if (nd->is_empty) {
-                        dist = (F)jsmin(10.0, nd->min_distance * 0.99);
+                        dd = jsmin(10.0, nd->min_distance * 0.99);
                     }
                 }
             } else {  // BVH.getPrimitivesAt (bvh.ts:95-121): every leaf whose box contains p, left before right
@@ -592,9 +650,8 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                     if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
                     int left = nd->left, right = nd->right;
                     if (left < 0 && right < 0) {
-                        const int32_t* lp = P.scene.leaf_prims + nd->prim_first;
                         int pc = nd->prim_count;
-                        for (int k = 0; k < pc; ++k) dist = NP::fmin_(prim_sdf<NP, PK>(P, lp[k], r.q, r.nSphere, r.nBox), dist);
+                        leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
                         cnt += (unsigned)pc;
                     } else {
                         if (right >= 0 && sp < kBvhStack) stack[sp++] = right;  // popped after left
@@ -602,11 +659,17 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                     }
                 }
                 if (cnt == 0) needAll = true;  // candidates.length === 0 -> every primitive (scene.ts:173)
+                else polish = true;
             }
+        }
+        if constexpr (!NP::kExact) {
+            // fast model: one fp64 evaluation of the nearest candidate found by the fp32 search
+            if (polish && argmin >= 0)
+                dd = jsmin(prim_sdf_exact(P.scene, argmin, (double)r.q[0], (double)r.q[1], (double)r.q[2], 1), 10.0);
         }
         // dense all-primitives pass for the lanes that need it
         if (needAll) {
-            dist = scene_all_prims<NP, PK>(P, r.q);
+            dd = scene_all_prims<NP, PK>(P, r.q);
             cnt = (unsigned)P.scene.n_prims;
             r.nSphere += P.scene.type_hist[0];
             r.nBox += P.scene.type_hist[1];
@@ -615,7 +678,6 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         // ---- (e) consume the query result ----
         if (waiting) {
             r.sdf += cnt;
-            const double dd = (double)dist;  // control arithmetic continues in double
             switch (r.phase) {
                 case PH_WAIT_MARCH: {
                     r.phase = PH_STEP;
@@ -702,30 +764,30 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                     break;
                 }
                 case PH_WAIT_N0:  // raymarcher.ts:124-128
-                    r.nd = dist;
+                    r.nd = dd;
                     r.q[0] = f32r((double)r.h[0] - 0.01);
                     r.phase = PH_WAIT_N1;
                     break;
                 case PH_WAIT_N1:
-                    r.n0 = (float)(r.nd - dist);  // n[0] = d - d(p - e_x): Float32Array store
+                    r.n0 = f32r(r.nd - dd);  // n[0] = d - d(p - e_x): Float32Array store
                     r.q[0] = r.h[0];
                     r.q[1] = f32r((double)r.h[1] - 0.01);
                     r.phase = PH_WAIT_N2;
                     break;
                 case PH_WAIT_N2:
-                    r.n1 = (float)(r.nd - dist);
+                    r.n1 = f32r(r.nd - dd);
                     r.q[1] = r.h[1];
                     r.q[2] = f32r((double)r.h[2] - 0.01);
                     r.phase = PH_WAIT_N3;
                     break;
                 default: {  // PH_WAIT_N3: normalise (raymarcher.ts:131-133)
-                    r.n2 = (float)(r.nd - dist);
-                    F x = (F)r.n0, y = (F)r.n1, z = (F)r.n2;
-                    F len = x * x + y * y + z * z;
-                    if (len > (F)0) len = NP::rsqrt_(len);
-                    r.n0 = (float)(x * len);
-                    r.n1 = (float)(y * len);
-                    r.n2 = (float)(z * len);
+                    r.n2 = f32r(r.nd - dd);
+                    double x = (double)r.n0, y = (double)r.n1, z = (double)r.n2;
+                    double len = x * x + y * y + z * z;
+                    if (len > 0.0) len = 1.0 / sqrt(len);
+                    r.n0 = f32r(x * len);
+                    r.n1 = f32r(y * len);
+                    r.n2 = f32r(z * len);
                     r.phase = PH_FINAL;
                     break;
                 }
@@ -735,9 +797,9 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         // ---- (f) finalize: quantise, shade, store, accumulate diagnostics (raymarcher.ts:103-106) ----
         if (r.phase == PH_FINAL) {
             size_t idx = (size_t)r.py * P.width + r.px;
-            unsigned nb0 = to_u8_clamp(((F)r.n0 + (F)1) * (F)0.5 * (F)255);
-            unsigned nb1 = to_u8_clamp(((F)r.n1 + (F)1) * (F)0.5 * (F)255);
-            unsigned nb2 = to_u8_clamp(((F)r.n2 + (F)1) * (F)0.5 * (F)255);
+            unsigned nb0 = to_u8_clamp(((double)r.n0 + 1.0) * 0.5 * 255.0);
+            unsigned nb1 = to_u8_clamp(((double)r.n1 + 1.0) * 0.5 * 255.0);
+            unsigned nb2 = to_u8_clamp(((double)r.n2 + 1.0) * 0.5 * 255.0);
             unsigned db = to_u8_clamp(r.depth);
             unsigned sdf16 = r.sdf & 0xffffu, it16 = r.iters & 0xffffu;
             P.depth[idx] = (uint8_t)db;
