@@ -267,6 +267,7 @@ struct Ray {
     int phase;
     int px, py;  // pixel (x, band-local y)
     bool done;   // rayMarch has returned (depth is valid)
+    bool pending;  // parked on the dense all-primitives pass
     int cur, nIv;  // BVH interval cursor (bvh.ts:204-240)
 };
 
@@ -486,9 +487,24 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
     int tile = -1, tilePos = kTileW * kTileH;
     bool queueEmpty = false;
 
+    // Warp scheduler thresholds.  Expensive, warp-serialising stages are deferred until enough lanes
+    // want them: the all-primitives pass (cost ~ n_prims per execution, independent of how many lanes
+    // take part) runs when kBfLanes lanes are parked on it, BVH ray set-up (a full tree traversal) when
+    // kInitLanes lanes are free.  Both are forced as soon as no lane can make progress otherwise.
+    const int bfLanes = (ACCEL == RM_ACCEL_NONE) ? 1 : (P.scene.n_prims >= 2048 ? 24 : (P.scene.n_prims >= 256 ? 12 : 1));
+    const int initLanes = (ACCEL == RM_ACCEL_BVH) ? (P.scene.n_prims >= 256 ? 16 : 4) : 1;
+    r.pending = false;
+
     for (;;) {
         // ---- (a) refill: lanes without a ray claim the next pixels of the warp's current tile ----
         unsigned idle = __ballot_sync(kFull, r.phase == PH_IDLE);
+        {
+            const int nIdle = __popc(idle);
+            const int nPend = __popc(__ballot_sync(kFull, r.pending));
+            const int nAct = 32 - nIdle - nPend;
+            const bool doRefill = (nAct == 0) ? (nPend < bfLanes) : (nIdle >= initLanes);
+            if (!doRefill) idle = 0u;
+        }
         while (idle && !queueEmpty) {
             if (tilePos >= kTileW * kTileH) {
                 unsigned t = 0;
@@ -521,7 +537,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             tilePos += take;
             idle = __ballot_sync(kFull, r.phase == PH_IDLE);
         }
-        if (__ballot_sync(kFull, r.phase != PH_IDLE) == 0u) break;  // queue drained and every ray retired
+        if (queueEmpty && __ballot_sync(kFull, r.phase != PH_IDLE) == 0u) break;  // queue drained and every ray retired
 
         // ---- (b) ray set-up (raymarcher.ts:73-88 + onRayMarchStart) ----
         if (r.phase == PH_NEW) {
@@ -621,7 +637,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         int argmin = -1;       // fast model: its primitive
         unsigned cnt = 0;
         bool needAll = false, polish = false;
-        if (waiting) {
+        if (waiting && !r.pending) {
             if constexpr (ACCEL == RM_ACCEL_NONE) {
                 needAll = true;
             } else if constexpr (ACCEL == RM_ACCEL_OCTREE) {
@@ -667,16 +683,24 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             if (polish && argmin >= 0)
                 dd = jsmin(prim_sdf_exact(P.scene, argmin, (double)r.q[0], (double)r.q[1], (double)r.q[2], 1), 10.0);
         }
-        // dense all-primitives pass for the lanes that need it
-        if (needAll) {
-            dd = scene_all_prims<NP, PK>(P, r.q);
-            cnt = (unsigned)P.scene.n_prims;
-            r.nSphere += P.scene.type_hist[0];
-            r.nBox += P.scene.type_hist[1];
+        // dense all-primitives pass: lanes that need it park (r.pending) until enough of them have
+        // gathered or nothing else in the warp can make progress
+        r.pending = r.pending || needAll;
+        {
+            const unsigned pend = __ballot_sync(kFull, r.pending);
+            const unsigned others = __ballot_sync(kFull, r.phase != PH_IDLE && !r.pending);
+            const bool doAll = pend != 0u && (__popc(pend) >= bfLanes || others == 0u);
+            if (doAll && r.pending) {
+                dd = scene_all_prims<NP, PK>(P, r.q);
+                cnt = (unsigned)P.scene.n_prims;
+                r.nSphere += P.scene.type_hist[0];
+                r.nBox += P.scene.type_hist[1];
+                r.pending = false;
+            }
         }
 
         // ---- (e) consume the query result ----
-        if (waiting) {
+        if (waiting && !r.pending) {
             r.sdf += cnt;
             switch (r.phase) {
                 case PH_WAIT_MARCH: {
