@@ -145,53 +145,176 @@ RM_DEV float prim_sdf_f32(const float4* __restrict__ rec, int j, const float q[3
     }
 }
 
-// Dense all-primitives evaluation: closest = min over every primitive (scene.ts:183-189), starting
-// from MAX_DIST = 10.  Every lane walks the same primitive index -> broadcast loads.
-//   exact model: the reference's Math.min chain in doubles;
-//   fast model : fp32 SEARCH for the nearest primitive (the FLOP-dominant N-primitive loop), then ONE
-//                fp64 evaluation of that primitive ("f32 search, f64 polish").  The hot loop keeps only
-//                a running min per 32-primitive chunk (1 FMNMX per evaluation); the winning chunk is
-//                re-scanned once to recover the index.
-constexpr int kChunk = 32;
-template <class NP, int PK>
-RM_DEV double scene_all_prims(const RenderParams& P, const float q[3]) {
-    const int n = P.scene.n_prims;
-    if constexpr (NP::kExact) {
-        double closest = 10.0;
-        for (int j = 0; j < n; ++j)
-            closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
-        return closest;
+// ------------------------------------------------------------------------------------------
+// TMA bulk staging of primitive records into shared memory (per-warp double buffer)
+// ------------------------------------------------------------------------------------------
+constexpr int kStageBytes = 2048;  // one stage = 128 translation-sphere records or 32 general records
+constexpr int kWarpsPerCta = 4;
+constexpr int kChunk = 32;         // argmin granularity of the fp32 search
+constexpr int kQueueCap = kWarpsPerCta * 32;  // each thread has at most one request outstanding
+
+RM_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RM_DEV void mbar_init(uint32_t bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+RM_DEV void mbar_expect_tx(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+RM_DEV void bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {  // SASS: UBLKCP
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+RM_DEV void mbar_wait(uint32_t bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// Per-warp staging state: two 2 KB shared-memory stages + two mbarriers, phase parity kept in a register.
+struct WarpStage {
+    const float4* buf[2];
+    uint32_t bufAddr[2], bar[2];
+    unsigned phase;
+};
+
+template <int PK>
+RM_DEV float sdf_from_stage(const float4* __restrict__ st, int k, const float q[3]) {
+    if constexpr (PK == PK_TSPHERE) {
+        const float4 s = st[k];
+        float lx = q[0] + s.x, ly = q[1] + s.y, lz = q[2] + s.z;
+        return NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - s.w;
     } else {
-        const float4* __restrict__ rec = P.scene.rec;
-        float best = 10.f;
-        int bestChunk = -1, bestIdx = -1;
-        int j = 0;
-        for (; j + kChunk <= n; j += kChunk) {
-            float m = prim_sdf_f32<PK>(rec, j, q);
-#pragma unroll 8
-            for (int k = 1; k < kChunk; ++k) m = fminf(m, prim_sdf_f32<PK>(rec, j + k, q));
+        const float4 r0 = st[4 * k + 0], r1 = st[4 * k + 1], r2 = st[4 * k + 2], pr = st[4 * k + 3];
+        float lx = fmaf(r0.x, q[0], fmaf(r0.y, q[1], fmaf(r0.z, q[2], r0.w)));
+        float ly = fmaf(r1.x, q[0], fmaf(r1.y, q[1], fmaf(r1.z, q[2], r1.w)));
+        float lz = fmaf(r2.x, q[0], fmaf(r2.y, q[1], fmaf(r2.z, q[2], r2.w)));
+        int type = __float_as_int(pr.w);
+        if (type == RM_PRIM_SPHERE) {
+            return NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - pr.x;
+        } else if (type == RM_PRIM_BOX) {
+            float q0 = fabsf(lx) - pr.x, q1 = fabsf(ly) - pr.y, q2 = fabsf(lz) - pr.z;
+            float o0 = fmaxf(q0, 0.f), o1 = fmaxf(q1, 0.f), o2 = fmaxf(q2, 0.f);
+            return NumFast::sqrt_(fmaf(o0, o0, fmaf(o1, o1, o2 * o2))) + fminf(fmaxf(q0, fmaxf(q1, q2)), 0.f);
+        } else {
+            float qx = NumFast::sqrt_(fmaf(lx, lx, lz * lz)) - pr.x;
+            return NumFast::sqrt_(fmaf(qx, qx, ly * ly)) - pr.y;
+        }
+    }
+}
+
+// Dense all-primitives evaluation: closest = min over every primitive (scene.ts:183-189), from MAX_DIST = 10.
+//   exact model: the reference's Math.min chain in doubles (per lane, records read from global memory);
+//   fast model : executed by the WHOLE warp (call it convergently; lanes with active == false just help
+//                with the staging).  The primitive array streams through the warp's two shared-memory
+//                stages with TMA bulk copies (one elected lane issues cp.async.bulk; completion on an
+//                mbarrier) while every lane evaluates its own sample point against the stage in flight —
+//                one broadcast LDS.128 per primitive.  fp32 SEARCH for the nearest primitive keeps a
+//                running min per 32-primitive chunk (FMNMX only); the winning chunk is re-scanned once
+//                to recover the index, and that ONE primitive is evaluated in fp64 (the "polish").
+// fp32 search over the stages c = first, first + stride, ... (every warp of a CTA takes an interleaved
+// share when the pass is CTA-cooperative; first = 0, stride = 1 when a warp serves itself).
+// Returns the running min and a code: idx >= 0 exact index | (chunk | kChunkFlag) 32-primitive chunk | -1 none.
+constexpr int kChunkFlag = 0x40000000;
+template <int PK>
+RM_DEV void search_stages(const RenderParams& P, const float q[3], WarpStage& ws, int lane, int first, int stride, float& best,
+                          int& code) {
+    constexpr int kF4 = (PK == PK_TSPHERE) ? 1 : 4;     // float4 per primitive
+    constexpr int kPerStage = kStageBytes / (16 * kF4);  // primitives per stage (128 / 32)
+    const int n = P.scene.n_prims;
+    const float4* __restrict__ rec = P.scene.rec;
+    const int nStages = (n + kPerStage - 1) / kPerStage;
+    const int myStages = nStages > first ? (nStages - first + stride - 1) / stride : 0;
+    auto issue = [&](int i) {  // elected lane: my i-th stage -> buffer i&1
+        const int c = first + i * stride, sgi = i & 1;
+        const int cnt = min(kPerStage, n - c * kPerStage);
+        const unsigned bytes = (unsigned)(cnt * 16 * kF4);
+        mbar_expect_tx(ws.bar[sgi], bytes);
+        bulk_g2s(ws.bufAddr[sgi], rec + (size_t)c * kPerStage * kF4, bytes, ws.bar[sgi]);
+    };
+    if (lane == 0) {
+        if (myStages > 0) issue(0);
+        if (myStages > 1) issue(1);
+    }
+    best = 10.f;
+    code = -1;
+    for (int i = 0; i < myStages; ++i) {
+        const int sgi = i & 1;
+        mbar_wait(ws.bar[sgi], (ws.phase >> sgi) & 1u);
+        ws.phase ^= (1u << sgi);
+        const float4* __restrict__ st = ws.buf[sgi];
+        const int base = (first + i * stride) * kPerStage;
+        const int cnt = min(kPerStage, n - base);
+        int k = 0;
+        for (; k + kChunk <= cnt; k += kChunk) {
+            float m = sdf_from_stage<PK>(st, k, q);
+#pragma unroll
+            for (int u = 1; u < kChunk; ++u) m = fminf(m, sdf_from_stage<PK>(st, k + u, q));
             if (m < best) {
                 best = m;
-                bestChunk = j;
+                code = (base + k) | kChunkFlag;
             }
         }
-        for (; j < n; ++j) {  // tail (and the whole scene when n < 32)
-            float d = prim_sdf_f32<PK>(rec, j, q);
+        for (; k < cnt; ++k) {  // tail (and the whole scene when n < 32)
+            float d = sdf_from_stage<PK>(st, k, q);
             if (d < best) {
                 best = d;
-                bestIdx = j;
-                bestChunk = -1;
+                code = base + k;
             }
         }
-        if (bestChunk >= 0) {
-            for (int k = 0; k < kChunk; ++k)
-                if (prim_sdf_f32<PK>(rec, bestChunk + k, q) == best) {
-                    bestIdx = bestChunk + k;
-                    break;
-                }
+        __syncwarp();  // every lane is done reading this stage before it is refilled
+        if (lane == 0 && i + 2 < myStages) issue(i + 2);
+    }
+}
+
+// Turn the search result into the scene distance: recover the index inside the winning chunk, then ONE
+// fp64 evaluation of that primitive (the "polish"), clamped to MAX_DIST like scene.ts:145-146.
+template <int PK>
+RM_DEV double finish_search(const RenderParams& P, const float q[3], int code) {
+    if (code < 0) return 10.0;  // nothing closer than MAX_DIST
+    int idx = code;
+    if (code & kChunkFlag) {
+        const int chunk = code & ~kChunkFlag;
+        float mm = 3.0e38f;
+        for (int k = 0; k < kChunk; ++k) {
+            float d = prim_sdf_f32<PK>(P.scene.rec, chunk + k, q);
+            if (d < mm) {
+                mm = d;
+                idx = chunk + k;
+            }
         }
-        if (bestIdx < 0) return 10.0;  // nothing closer than MAX_DIST
-        return jsmin(prim_sdf_exact(P.scene, bestIdx, (double)q[0], (double)q[1], (double)q[2], 1), 10.0);
+    }
+    return jsmin(prim_sdf_exact(P.scene, idx, (double)q[0], (double)q[1], (double)q[2], 1), 10.0);
+}
+
+// Dense all-primitives evaluation by one warp for its own lanes: closest = min over every primitive
+// (scene.ts:183-189), from MAX_DIST = 10.
+//   exact model: the reference's Math.min chain in doubles (per lane, records read from global memory);
+//   fast model : executed by the WHOLE warp (call it convergently; lanes with active == false only help
+//                with the staging).  The primitive array streams through the warp's two shared-memory
+//                stages with TMA bulk copies (one elected lane issues cp.async.bulk; completion on an
+//                mbarrier) while every lane evaluates its own sample point against the stage in flight —
+//                one broadcast LDS.128 per primitive.  The fp32 SEARCH keeps only a running min per
+//                32-primitive chunk (FMNMX); the winner is re-scanned once for its index and that ONE
+//                primitive is evaluated in fp64.
+template <class NP, int PK>
+RM_DEV double scene_all_prims(const RenderParams& P, const float q[3], WarpStage& ws, bool active, int lane) {
+    if constexpr (NP::kExact) {
+        const int n = P.scene.n_prims;
+        double closest = 10.0;
+        if (active)
+            for (int j = 0; j < n; ++j)
+                closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
+        return closest;
+    } else {
+        float best;
+        int code;
+        search_stages<PK>(P, q, ws, lane, 0, 1, best, code);
+        if (!active) return 10.0;
+        return finish_search<PK>(P, q, code);
     }
 }
 
@@ -483,26 +606,144 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
     IvList iv;  // only touched when ACCEL == BVH (lives in local memory)
     LaneStats st;
 
+    // ---- shared memory: per-warp TMA stages for the primitive stream, and the CTA-wide request queue of
+    //      the all-primitives service (requests are just a point, so they can move between warps even
+    //      though ray state cannot: any warp that finds 32 of them serves them at full lane occupancy) ----
+    __shared__ __align__(128) float4 shStage[kWarpsPerCta][2][kStageBytes / 16];
+    __shared__ __align__(8) unsigned long long shBar[kWarpsPerCta][2];
+    __shared__ float4 shReq[kQueueCap];               // ring of requests: x, y, z, owner thread
+    __shared__ double shRes[kWarpsPerCta * 32];        // results by owner thread
+    __shared__ unsigned shReady[kWarpsPerCta * 32];
+    __shared__ float shPartBest[kWarpsPerCta][32];     // per-warp partial search results of the batch in flight
+    __shared__ int shPartCode[kWarpsPerCta][32];
+    __shared__ unsigned shTail, shHead, shGo, shStuck, shFinished;
+    const int warpId = threadIdx.x >> 5;
+    WarpStage ws;
+    ws.phase = 0u;
+#pragma unroll
+    for (int sgi = 0; sgi < 2; ++sgi) {
+        ws.buf[sgi] = shStage[warpId][sgi];
+        ws.bufAddr[sgi] = smem_u32(shStage[warpId][sgi]);
+        ws.bar[sgi] = smem_u32(&shBar[warpId][sgi]);
+    }
+    if constexpr (!NP::kExact) {
+        if (lane == 0) {
+            mbar_init(ws.bar[0], 1);
+            mbar_init(ws.bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    shReady[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        shTail = 0u;
+        shHead = 0u;
+        shGo = 0u;
+        shStuck = 0u;
+        shFinished = 0u;
+    }
+    __syncthreads();
+    bool wasStuck = false, wasFinished = false;  // this warp's contribution to shStuck / shFinished
+    // the shared queue pays off when one all-primitives pass is much more expensive than a march step
+    const bool useQueue = !NP::kExact && (ACCEL == RM_ACCEL_BVH) && P.scene.n_prims >= 256;
+
     // warp-uniform work-queue cursor
     int tile = -1, tilePos = kTileW * kTileH;
     bool queueEmpty = false;
 
-    // Warp scheduler thresholds.  Expensive, warp-serialising stages are deferred until enough lanes
-    // want them: the all-primitives pass (cost ~ n_prims per execution, independent of how many lanes
-    // take part) runs when kBfLanes lanes are parked on it, BVH ray set-up (a full tree traversal) when
-    // kInitLanes lanes are free.  Both are forced as soon as no lane can make progress otherwise.
-    const int bfLanes = (ACCEL == RM_ACCEL_NONE) ? 1 : (P.scene.n_prims >= 2048 ? 24 : (P.scene.n_prims >= 256 ? 12 : 1));
+    // Warp scheduler.  Expensive, warp-serialising stages are deferred until enough lanes want them: BVH
+    // ray set-up (a full tree traversal) runs when initLanes lanes are free or nothing else can progress;
+    // the all-primitives pass goes through the CTA-wide request queue below.
     const int initLanes = (ACCEL == RM_ACCEL_BVH) ? (P.scene.n_prims >= 256 ? 16 : 4) : 1;
     r.pending = false;
 
     for (;;) {
+        // ---- (0) CTA rendezvous for the all-primitives pass (cooperative mode only) ----
+        if (useQueue) {
+            bool leave = false;
+            for (;;) {
+                unsigned go = 0;
+                if (lane == 0) go = *(volatile unsigned*)&shGo;
+                go = __shfl_sync(kFull, go, 0);
+                if (go) {
+                    // Every warp of the CTA joins: request i <-> lane i in each warp; warp w searches the stages
+                    // c = w (mod W) of the primitive stream, partial minima are combined through shared memory.
+                    __syncthreads();
+                    const unsigned head = *(volatile unsigned*)&shHead, tail = *(volatile unsigned*)&shTail;
+                    const unsigned nBatch = min(32u, tail - head);
+                    float rq[3] = {0.f, 0.f, 0.f};
+                    if ((unsigned)lane < nBatch) {
+                        const float4 v = shReq[(head + (unsigned)lane) % kQueueCap];
+                        rq[0] = v.x;
+                        rq[1] = v.y;
+                        rq[2] = v.z;
+                    }
+                    float pbest;
+                    int pcode;
+                    if constexpr (!NP::kExact) {
+                        search_stages<PK>(P, rq, ws, lane, warpId, kWarpsPerCta, pbest, pcode);
+                    } else {
+                        pbest = 10.f;
+                        pcode = -1;
+                    }
+                    shPartBest[warpId][lane] = pbest;
+                    shPartCode[warpId][lane] = pcode;
+                    __syncthreads();
+                    // combine: request i is finished by thread i (warp i / 32 ... only the first 32 threads have one)
+                    if (threadIdx.x < nBatch) {
+                        const float4 v = shReq[(head + threadIdx.x) % kQueueCap];
+                        const float q3[3] = {v.x, v.y, v.z};
+                        const int owner = __float_as_int(v.w);
+                        double res;
+                        if constexpr (!NP::kExact) {
+                            float bb = shPartBest[0][threadIdx.x];
+                            int bc = shPartCode[0][threadIdx.x];
+#pragma unroll
+                            for (int w = 1; w < kWarpsPerCta; ++w) {
+                                const float ob = shPartBest[w][threadIdx.x];
+                                if (ob < bb) {
+                                    bb = ob;
+                                    bc = shPartCode[w][threadIdx.x];
+                                }
+                            }
+                            res = finish_search<PK>(P, q3, bc);
+                        } else {
+                            res = 10.0;
+                            for (int j = 0; j < P.scene.n_prims; ++j)
+                                res = jsmin(prim_sdf_exact(P.scene, j, (double)q3[0], (double)q3[1], (double)q3[2], P.length_sqrt), res);
+                        }
+                        shRes[owner] = res;
+                        shReady[owner] = 1u;
+                    }
+                    if (threadIdx.x == 0) {
+                        shHead = head + nBatch;
+                        shGo = (tail - head - nBatch >= 32u) ? 1u : 0u;
+                    }
+                    __syncthreads();
+                    continue;
+                }
+                if (!wasStuck) break;  // run a normal iteration
+                // stuck: leave the wait as soon as one of our parked lanes has its result, or everybody is finished
+                const unsigned got = __ballot_sync(kFull, r.pending && ((volatile unsigned*)shReady)[threadIdx.x] != 0u);
+                if (got) break;
+                unsigned fin = 0;
+                if (lane == 0) fin = *(volatile unsigned*)&shFinished;
+                fin = __shfl_sync(kFull, fin, 0);
+                if (wasFinished && fin == (unsigned)kWarpsPerCta) {
+                    leave = true;
+                    break;
+                }
+                __nanosleep(128);
+            }
+            if (leave) break;
+        }
+
         // ---- (a) refill: lanes without a ray claim the next pixels of the warp's current tile ----
         unsigned idle = __ballot_sync(kFull, r.phase == PH_IDLE);
         {
             const int nIdle = __popc(idle);
             const int nPend = __popc(__ballot_sync(kFull, r.pending));
             const int nAct = 32 - nIdle - nPend;
-            const bool doRefill = (nAct == 0) ? (nPend < bfLanes) : (nIdle >= initLanes);
+            const bool doRefill = (nAct == 0) || (nIdle >= initLanes);
             if (!doRefill) idle = 0u;
         }
         while (idle && !queueEmpty) {
@@ -537,7 +778,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             tilePos += take;
             idle = __ballot_sync(kFull, r.phase == PH_IDLE);
         }
-        if (queueEmpty && __ballot_sync(kFull, r.phase != PH_IDLE) == 0u) break;  // queue drained and every ray retired
+        if (!useQueue && queueEmpty && __ballot_sync(kFull, r.phase != PH_IDLE) == 0u) break;  // queue drained and every ray retired
 
         // ---- (b) ray set-up (raymarcher.ts:73-88 + onRayMarchStart) ----
         if (r.phase == PH_NEW) {
@@ -683,19 +924,48 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             if (polish && argmin >= 0)
                 dd = jsmin(prim_sdf_exact(P.scene, argmin, (double)r.q[0], (double)r.q[1], (double)r.q[2], 1), 10.0);
         }
-        // dense all-primitives pass: lanes that need it park (r.pending) until enough of them have
-        // gathered or nothing else in the warp can make progress
-        r.pending = r.pending || needAll;
-        {
-            const unsigned pend = __ballot_sync(kFull, r.pending);
-            const unsigned others = __ballot_sync(kFull, r.phase != PH_IDLE && !r.pending);
-            const bool doAll = pend != 0u && (__popc(pend) >= bfLanes || others == 0u);
-            if (doAll && r.pending) {
-                dd = scene_all_prims<NP, PK>(P, r.q);
+        // ---- (d2) the dense all-primitives pass ----
+        if (!useQueue) {
+            // small scenes / no acceleration structure: the warp serves its own lanes right away
+            const unsigned need = __ballot_sync(kFull, needAll);
+            if (need) {
+                double v = scene_all_prims<NP, PK>(P, r.q, ws, needAll, lane);
+                if (needAll) {
+                    dd = v;
+                    cnt = (unsigned)P.scene.n_prims;
+                    r.nSphere += P.scene.type_hist[0];
+                    r.nBox += P.scene.type_hist[1];
+                }
+            }
+        } else {
+            // CTA-cooperative mode: requests go to the shared ring; the pass itself runs in bf_phase (loop top)
+            volatile unsigned* vReady = shReady;
+            // 1. owners pick up finished requests
+            if (r.pending && vReady[threadIdx.x] != 0u) {
+                dd = ((volatile double*)shRes)[threadIdx.x];
+                vReady[threadIdx.x] = 0u;
+                r.pending = false;
                 cnt = (unsigned)P.scene.n_prims;
                 r.nSphere += P.scene.type_hist[0];
                 r.nBox += P.scene.type_hist[1];
-                r.pending = false;
+            }
+            // 2. lanes that need every primitive publish a request (warp-aggregated slot reservation)
+            const unsigned need = __ballot_sync(kFull, needAll);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(&shTail, (unsigned)__popc(need));
+                base = __shfl_sync(kFull, base, leader);
+                if (needAll) {
+                    const unsigned slot = base + (unsigned)__popc(need & lt_mask);
+                    shReq[slot % kQueueCap] = make_float4(r.q[0], r.q[1], r.q[2], __int_as_float((int)threadIdx.x));
+                    r.pending = true;
+                }
+                __syncwarp();
+                if (lane == leader) {
+                    __threadfence_block();
+                    if (base + (unsigned)__popc(need) - *(volatile unsigned*)&shHead >= 32u) *(volatile unsigned*)&shGo = 1u;  // a full batch is waiting
+                }
             }
         }
 
@@ -850,6 +1120,28 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             st.max_iters = max(st.max_iters, it16);
             st.min_iters = min(st.min_iters, it16);
             r.phase = PH_IDLE;
+        }
+
+        // ---- (g) cooperative mode: publish whether this warp can still make progress on its own ----
+        if (useQueue) {
+            const unsigned pendM = __ballot_sync(kFull, r.pending);
+            const unsigned actM = __ballot_sync(kFull, r.phase != PH_IDLE && !r.pending);
+            const unsigned idleM = __ballot_sync(kFull, r.phase == PH_IDLE);
+            const bool stuckNow = (actM == 0u) && (queueEmpty || idleM == 0u);
+            const bool finishedNow = stuckNow && pendM == 0u;
+            if (lane == 0) {
+                if (finishedNow != wasFinished) atomicAdd(&shFinished, finishedNow ? 1u : 0xffffffffu);
+                if (stuckNow != wasStuck) {
+                    const unsigned prev = atomicAdd(&shStuck, stuckNow ? 1u : 0xffffffffu);
+                    // last warp to get stuck: nobody can progress any more -> serve whatever is queued
+                    if (stuckNow && prev + 1u == (unsigned)kWarpsPerCta) {
+                        __threadfence_block();
+                        if (*(volatile unsigned*)&shTail != *(volatile unsigned*)&shHead) *(volatile unsigned*)&shGo = 1u;
+                    }
+                }
+            }
+            wasStuck = stuckNow;
+            wasFinished = finishedNow;
         }
     }
 
