@@ -430,6 +430,22 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             }
         }
         ds.n_nodes = nn;
+        if (s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64)) {
+            // fast path: locate leaf boxes through a uniform grid instead of descending the tree
+            LeafGrid grid;
+            build_leaf_grid(bvh, grid);
+            static_assert(sizeof(LeafRef) == sizeof(uint3), "LeafRef layout");
+            for (int k = 0; k < 3; ++k) {
+                ds.grid_dims[k] = grid.dims[k];
+                ds.grid_origin[k] = grid.origin[k];
+                ds.grid_inv[k] = grid.inv_cell[k];
+                ds.grid_cell[k] = grid.cell[k];
+            }
+            if ((rc = upload(c, (const uint3*)grid.leaves.data(), grid.leaves.size(), &ds.grid_leaves))) return rc;
+            if ((rc = upload(c, grid.cell_start.data(), grid.cell_start.size(), &ds.grid_cell_start))) return rc;
+            if ((rc = upload(c, grid.cell_leaf.data(), grid.cell_leaf.size(), &ds.grid_cell_leaf))) return rc;
+            CU(c, cudaStreamSynchronize(c->stream));  // `grid` goes out of scope
+        }
         if ((rc = upload(c, bvh.data(), bvh.size(), &ds.bvh))) return rc;
         if ((rc = upload(c, oct.data(), oct.size(), &ds.oct))) return rc;
         if ((rc = upload(c, leaf.data(), leaf.size(), &ds.leaf_prims))) return rc;

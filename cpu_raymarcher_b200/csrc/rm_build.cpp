@@ -200,6 +200,72 @@ void build_bvh(const std::vector<PrimGeom>& geom, std::vector<rm_bvh_node>& node
     b.build(all, bmin, bmax, 0);
 }
 
+// ------------------------------------------------------------------------------------ leaf grid
+void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
+    g = LeafGrid();
+    if (nodes.empty()) {
+        g.cell_start.assign(2, 0u);
+        return;
+    }
+    std::vector<int32_t> leafNodes;
+    for (size_t i = 0; i < nodes.size(); ++i)
+        if (nodes[i].left < 0 && nodes[i].right < 0 && nodes[i].prim_count > 0) leafNodes.push_back((int32_t)i);
+    const rm_bvh_node& root = nodes[0];
+    // resolution: about 2.5 * cbrt(#leaves) cells along the longest axis, at most 128 (ranges pack into bytes)
+    double ext[3], maxExt = 0;
+    for (int k = 0; k < 3; ++k) {
+        ext[k] = (double)root.bmax[k] - (double)root.bmin[k];
+        if (ext[k] > maxExt) maxExt = ext[k];
+    }
+    int target = (int)std::lround(2.5 * std::cbrt((double)std::max<size_t>(leafNodes.size(), 1)));
+    target = std::min(128, std::max(1, target));
+    for (int k = 0; k < 3; ++k) {
+        g.origin[k] = root.bmin[k];
+        int d = (maxExt > 0 && ext[k] > 0) ? (int)std::ceil(target * ext[k] / maxExt) : 1;
+        g.dims[k] = std::min(128, std::max(1, d));
+        g.cell[k] = ext[k] > 0 ? (float)(ext[k] / g.dims[k]) : 0.f;
+        g.inv_cell[k] = ext[k] > 0 ? (float)(g.dims[k] / ext[k]) : 0.f;
+    }
+    const double eps = 1e-3;  // outward slack in cell units: covers every float/double rounding of cell indices
+    auto lo_idx = [&](double x, int k) {
+        if (g.inv_cell[k] == 0.f) return 0;
+        double c = std::floor((x - (double)g.origin[k]) * (double)g.inv_cell[k] - eps);
+        return (int)std::min<double>(g.dims[k] - 1, std::max<double>(0, c));
+    };
+    auto hi_idx = [&](double x, int k) {
+        if (g.inv_cell[k] == 0.f) return 0;
+        double c = std::floor((x - (double)g.origin[k]) * (double)g.inv_cell[k] + eps);
+        return (int)std::min<double>(g.dims[k] - 1, std::max<double>(0, c));
+    };
+    const size_t nCells = (size_t)g.dims[0] * g.dims[1] * g.dims[2];
+    g.leaves.resize(leafNodes.size());
+    std::vector<uint32_t> count(nCells + 1, 0u);
+    for (size_t li = 0; li < leafNodes.size(); ++li) {
+        const rm_bvh_node& nd = nodes[(size_t)leafNodes[li]];
+        int lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = lo_idx(nd.bmin[k], k);
+            hi[k] = hi_idx(nd.bmax[k], k);
+        }
+        g.leaves[li] = {leafNodes[li], (uint32_t)(lo[0] | (lo[1] << 8) | (lo[2] << 16)), (uint32_t)(hi[0] | (hi[1] << 8) | (hi[2] << 16))};
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) count[((size_t)z * g.dims[1] + y) * g.dims[0] + x + 1]++;
+    }
+    for (size_t c = 0; c < nCells; ++c) count[c + 1] += count[c];
+    g.cell_start = count;
+    g.cell_leaf.assign(g.cell_start[nCells], 0);
+    std::vector<uint32_t> fill(g.cell_start.begin(), g.cell_start.end() - 1);
+    for (size_t li = 0; li < g.leaves.size(); ++li) {  // ascending leaf ordinal within each cell
+        const LeafRef& lr = g.leaves[li];
+        int lo[3] = {(int)(lr.lo & 255), (int)((lr.lo >> 8) & 255), (int)((lr.lo >> 16) & 255)};
+        int hi[3] = {(int)(lr.hi & 255), (int)((lr.hi >> 8) & 255), (int)((lr.hi >> 16) & 255)};
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) g.cell_leaf[fill[((size_t)z * g.dims[1] + y) * g.dims[0] + x]++] = (int32_t)li;
+    }
+}
+
 // --------------------------------------------------------------------------------------- octree
 static double box_distance(const float* amin, const float* amax, const float* bmin, const float* bmax) {  // distanceToBox
     double d[3];

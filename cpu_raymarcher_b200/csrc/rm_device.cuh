@@ -392,6 +392,8 @@ struct Ray {
     bool done;   // rayMarch has returned (depth is valid)
     bool pending;  // parked on the dense all-primitives pass
     int cur, nIv;  // BVH interval cursor (bvh.ts:204-240)
+    double curEnter, curExit;  // the interval under the cursor
+    bool curValid, lazy;
 };
 
 // BVH per-ray interval list.  The cursor advances at most one slot per march-loop index
@@ -442,17 +444,191 @@ static __device__ __noinline__ int bvh_collect(const rm_bvh_node* __restrict__ n
     return n;
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast path: the same BVH questions answered through the uniform leaf grid (rm_host.h LeafGrid).
+// Every accepted leaf still goes through the reference's exact box test / slab test; the grid only
+// decides which leaf boxes are looked at, with conservative cell ranges.
+// ------------------------------------------------------------------------------------------
+RM_DEV int grid_coord(float x, float o, float inv, int n) {
+    int c = (int)floorf((x - o) * inv);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+RM_DEV bool cell_in_range(uint32_t lo, uint32_t hi, int x, int y, int z) {
+    return x >= (int)(lo & 255u) && x <= (int)(hi & 255u) && y >= (int)((lo >> 8) & 255u) && y <= (int)((hi >> 8) & 255u) &&
+           z >= (int)((lo >> 16) & 255u) && z <= (int)((hi >> 16) & 255u);
+}
+
+// Lazy, ordered generation of the per-ray leaf intervals of BVH.findRayIntersections (bvh.ts:126-178).
+// A 3D-DDA walks the grid cells the ray crosses front to back.  A leaf is examined in the FIRST visited
+// cell of its (convex) cell range, with the reference's exact slab test; accepted intervals wait in a small
+// buffer sorted by (tEnter, right-first DFS order) and are released once the walk has passed their tEnter,
+// so the consumer sees exactly the stably-sorted list of the reference — but only as far as the march needs.
+constexpr int kPendCap = 64;
+struct LazyIv {
+    double tNext[3], tDelta[3];
+    double tEnd, safeT;
+    double pEnter[kPendCap], pExit[kPendCap];
+    int pNode[kPendCap];
+    int cell[3], prev[3], step[3];
+    int head, count;
+    bool done, overflow;
+};
+
+RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node) {
+    if (lz.head + lz.count >= kPendCap) {  // compact
+        for (int i = 0; i < lz.count; ++i) {
+            lz.pEnter[i] = lz.pEnter[lz.head + i];
+            lz.pExit[i] = lz.pExit[lz.head + i];
+            lz.pNode[i] = lz.pNode[lz.head + i];
+        }
+        lz.head = 0;
+        if (lz.count >= kPendCap) {
+            lz.overflow = true;
+            return;
+        }
+    }
+    int pos = lz.head + lz.count;
+    // ascending tEnter; ties in right-first DFS order = descending pre-order node index (bvh.ts:141,160-161)
+    while (pos > lz.head && (enter < lz.pEnter[pos - 1] || (enter == lz.pEnter[pos - 1] && node > lz.pNode[pos - 1]))) {
+        lz.pEnter[pos] = lz.pEnter[pos - 1];
+        lz.pExit[pos] = lz.pExit[pos - 1];
+        lz.pNode[pos] = lz.pNode[pos - 1];
+        --pos;
+    }
+    lz.pEnter[pos] = enter;
+    lz.pExit[pos] = exit_;
+    lz.pNode[pos] = node;
+    lz.count++;
+}
+
+// returns false when the ray misses the root box (=> no intervals at all)
+static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz) {
+    lz.head = 0;
+    lz.count = 0;
+    lz.done = false;
+    lz.overflow = false;
+    lz.safeT = -1.0;
+    double invD[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) invD[i] = 1.0 / (double)d[i];
+    double tE, tX;
+    const rm_bvh_node* root = sc.bvh;
+    if (!box_intersect_ray(root->bmin, root->bmax, o, d, invD, tE, tX) || tX < 0.0 || tE > 10.0) {
+        lz.done = true;
+        return false;
+    }
+    const double t0 = tE > 0.0 ? tE : 0.0;
+    lz.tEnd = tX < 10.0 ? tX : 10.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double p = o[k] + (double)d[k] * t0;
+        const double org = (double)sc.grid_origin[k], cs = (double)sc.grid_cell[k];
+        int c = (sc.grid_inv[k] > 0.f) ? (int)floor((p - org) * (double)sc.grid_inv[k]) : 0;
+        c = c < 0 ? 0 : (c >= sc.grid_dims[k] ? sc.grid_dims[k] - 1 : c);
+        lz.cell[k] = c;
+        lz.prev[k] = -1;
+        const double dk = (double)d[k];
+        if (dk > 0.0 && cs > 0.0) {
+            lz.step[k] = 1;
+            lz.tDelta[k] = cs * invD[k];
+            lz.tNext[k] = (org + (double)(c + 1) * cs - o[k]) * invD[k];
+        } else if (dk < 0.0 && cs > 0.0) {
+            lz.step[k] = -1;
+            lz.tDelta[k] = -cs * invD[k];
+            lz.tNext[k] = (org + (double)c * cs - o[k]) * invD[k];
+        } else {
+            lz.step[k] = 0;
+            lz.tDelta[k] = d_inf();
+            lz.tNext[k] = d_inf();
+        }
+    }
+    return true;
+}
+
+// examine the current cell, then step to the next one
+static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz) {
+    double invD[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) invD[i] = 1.0 / (double)d[i];
+    const int cx = lz.cell[0], cy = lz.cell[1], cz = lz.cell[2];
+    const size_t c = ((size_t)cz * sc.grid_dims[1] + cy) * sc.grid_dims[0] + cx;
+    const uint32_t e0 = sc.grid_cell_start[c], e1 = sc.grid_cell_start[c + 1];
+    const bool hasPrev = lz.prev[0] >= 0;
+    for (uint32_t e = e0; e < e1; ++e) {
+        const uint3 lr = sc.grid_leaves[sc.grid_cell_leaf[e]];
+        if (hasPrev && cell_in_range(lr.y, lr.z, lz.prev[0], lz.prev[1], lz.prev[2])) continue;  // seen in an earlier cell
+        const rm_bvh_node* nd = sc.bvh + lr.x;
+        double tE, tX;
+        if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tE, tX)) continue;
+        if (tX < 0.0 || tE > 10.0) continue;
+        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)lr.x);
+    }
+    int ax = 0;
+    if (lz.tNext[1] < lz.tNext[ax]) ax = 1;
+    if (lz.tNext[2] < lz.tNext[ax]) ax = 2;
+    const double tOut = lz.tNext[ax];
+    lz.safeT = tOut - 1e-5;
+    if (!(tOut < lz.tEnd)) {
+        lz.done = true;
+        return;
+    }
+    lz.prev[0] = cx;
+    lz.prev[1] = cy;
+    lz.prev[2] = cz;
+    const int nc = lz.cell[ax] + lz.step[ax];
+    if (nc < 0 || nc >= sc.grid_dims[ax]) {
+        lz.done = true;
+        return;
+    }
+    lz.cell[ax] = nc;
+    lz.tNext[ax] += lz.tDelta[ax];
+}
+
+// next interval of the sorted list, or false when the list is exhausted
+RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz, double& enter, double& exit_) {
+    for (;;) {
+        if (lz.count > 0 && (lz.done || lz.pEnter[lz.head] < lz.safeT)) {
+            enter = lz.pEnter[lz.head];
+            exit_ = lz.pExit[lz.head];
+            lz.head++;
+            lz.count--;
+            if (lz.count == 0) lz.head = 0;
+            return true;
+        }
+        if (lz.done || lz.overflow) return false;
+        lazy_advance_cell(sc, o, d, lz);
+    }
+}
+
+// Move the interval cursor to the next entry of the sorted list (currentIntervalIdx++).  Lazy mode pulls it
+// from the grid walk; if the walk's buffer overflowed, the ray falls back to the literal eager list.
+template <class NP, bool kLazy>
+RM_DEV void bvh_advance(const DevScene& sc, const double o[3], Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
+    r.cur++;
+    if constexpr (kLazy) {
+        if (r.lazy) {
+            r.curValid = lazy_pop(sc, o, r.d, lz, r.curEnter, r.curExit);
+            if (r.curValid || !lz.overflow) return;
+            r.nIv = bvh_collect(sc.bvh, o, r.d, iv, cap);  // overflow: rebuild the list the reference's way
+            r.lazy = false;
+        }
+    }
+    r.curValid = r.cur < r.nIv;
+    if (r.curValid) {
+        r.curEnter = iv.enter[r.cur];
+        r.curExit = iv.exit_[r.cur];
+    }
+}
+
 // BVH.onRayMarchStep (bvh.ts:204-240).
-template <class NP>
-RM_DEV double bvh_step(Ray<NP>& r, const IvList& iv) {
-    if (r.cur >= r.nIv) return -1.0;
-    double e = iv.enter[r.cur];
-    if (r.t < e) return e - r.t;
-    if (r.t > iv.exit_[r.cur]) {
-        r.cur++;
-        if (r.cur < r.nIv) {
-            double ne = iv.enter[r.cur];
-            if (ne > r.t) return ne - r.t;
+template <class NP, bool kLazy>
+RM_DEV double bvh_step(const DevScene& sc, const double o[3], Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
+    if (!r.curValid) return -1.0;  // currentIntervalIdx >= intervals.length
+    if (r.t < r.curEnter) return r.curEnter - r.t;
+    if (r.t > r.curExit) {
+        bvh_advance<NP, kLazy>(sc, o, r, iv, lz, cap);
+        if (r.curValid) {
+            if (r.curEnter > r.t) return r.curEnter - r.t;
         } else {
             return -1.0;
         }
@@ -604,6 +780,8 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
     r.cur = 0;
     r.nIv = 0;
     IvList iv;  // only touched when ACCEL == BVH (lives in local memory)
+    LazyIv lz;  // fast-path BVH: grid walk state (local memory)
+    constexpr bool kLazy = !NP::kExact && ACCEL == RM_ACCEL_BVH;
     LaneStats st;
 
     // ---- shared memory: per-warp TMA stages for the primitive stream, and the CTA-wide request queue of
@@ -807,8 +985,16 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
             r.depth = 0.0;
             r.phase = PH_STEP;
             if constexpr (ACCEL == RM_ACCEL_BVH) {
-                r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
-                if (r.nIv == 0) {  // {terminate:true} -> return MAX_DIST (sphereTracer.ts:38-40)
+                r.cur = -1;
+                r.nIv = 0;
+                r.lazy = kLazy;
+                if constexpr (kLazy) {
+                    if (!lazy_init(P.scene, o, r.d, lz)) r.lazy = true;  // missed the root box: lz.done, empty list
+                } else {
+                    r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
+                }
+                bvh_advance<NP, kLazy>(P.scene, o, r, iv, lz, maxSteps + 1);  // cursor -> interval 0
+                if (!r.curValid) {  // {terminate:true} -> return MAX_DIST (sphereTracer.ts:38-40)
                     r.depth = MAX_DIST;
                     r.done = true;
                 }
@@ -827,7 +1013,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                               f32r(o[2] + (double)r.d[2] * r.t)};
                 if constexpr (ACCEL != RM_ACCEL_NONE) {
                     double skip;
-                    if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP>(r, iv);
+                    if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP, kLazy>(P.scene, o, r, iv, lz, maxSteps + 1);
                     else skip = octree_march(P.scene.oct, o, r.d, r.t, p);
                     if (skip == -1.0) {  // nothing left: `return MAX_DIST`
                         r.depth = MAX_DIST;
@@ -898,21 +1084,39 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
                 }
             } else {  // BVH.getPrimitivesAt (bvh.ts:95-121): every leaf whose box contains p, left before right
                 const rm_bvh_node* nodes = P.scene.bvh;
-                int stack[kBvhStack];
-                int sp = 0;
-                stack[sp++] = 0;
-                while (sp > 0) {
-                    int ni = stack[--sp];
-                    const rm_bvh_node* nd = nodes + ni;
-                    if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
-                    int left = nd->left, right = nd->right;
-                    if (left < 0 && right < 0) {
-                        int pc = nd->prim_count;
-                        leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
-                        cnt += (unsigned)pc;
-                    } else {
-                        if (right >= 0 && sp < kBvhStack) stack[sp++] = right;  // popped after left
-                        if (left >= 0 && sp < kBvhStack) stack[sp++] = left;
+                if constexpr (kLazy) {
+                    // fast path: the leaves overlapping p's grid cell, each with the reference's box test
+                    if (box_contains(nodes[0].bmin, nodes[0].bmax, r.q)) {
+                        const int gx = grid_coord(r.q[0], P.scene.grid_origin[0], P.scene.grid_inv[0], P.scene.grid_dims[0]);
+                        const int gy = grid_coord(r.q[1], P.scene.grid_origin[1], P.scene.grid_inv[1], P.scene.grid_dims[1]);
+                        const int gz = grid_coord(r.q[2], P.scene.grid_origin[2], P.scene.grid_inv[2], P.scene.grid_dims[2]);
+                        const size_t c = ((size_t)gz * P.scene.grid_dims[1] + gy) * P.scene.grid_dims[0] + gx;
+                        const uint32_t e0 = P.scene.grid_cell_start[c], e1 = P.scene.grid_cell_start[c + 1];
+                        for (uint32_t e = e0; e < e1; ++e) {
+                            const rm_bvh_node* nd = nodes + P.scene.grid_leaves[P.scene.grid_cell_leaf[e]].x;
+                            if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
+                            const int pc = nd->prim_count;
+                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
+                            cnt += (unsigned)pc;
+                        }
+                    }
+                } else {
+                    int stack[kBvhStack];
+                    int sp = 0;
+                    stack[sp++] = 0;
+                    while (sp > 0) {
+                        int ni = stack[--sp];
+                        const rm_bvh_node* nd = nodes + ni;
+                        if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
+                        int left = nd->left, right = nd->right;
+                        if (left < 0 && right < 0) {
+                            int pc = nd->prim_count;
+                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
+                            cnt += (unsigned)pc;
+                        } else {
+                            if (right >= 0 && sp < kBvhStack) stack[sp++] = right;  // popped after left
+                            if (left >= 0 && sp < kBvhStack) stack[sp++] = left;
+                        }
                     }
                 }
                 if (cnt == 0) needAll = true;  // candidates.length === 0 -> every primitive (scene.ts:173)

@@ -18,4 +18,23 @@ void compute_prim_geometry(int32_t n, const uint8_t* type, const float* w2l, con
 void build_bvh(const std::vector<PrimGeom>& geom, std::vector<rm_bvh_node>& nodes, std::vector<int32_t>& leafPrims);
 void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>& nodes, std::vector<int32_t>& leafPrims);
 
+// Uniform grid over the BVH's leaf boxes (fast path only).  It does not change any result: it answers the
+// two questions the reference asks its BVH — "which leaves contain this point" (bvh.ts:95-121) and "which
+// leaf boxes does this ray cross, in order of entry" (bvh.ts:126-178) — with the same boxes, just located
+// through cells instead of a 17-level descent.  Cell ranges are conservative (outward epsilon).
+struct LeafRef {
+    int32_t node;        // index of the leaf in the rm_bvh_node array
+    uint32_t lo, hi;     // packed cell range: x | y << 8 | z << 16 (inclusive)
+};
+struct LeafGrid {
+    int32_t dims[3] = {1, 1, 1};
+    float origin[3] = {0, 0, 0};   // root bmin
+    float inv_cell[3] = {0, 0, 0};  // cells per world unit (0 when the root is flat on that axis)
+    float cell[3] = {0, 0, 0};      // world units per cell
+    std::vector<LeafRef> leaves;        // in pre-order (left-first) leaf order
+    std::vector<uint32_t> cell_start;   // [nx*ny*nz + 1]
+    std::vector<int32_t> cell_leaf;     // leaf ordinals, ascending within a cell
+};
+void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& grid);
+
 }  // namespace rm

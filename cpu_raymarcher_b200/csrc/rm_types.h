@@ -36,6 +36,12 @@ struct DevScene {
     const rm_octree_node* oct;
     const int32_t* leaf_prims;
     uint32_t type_hist[3];  // number of sphere / box / torus primitives in the scene
+    // uniform grid over the BVH leaf boxes (fast path; see rm_host.h LeafGrid)
+    const uint3* grid_leaves;         // per leaf ordinal: x = node index, y = packed lo cell, z = packed hi cell
+    const uint32_t* grid_cell_start;  // [nx*ny*nz + 1]
+    const int32_t* grid_cell_leaf;    // leaf ordinals, ascending within a cell
+    int32_t grid_dims[3];
+    float grid_origin[3], grid_inv[3], grid_cell[3];
 };
 
 // Per-launch statistics accumulated by the render kernel's epilogue (one atomic set per warp).
