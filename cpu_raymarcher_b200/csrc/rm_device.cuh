@@ -134,6 +134,21 @@ RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], u
     }
 }
 
+// The fp64 "polish" of the fast path: the reference's value of primitive j's SDF at q, to double rounding
+// (plain sqrt instead of V8's Kahan hypot; the fast path only accepts affine transforms, for which the
+// homogeneous divide is by exactly 1).  Keeps the reference's f32 rounding of the local position.
+template <int PK>
+RM_DEV double prim_sdf_polish(const DevScene& sc, int j, const float q[3]) {
+    if constexpr (PK == PK_TSPHERE) {
+        const float4 s = __ldg(sc.rec + j);
+        // f32(x + m12): the float add IS the correctly rounded double sum of two floats
+        const double lx = (double)__fadd_rn(q[0], s.x), ly = (double)__fadd_rn(q[1], s.y), lz = (double)__fadd_rn(q[2], s.z);
+        return sqrt(lx * lx + ly * ly + lz * lz) - sc.params[4 * (size_t)j];
+    } else {
+        return prim_sdf_exact(sc, j, (double)q[0], (double)q[1], (double)q[2], 1);
+    }
+}
+
 // fp32 evaluation of primitive j by either fast record layout.
 template <int PK>
 RM_DEV float prim_sdf_f32(const float4* __restrict__ rec, int j, const float q[3]) {
@@ -179,16 +194,24 @@ struct WarpStage {
     const float4* buf[2];
     uint32_t bufAddr[2], bar[2];
     unsigned phase;
+    bool resident;  // the whole scene fits one stage and was loaded once at kernel start
 };
 
+RM_DEV float4 lds128(uint32_t addr) {  // explicit shared-space load: the compiler cannot fall back to generic LD
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 template <int PK>
-RM_DEV float sdf_from_stage(const float4* __restrict__ st, int k, const float q[3]) {
+RM_DEV float sdf_from_stage(uint32_t st, int k, const float q[3]) {
     if constexpr (PK == PK_TSPHERE) {
-        const float4 s = st[k];
+        const float4 s = lds128(st + 16u * (unsigned)k);
         float lx = q[0] + s.x, ly = q[1] + s.y, lz = q[2] + s.z;
         return NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - s.w;
     } else {
-        const float4 r0 = st[4 * k + 0], r1 = st[4 * k + 1], r2 = st[4 * k + 2], pr = st[4 * k + 3];
+        const float4 r0 = lds128(st + 64u * (unsigned)k), r1 = lds128(st + 64u * (unsigned)k + 16u), r2 = lds128(st + 64u * (unsigned)k + 32u),
+                     pr = lds128(st + 64u * (unsigned)k + 48u);
         float lx = fmaf(r0.x, q[0], fmaf(r0.y, q[1], fmaf(r0.z, q[2], r0.w)));
         float ly = fmaf(r1.x, q[0], fmaf(r1.y, q[1], fmaf(r1.z, q[2], r1.w)));
         float lz = fmaf(r2.x, q[0], fmaf(r2.y, q[1], fmaf(r2.z, q[2], r2.w)));
@@ -235,7 +258,8 @@ RM_DEV void search_stages(const RenderParams& P, const float q[3], WarpStage& ws
         mbar_expect_tx(ws.bar[sgi], bytes);
         bulk_g2s(ws.bufAddr[sgi], rec + (size_t)c * kPerStage * kF4, bytes, ws.bar[sgi]);
     };
-    if (lane == 0) {
+    const bool resident = ws.resident && first == 0 && stride == 1;
+    if (lane == 0 && !resident) {
         if (myStages > 0) issue(0);
         if (myStages > 1) issue(1);
     }
@@ -243,9 +267,11 @@ RM_DEV void search_stages(const RenderParams& P, const float q[3], WarpStage& ws
     code = -1;
     for (int i = 0; i < myStages; ++i) {
         const int sgi = i & 1;
-        mbar_wait(ws.bar[sgi], (ws.phase >> sgi) & 1u);
-        ws.phase ^= (1u << sgi);
-        const float4* __restrict__ st = ws.buf[sgi];
+        if (!resident) {
+            mbar_wait(ws.bar[sgi], (ws.phase >> sgi) & 1u);
+            ws.phase ^= (1u << sgi);
+        }
+        const uint32_t st = ws.bufAddr[sgi];
         const int base = (first + i * stride) * kPerStage;
         const int cnt = min(kPerStage, n - base);
         int k = 0;
@@ -287,7 +313,7 @@ RM_DEV double finish_search(const RenderParams& P, const float q[3], int code) {
             }
         }
     }
-    return jsmin(prim_sdf_exact(P.scene, idx, (double)q[0], (double)q[1], (double)q[2], 1), 10.0);
+    return jsmin(prim_sdf_polish<PK>(P.scene, idx, q), 10.0);
 }
 
 // Dense all-primitives evaluation by one warp for its own lanes: closest = min over every primitive
@@ -804,11 +830,25 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         ws.bufAddr[sgi] = smem_u32(shStage[warpId][sgi]);
         ws.bar[sgi] = smem_u32(&shBar[warpId][sgi]);
     }
+    ws.resident = false;
     if constexpr (!NP::kExact) {
         if (lane == 0) {
             mbar_init(ws.bar[0], 1);
             mbar_init(ws.bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        // small scenes: stage the whole primitive array once and keep it resident in shared memory
+        constexpr int kPerStage0 = kStageBytes / (16 * ((PK == PK_TSPHERE) ? 1 : 4));
+        if (P.scene.n_prims > 0 && P.scene.n_prims <= kPerStage0) {
+            const unsigned bytes = (unsigned)(P.scene.n_prims * 16 * ((PK == PK_TSPHERE) ? 1 : 4));
+            if (lane == 0) {
+                mbar_expect_tx(ws.bar[0], bytes);
+                bulk_g2s(ws.bufAddr[0], P.scene.rec, bytes, ws.bar[0]);
+            }
+            mbar_wait(ws.bar[0], 0u);
+            ws.phase ^= 1u;
+            ws.resident = true;
         }
     }
     shReady[threadIdx.x] = 0u;
@@ -1126,7 +1166,7 @@ __global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ Ren
         if constexpr (!NP::kExact) {
             // fast model: one fp64 evaluation of the nearest candidate found by the fp32 search
             if (polish && argmin >= 0)
-                dd = jsmin(prim_sdf_exact(P.scene, argmin, (double)r.q[0], (double)r.q[1], (double)r.q[2], 1), 10.0);
+                dd = jsmin(prim_sdf_polish<PK>(P.scene, argmin, r.q), 10.0);
         }
         // ---- (d2) the dense all-primitives pass ----
         if (!useQueue) {
