@@ -1,0 +1,213 @@
+// rm_napi.cc — Node N-API addon over the C ABI of include/rm.h (COMPILE-ONLY in this image: no Node.js).
+//
+// Exposes to JavaScript exactly what the reference's worker did (src/workers/raymarchWorker.ts):
+//   addon.uploadScene({type: Uint8Array, worldToLocal: Float32Array, params: Float64Array, accel: 'None'|'Octree'|'BVH'})
+//       -> rm_upload_scene          (replaces `new Scene(accel); scene.loadPreset(i)`, raymarchWorker.ts:37-38)
+//   addon.render(job, camera{rot3: Float32Array(9), origin: Float32Array(3)}) : Promise<Result>
+//       -> rm_render on a libuv worker thread (the JS event loop never blocks on CUDA); Result carries the
+//          four typed arrays of raymarchWorker.ts:24-31 backed by fresh ArrayBuffers (ownership moves to JS,
+//          like the reference's transfer list :86-91)
+//   addon.stats() -> rm_stats       (diagnostics of main.ts:527-548 for the last band)
+// The `Worker` shim that makes main.ts use this unchanged is ts/gpuWorkerShim.ts.
+#include <cstring>
+#include <string>
+
+#ifdef RM_HAVE_NODE_API_H
+#include <node_api.h>
+#else
+#include "napi_min.h"
+#endif
+#include "../include/rm.h"
+
+namespace {
+rm_ctx* g_ctx = nullptr;
+
+double get_num(napi_env env, napi_value obj, const char* key, double dflt) {
+    bool has = false;
+    napi_has_named_property(env, obj, key, &has);
+    if (!has) return dflt;
+    napi_value v;
+    double d = dflt;
+    if (napi_get_named_property(env, obj, key, &v) != napi_ok || napi_get_value_double(env, v, &d) != napi_ok) return dflt;
+    return d;
+}
+std::string get_str(napi_env env, napi_value obj, const char* key) {
+    napi_value v;
+    char buf[64] = {0};
+    size_t n = 0;
+    if (napi_get_named_property(env, obj, key, &v) == napi_ok) napi_get_value_string_utf8(env, v, buf, sizeof(buf), &n);
+    return std::string(buf, n);
+}
+void* get_ta(napi_env env, napi_value obj, const char* key, size_t* len) {
+    napi_value v;
+    void* data = nullptr;
+    napi_typedarray_type t;
+    napi_value ab;
+    size_t off;
+    *len = 0;
+    if (napi_get_named_property(env, obj, key, &v) != napi_ok) return nullptr;
+    if (napi_get_typedarray_info(env, v, &t, len, &data, &ab, &off) != napi_ok) return nullptr;
+    return data;
+}
+int algorithm_id(const std::string& a) {  // raymarchWorker.ts:49-68 (unknown -> sphere tracer)
+    if (a == "fixed-step") return RM_ALG_FIXED_STEP;
+    if (a == "adaptive-step") return RM_ALG_ADAPTIVE_STEP;
+    if (a == "adaptive-step-v2") return RM_ALG_ADAPTIVE_STEP_V2;
+    if (a == "adaptive-step-v3") return RM_ALG_ADAPTIVE_STEP_V3;
+    return RM_ALG_SPHERE_TRACER;
+}
+int accel_id(const std::string& a) { return a == "Octree" ? RM_ACCEL_OCTREE : (a == "BVH" ? RM_ACCEL_BVH : RM_ACCEL_NONE); }
+
+napi_value UploadScene(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value arg;
+    napi_get_cb_info(env, info, &argc, &arg, nullptr, nullptr);
+    if (!g_ctx && rm_create(&g_ctx, 0, 0) != RM_OK) {
+        napi_throw_error(env, "RM_ERR_CUDA", rm_last_error(nullptr));
+        return nullptr;
+    }
+    rm_scene s;
+    std::memset(&s, 0, sizeof(s));
+    size_t nt, nm, np;
+    s.type = (const uint8_t*)get_ta(env, arg, "type", &nt);
+    s.world_to_local = (const float*)get_ta(env, arg, "worldToLocal", &nm);
+    s.params = (const double*)get_ta(env, arg, "params", &np);
+    s.n_prims = (int32_t)nt;
+    s.accel_kind = accel_id(get_str(env, arg, "accel"));
+    if (nm != 16 * nt || np != 4 * nt) {
+        napi_throw_error(env, "RM_ERR_ARG", "worldToLocal must hold 16 and params 4 values per primitive");
+        return nullptr;
+    }
+    if (rm_upload_scene(g_ctx, &s) != RM_OK) napi_throw_error(env, "RM_ERR", rm_last_error(g_ctx));
+    return nullptr;
+}
+
+struct RenderWork {
+    rm_request rq;
+    rm_result out;
+    napi_value unused;
+    napi_deferred deferred;
+    napi_async_work work;
+    napi_ref keep;
+    int rc;
+    std::string err;
+    size_t npx;
+    // ArrayBuffers are created on the JS thread before the work is queued; the worker thread only fills them
+    void *depth, *normal, *sdf, *iters;
+    napi_value result_obj;
+};
+
+void RenderExecute(napi_env, void* data) {  // libuv worker thread: no JS here
+    RenderWork* w = (RenderWork*)data;
+    w->rc = rm_render(g_ctx, &w->rq, &w->out);
+    if (w->rc != RM_OK) w->err = rm_last_error(g_ctx);
+}
+void RenderComplete(napi_env env, napi_status, void* data) {
+    RenderWork* w = (RenderWork*)data;
+    if (w->rc == RM_OK) {
+        napi_resolve_deferred(env, w->deferred, w->result_obj);
+    } else {
+        napi_value msg, e;
+        napi_create_string_utf8(env, w->err.c_str(), w->err.size(), &msg);
+        napi_create_error(env, nullptr, msg, &e);
+        napi_reject_deferred(env, w->deferred, e);
+    }
+    napi_delete_async_work(env, w->work);
+    delete w;
+}
+
+napi_value Render(napi_env env, napi_callback_info info) {
+    size_t argc = 2;
+    napi_value argv[2];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    napi_value job = argv[0], cam = argv[1];
+    RenderWork* w = new RenderWork();
+    std::memset(&w->rq, 0, sizeof(w->rq));
+    std::memset(&w->out, 0, sizeof(w->out));
+    w->rq.width = (int32_t)get_num(env, job, "width", 0);
+    w->rq.height = (int32_t)get_num(env, job, "height", 0);
+    w->rq.y_start = (int32_t)get_num(env, job, "yStart", 0);
+    w->rq.y_end = (int32_t)get_num(env, job, "yEnd", w->rq.height);
+    w->rq.time = get_num(env, job, "time", 0);
+    w->rq.algorithm = algorithm_id(get_str(env, job, "algorithm"));
+    w->rq.step_size = get_num(env, job, "stepSize", 0.1);
+    w->rq.overshoot_factor = get_num(env, job, "overshootFactor", 1.2);
+    w->rq.shader = RM_SHADER_NONE;  // main.ts shades on its own thread (main.ts:493-515); fuse by passing a shader id
+    w->rq.shader_analytics = RM_SHADER_NONE;
+    size_t n9, n3;
+    const float* rot3 = (const float*)get_ta(env, cam, "rot3", &n9);
+    const float* org = (const float*)get_ta(env, cam, "origin", &n3);
+    if (!rot3 || !org || n9 != 9 || n3 != 3) {
+        delete w;
+        napi_throw_error(env, "RM_ERR_ARG", "camera.rot3 (Float32Array 9) and camera.origin (Float32Array 3) required");
+        return nullptr;
+    }
+    std::memcpy(w->rq.rot3, rot3, sizeof(w->rq.rot3));
+    std::memcpy(w->rq.origin, org, sizeof(w->rq.origin));
+    const int th = w->rq.y_end > w->rq.y_start ? w->rq.y_end - w->rq.y_start : 0;
+    w->npx = (size_t)w->rq.width * th;
+    // Result arrays (raymarchWorker.ts:42-46) allocated as JS ArrayBuffers; rm_render writes straight into them
+    napi_value ab, ta, res, v;
+    napi_create_object(env, &res);
+    napi_create_arraybuffer(env, w->npx, &w->depth, &ab);
+    napi_create_typedarray(env, napi_uint8_clamped_array, w->npx, ab, 0, &ta);
+    napi_set_named_property(env, res, "depth", ta);
+    napi_create_arraybuffer(env, 3 * w->npx, &w->normal, &ab);
+    napi_create_typedarray(env, napi_uint8_clamped_array, 3 * w->npx, ab, 0, &ta);
+    napi_set_named_property(env, res, "normal", ta);
+    napi_create_arraybuffer(env, 2 * w->npx, &w->sdf, &ab);
+    napi_create_typedarray(env, napi_uint16_array, w->npx, ab, 0, &ta);
+    napi_set_named_property(env, res, "sdfEval", ta);
+    napi_create_arraybuffer(env, 2 * w->npx, &w->iters, &ab);
+    napi_create_typedarray(env, napi_uint16_array, w->npx, ab, 0, &ta);
+    napi_set_named_property(env, res, "iters", ta);
+    napi_create_int32(env, w->rq.y_start, &v);
+    napi_set_named_property(env, res, "yStart", v);
+    napi_create_int32(env, w->rq.y_end, &v);
+    napi_set_named_property(env, res, "yEnd", v);
+    w->out.depth = (uint8_t*)w->depth;
+    w->out.normal = (uint8_t*)w->normal;
+    w->out.sdf_eval = (uint16_t*)w->sdf;
+    w->out.iters = (uint16_t*)w->iters;
+    w->result_obj = res;  // kept alive by the promise resolution below (a napi_ref would be used in production)
+    napi_value promise, name;
+    napi_create_promise(env, &w->deferred, &promise);
+    napi_create_string_utf8(env, "rm_render", 9, &name);
+    napi_create_async_work(env, nullptr, name, RenderExecute, RenderComplete, w, &w->work);
+    napi_queue_async_work(env, w->work);
+    return promise;
+}
+
+napi_value Stats(napi_env env, napi_callback_info) {
+    rm_stats_t st;
+    napi_value o, v;
+    napi_create_object(env, &o);
+    if (!g_ctx || rm_stats(g_ctx, &st) != RM_OK) return o;
+    napi_create_double(env, (double)st.sum_sdf, &v);
+    napi_set_named_property(env, o, "totalSDFCalls", v);
+    napi_create_double(env, (double)st.max_sdf, &v);
+    napi_set_named_property(env, o, "maxSDFCalls", v);
+    napi_create_double(env, (double)st.min_sdf, &v);
+    napi_set_named_property(env, o, "minSDFCalls", v);
+    napi_create_double(env, (double)st.sum_iters, &v);
+    napi_set_named_property(env, o, "totalIterations", v);
+    napi_create_double(env, st.kernel_ms, &v);
+    napi_set_named_property(env, o, "kernelMs", v);
+    return o;
+}
+
+napi_value Init(napi_env env, napi_value exports) {
+    napi_property_descriptor d[] = {{"uploadScene", nullptr, UploadScene, nullptr, nullptr, nullptr, 0, nullptr},
+                                    {"render", nullptr, Render, nullptr, nullptr, nullptr, 0, nullptr},
+                                    {"stats", nullptr, Stats, nullptr, nullptr, nullptr, 0, nullptr}};
+    napi_define_properties(env, exports, 3, d);
+    return exports;
+}
+napi_module g_mod = {1, 0, __FILE__, Init, "rm_napi", nullptr, {nullptr, nullptr, nullptr, nullptr}};
+struct Registrar {
+    Registrar() { napi_module_register(&g_mod); }
+};
+#ifdef RM_HAVE_NODE_API_H
+Registrar g_registrar;  // NAPI_MODULE(rm_napi, Init)
+#endif
+}  // namespace

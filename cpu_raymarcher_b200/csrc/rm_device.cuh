@@ -34,6 +34,14 @@
 namespace rm {
 
 constexpr unsigned kFull = 0xffffffffu;
+// CTAs (128 threads) per SM the register allocator must leave room for.  Measured on B200: the BVH kernels want
+// registers (the 32-wide unrolled search + interval state; 3 CTAs/SM = 168 registers), everything else wants occupancy.
+#ifndef RM_MIN_BLOCKS_BVH
+#define RM_MIN_BLOCKS_BVH 3
+#endif
+#ifndef RM_MIN_BLOCKS_OTHER
+#define RM_MIN_BLOCKS_OTHER 8
+#endif
 
 enum Phase : int {
     PH_IDLE = 0,
@@ -789,7 +797,7 @@ RM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
 }
 
 template <class NP, int ACCEL, int PK>
-__global__ void __launch_bounds__(128) render_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_BVH : RM_MIN_BLOCKS_OTHER) render_kernel(const __grid_constant__ RenderParams P) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
