@@ -116,8 +116,9 @@ RM_DEV float prim_sdf_fast_general(const float4* __restrict__ rec, int j, float 
     }
 }
 // Fast model, translation-only sphere: local = p + t.
-RM_DEV float prim_sdf_fast_tsphere(const float4* __restrict__ rec, int j, float x, float y, float z) {
-    const float4 s = __ldg(rec + j);
+// `rec1` = one float4 (tx,ty,tz,r) per primitive (the streamed search uses the chunk-SoA copy instead).
+RM_DEV float prim_sdf_fast_tsphere(const float4* __restrict__ rec1, int j, float x, float y, float z) {
+    const float4 s = __ldg(rec1 + j);
     float lx = x + s.x, ly = y + s.y, lz = z + s.z;
     return NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - s.w;
 }
@@ -132,7 +133,7 @@ RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], u
         return prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt);
     } else if constexpr (PK == PK_TSPHERE) {
         nSphere += 1;
-        return prim_sdf_fast_tsphere(P.scene.rec, j, q[0], q[1], q[2]);
+        return prim_sdf_fast_tsphere(P.scene.rec1, j, q[0], q[1], q[2]);
     } else {
         int type;
         float d = prim_sdf_fast_general(P.scene.rec, j, q[0], q[1], q[2], type);
@@ -148,7 +149,7 @@ RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], u
 template <int PK>
 RM_DEV double prim_sdf_polish(const DevScene& sc, int j, const float q[3]) {
     if constexpr (PK == PK_TSPHERE) {
-        const float4 s = __ldg(sc.rec + j);
+        const float4 s = __ldg(sc.rec1 + j);
         // f32(x + m12): the float add IS the correctly rounded double sum of two floats
         const double lx = (double)__fadd_rn(q[0], s.x), ly = (double)__fadd_rn(q[1], s.y), lz = (double)__fadd_rn(q[2], s.z);
         return sqrt(lx * lx + ly * ly + lz * lz) - sc.params[4 * (size_t)j];
@@ -211,6 +212,191 @@ RM_DEV float4 lds128(uint32_t addr) {  // explicit shared-space load: the compil
     return v;
 }
 
+// Blackwell packed fp32 (FADD2 / FMUL2 / FFMA2): two lanes per issue slot.
+typedef unsigned long long f32x2;
+RM_DEV f32x2 pk2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+RM_DEV void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+RM_DEV f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+RM_DEV f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+RM_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Squared centre distances of the 32 spheres of one chunk-SoA block in shared memory; returns their minimum.
+RM_DEV float chunk_min_sq(uint32_t ch, f32x2 qx, f32x2 qy, f32x2 qz) {
+    float m = 3.0e38f;
+    // unrolled by 4 groups only: the whole screened loop must stay resident in the SM's small L0 instruction cache
+#pragma unroll 4
+    for (int g = 0; g < 8; ++g) {
+        const float4 X = lds128(ch + 16u * g), Y = lds128(ch + 128u + 16u * g), Z = lds128(ch + 256u + 16u * g);
+        f32x2 lx0 = add2(qx, pk2(X.x, X.y)), lx1 = add2(qx, pk2(X.z, X.w));
+        f32x2 ly0 = add2(qy, pk2(Y.x, Y.y)), ly1 = add2(qy, pk2(Y.z, Y.w));
+        f32x2 lz0 = add2(qz, pk2(Z.x, Z.y)), lz1 = add2(qz, pk2(Z.z, Z.w));
+        f32x2 s0 = fma2(lx0, lx0, fma2(ly0, ly0, mul2(lz0, lz0)));
+        f32x2 s1 = fma2(lx1, lx1, fma2(ly1, ly1, mul2(lz1, lz1)));
+        float a, b, c, d;
+        upk2(s0, a, b);
+        upk2(s1, c, d);
+        m = fminf(m, fminf(a, b));
+        m = fminf(m, fminf(c, d));
+    }
+    return m;
+}
+// Exact fp32 SDFs of the 32 spheres of a chunk held in shared memory: running (min, argmin).
+RM_DEV void chunk_exact_smem(uint32_t ch, int base, int valid, const float q[3], float& best, int& idx) {
+    const int groups = (valid + 3) >> 2;  // padded dummies inside the last group lose every comparison
+#pragma unroll 2
+    for (int g = 0; g < groups; ++g) {
+        const float4 X = lds128(ch + 16u * g), Y = lds128(ch + 128u + 16u * g), Z = lds128(ch + 256u + 16u * g),
+                     R = lds128(ch + 384u + 16u * g);
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w}, rs[4] = {R.x, R.y, R.z, R.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float lx = q[0] + xs[u], ly = q[1] + ys[u], lz = q[2] + zs[u];
+            float d = NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - rs[u];
+            if (d < best) {
+                best = d;
+                idx = base + 4 * g + u;
+            }
+        }
+    }
+}
+// Same from global memory (per-lane chunk; used to resolve the few screened candidates).
+RM_DEV void chunk_exact_gmem(const float4* __restrict__ rec, int chunk, const float q[3], float& best, int& idx) {
+    const float4* c = rec + (size_t)chunk * 32;
+#pragma unroll 2
+    for (int g = 0; g < 8; ++g) {
+        const float4 X = __ldg(c + g), Y = __ldg(c + 8 + g), Z = __ldg(c + 16 + g), R = __ldg(c + 24 + g);
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w}, rs[4] = {R.x, R.y, R.z, R.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float lx = q[0] + xs[u], ly = q[1] + ys[u], lz = q[2] + zs[u];
+            float d = NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - rs[u];
+            if (d < best) {
+                best = d;
+                idx = chunk * 32 + 4 * g + u;
+            }
+        }
+    }
+}
+
+// All-primitives search for translation-only spheres over the stages c = first, first + stride, ...
+//   n_chunks <  kScreenMinChunks : every sphere's SDF (sqrt) straight from the stage;
+//   otherwise SCREENED            : the hot loop only computes squared centre distances (packed FADD2 / FMUL2 /
+//     FFMA2, no MUFU, radii not even loaded).  With S = min_j |p - c_j|^2 the nearest surface satisfies
+//     d* <= sqrt(S) - r_min, so sphere j can only win if |p - c_j| <= sqrt(S) + (r_max - r_min); chunks whose
+//     minimum squared distance passes that test against the RUNNING S are remembered (a handful per query)
+//     and resolved exactly afterwards.  Same result as evaluating every SDF; ~6 instead of ~10 issue slots.
+constexpr int kScreenMinChunks = 16;
+constexpr int kCandCap = 48;
+RM_DEV void search_stages_ts(const RenderParams& P, const float q[3], WarpStage& ws, int lane, int first, int stride, float& best,
+                             int& code) {
+    const float4* __restrict__ rec = P.scene.rec;
+    const int nChunks = P.scene.n_chunks;
+    const int nStages = (nChunks + 3) / 4;  // 4 chunks (2 KB) per stage
+    const int myStages = nStages > first ? (nStages - first + stride - 1) / stride : 0;
+    auto issue = [&](int i) {
+        const int c = first + i * stride, sgi = i & 1;
+        const int cnt = min(4, nChunks - 4 * c);
+        const unsigned bytes = (unsigned)(cnt * 512);
+        mbar_expect_tx(ws.bar[sgi], bytes);
+        bulk_g2s(ws.bufAddr[sgi], rec + (size_t)c * 128, bytes, ws.bar[sgi]);
+    };
+    const bool resident = ws.resident && first == 0 && stride == 1;
+    const f32x2 qx = pk2(q[0], q[0]), qy = pk2(q[1], q[1]), qz = pk2(q[2], q[2]);
+    const float rMin = P.scene.r_min;
+    // attempt 0: screened (large scenes); attempt 1: plain SDF of every sphere, taken by the whole warp when some
+    // lane's candidate list overflowed (radius spread inside the chunks too wide for the screen to be selective)
+    for (int attempt = (nChunks >= kScreenMinChunks) ? 0 : 1; attempt < 2; ++attempt) {
+        const bool screened = attempt == 0;
+        if (lane == 0 && !resident) {
+            if (myStages > 0) issue(0);
+            if (myStages > 1) issue(1);
+        }
+        best = 10.f;
+        code = -1;
+        float sRun = 3.0e38f, rootS = 1.0e19f;  // running min squared centre distance and its square root
+        unsigned short candChunk[kCandCap];
+        float candS[kCandCap];
+        int nCand = 0;
+        bool overflow = false;
+        for (int i = 0; i < myStages; ++i) {
+            const int sgi = i & 1;
+            if (!resident) {
+                mbar_wait(ws.bar[sgi], (ws.phase >> sgi) & 1u);
+                ws.phase ^= (1u << sgi);
+            }
+            const uint32_t st = ws.bufAddr[sgi];
+            const int chunk0 = 4 * (first + i * stride);
+            const int cnt = min(4, nChunks - chunk0);
+            // largest radius of each of the stage's 4 chunks (array padded to a multiple of 4 on the host)
+            const float4 rm4 = __ldg(reinterpret_cast<const float4*>(P.scene.chunk_rmax) + (first + i * stride));
+            const float rmv[4] = {rm4.x, rm4.y, rm4.z, rm4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c >= cnt) break;
+                const uint32_t ch = st + 512u * (unsigned)c;
+                if (!screened) {
+                    chunk_exact_smem(ch, (chunk0 + c) * 32, min(32, P.scene.n_prims - (chunk0 + c) * 32), q, best, code);
+                } else {
+                    const float m = chunk_min_sq(ch, qx, qy, qz);
+                    if (m < sRun) {  // new nearest centre
+                        sRun = m;
+                        rootS = NumFast::sqrt_(m);
+                    }
+                    // a sphere of this chunk can only win if |p - c_j| <= sqrt(S) - r_min + r_max(chunk)  (+ slack)
+                    const float t = rootS + (rmv[c] - rMin);
+                    if (m <= t * t * 1.00001f + 1e-30f) {
+                        if (nCand == kCandCap) {  // compact against the current bound before giving up
+                            int w = 0;
+                            for (int e = 0; e < nCand; ++e) {
+                                const float te = rootS + (__ldg(P.scene.chunk_rmax + candChunk[e]) - rMin);
+                                if (candS[e] <= te * te * 1.00001f + 1e-30f) {
+                                    candChunk[w] = candChunk[e];
+                                    candS[w] = candS[e];
+                                    ++w;
+                                }
+                            }
+                            nCand = w;
+                        }
+                        if (nCand < kCandCap) {
+                            candChunk[nCand] = (unsigned short)(chunk0 + c);
+                            candS[nCand] = m;
+                            ++nCand;
+                        } else {
+                            overflow = true;
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // every lane is done reading this stage before it is refilled
+            if (lane == 0 && i + 2 < myStages) issue(i + 2);
+        }
+        if (!screened) break;
+        if (__any_sync(kFull, overflow)) continue;  // rare: redo the pass unscreened, all lanes together
+        for (int e = 0; e < nCand; ++e) {
+            const float te = rootS + (__ldg(P.scene.chunk_rmax + candChunk[e]) - rMin);
+            if (candS[e] <= te * te * 1.00001f + 1e-30f) chunk_exact_gmem(rec, (int)candChunk[e], q, best, code);
+        }
+        break;
+    }
+    // padded dummies can never win (|l| ~ 1e15), so code < n_prims whenever it is set
+}
+
 template <int PK>
 RM_DEV float sdf_from_stage(uint32_t st, int k, const float q[3]) {
     if constexpr (PK == PK_TSPHERE) {
@@ -253,6 +439,10 @@ constexpr int kChunkFlag = 0x40000000;
 template <int PK>
 RM_DEV void search_stages(const RenderParams& P, const float q[3], WarpStage& ws, int lane, int first, int stride, float& best,
                           int& code) {
+    if constexpr (PK == PK_TSPHERE) {
+        search_stages_ts(P, q, ws, lane, first, stride, best, code);
+        return;
+    }
     constexpr int kF4 = (PK == PK_TSPHERE) ? 1 : 4;     // float4 per primitive
     constexpr int kPerStage = kStageBytes / (16 * kF4);  // primitives per stage (128 / 32)
     const int n = P.scene.n_prims;
@@ -314,7 +504,7 @@ RM_DEV double finish_search(const RenderParams& P, const float q[3], int code) {
         const int chunk = code & ~kChunkFlag;
         float mm = 3.0e38f;
         for (int k = 0; k < kChunk; ++k) {
-            float d = prim_sdf_f32<PK>(P.scene.rec, chunk + k, q);
+            float d = prim_sdf_f32<PK>((PK == PK_TSPHERE) ? P.scene.rec1 : P.scene.rec, chunk + k, q);
             if (d < mm) {
                 mm = d;
                 idx = chunk + k;
@@ -849,7 +1039,7 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
         // small scenes: stage the whole primitive array once and keep it resident in shared memory
         constexpr int kPerStage0 = kStageBytes / (16 * ((PK == PK_TSPHERE) ? 1 : 4));
         if (P.scene.n_prims > 0 && P.scene.n_prims <= kPerStage0) {
-            const unsigned bytes = (unsigned)(P.scene.n_prims * 16 * ((PK == PK_TSPHERE) ? 1 : 4));
+            const unsigned bytes = (PK == PK_TSPHERE) ? (unsigned)(P.scene.n_chunks * 512) : (unsigned)(P.scene.n_prims * 64);
             if (lane == 0) {
                 mbar_expect_tx(ws.bar[0], bytes);
                 bulk_g2s(ws.bufAddr[0], P.scene.rec, bytes, ws.bar[0]);
