@@ -689,7 +689,7 @@ RM_DEV bool cell_in_range(uint32_t lo, uint32_t hi, int x, int y, int z) {
 // so the consumer sees exactly the stably-sorted list of the reference — but only as far as the march needs.
 constexpr int kPendCap = 64;
 struct LazyIv {
-    double tNext[3], tDelta[3];
+    double tNext[3], tDelta[3], invD[3];  // invD = 1 / direction, computed once per ray
     double tEnd, safeT;
     double pEnter[kPendCap], pExit[kPendCap];
     int pNode[kPendCap];
@@ -734,7 +734,10 @@ static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o
     lz.safeT = -1.0;
     double invD[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) invD[i] = 1.0 / (double)d[i];
+    for (int i = 0; i < 3; ++i) {
+        invD[i] = 1.0 / (double)d[i];
+        lz.invD[i] = invD[i];
+    }
     double tE, tX;
     const rm_bvh_node* root = sc.bvh;
     if (!box_intersect_ray(root->bmin, root->bmax, o, d, invD, tE, tX) || tX < 0.0 || tE > 10.0) {
@@ -771,9 +774,7 @@ static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o
 
 // examine the current cell, then step to the next one
 static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz) {
-    double invD[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) invD[i] = 1.0 / (double)d[i];
+    const double invD[3] = {lz.invD[0], lz.invD[1], lz.invD[2]};
     const int cx = lz.cell[0], cy = lz.cell[1], cz = lz.cell[2];
     const size_t c = ((size_t)cz * sc.grid_dims[1] + cy) * sc.grid_dims[0] + cx;
     const uint32_t e0 = sc.grid_cell_start[c], e1 = sc.grid_cell_start[c + 1];
