@@ -36,6 +36,9 @@ namespace rm {
 constexpr unsigned kFull = 0xffffffffu;
 // CTAs (128 threads) per SM the register allocator must leave room for.  Measured on B200: the BVH kernels want
 // registers (the 32-wide unrolled search + interval state; 3 CTAs/SM = 168 registers), everything else wants occupancy.
+#ifndef RM_INIT_LANES
+#define RM_INIT_LANES 32  // lanes that must be free before a warp refills (32 = retire the whole tile first; measured best)
+#endif
 #ifndef RM_MIN_BLOCKS_BVH
 #define RM_MIN_BLOCKS_BVH 3
 #endif
@@ -1070,7 +1073,7 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
     // Warp scheduler.  Expensive, warp-serialising stages are deferred until enough lanes want them: BVH
     // ray set-up (a full tree traversal) runs when initLanes lanes are free or nothing else can progress;
     // the all-primitives pass goes through the CTA-wide request queue below.
-    const int initLanes = (ACCEL == RM_ACCEL_BVH) ? (P.scene.n_prims >= 256 ? 16 : 4) : 1;
+    const int initLanes = RM_INIT_LANES;
     r.pending = false;
 
     for (;;) {
