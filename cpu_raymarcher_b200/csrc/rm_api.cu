@@ -47,8 +47,9 @@ struct rm_ctx {
     rm_stats_t last{};
     // band staging for rm_render (device planes + pinned host mirror)
     DevBuf d_frame, h_frame;
-    // user allocations (rm_alloc)
+    // user allocations (rm_alloc / rm_host_alloc)
     std::vector<void*> user_allocs;
+    std::vector<std::pair<char*, size_t>> host_allocs;
 };
 
 namespace {
@@ -291,6 +292,7 @@ void rm_destroy(rm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_scene(c);
     for (void* p : c->user_allocs) cudaFree(p);
+    for (auto& h : c->host_allocs) cudaFreeHost(h.first);
     if (c->d_frame.p) cudaFree(c->d_frame.p);
     if (c->h_frame.p) cudaFreeHost(c->h_frame.p);
     if (c->d_stats) cudaFree(c->d_stats);
@@ -519,7 +521,6 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     const size_t oD64 = off; off += out->depth_f64 ? al(8 * np) : 0;
     const size_t total = off;
     if ((rc = ensure(c, c->d_frame, total + 256, false))) return rc;
-    if ((rc = ensure(c, c->h_frame, total + 256, true))) return rc;
     uint8_t* d = (uint8_t*)c->d_frame.p;
     rm_result dev{};
     dev.depth = d + oDepth;
@@ -533,8 +534,31 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     dev.depth_f64 = out->depth_f64 ? (double*)(d + oD64) : nullptr;
     rc = render_device_locked(c, rq, &dev, c->stream);
     if (rc) return rc;
-    if (np > 0) {
+    auto pinned = [&](const void* p, size_t bytes) {
+        if (!p) return true;
+        for (auto& h : c->host_allocs)
+            if ((const char*)p >= h.first && (const char*)p + bytes <= h.first + h.second) return true;
+        return false;
+    };
+    const bool direct = pinned(out->depth, np) && pinned(out->normal, 3 * np) && pinned(out->sdf_eval, 2 * np) && pinned(out->iters, 2 * np) &&
+                        pinned(wantRgba ? out->rgba : nullptr, 4 * np) && pinned(wantRgba2 ? out->rgba_analytics : nullptr, 4 * np) &&
+                        pinned(out->depth_f32, 4 * np) && pinned(out->sdf_eval_u32, 4 * np) && pinned(out->depth_f64, 8 * np);
+    if (np > 0 && direct) {
+        // caller's planes are page-locked memory of this context: DMA straight into them
+        auto cp = [&](void* dst, size_t off, size_t bytes) { return dst ? cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
+        CU(c, cp(out->depth, oDepth, np));
+        CU(c, cp(out->normal, oNormal, 3 * np));
+        CU(c, cp(out->sdf_eval, oSdf, 2 * np));
+        CU(c, cp(out->iters, oIters, 2 * np));
+        CU(c, cp(wantRgba ? out->rgba : nullptr, oRgba, 4 * np));
+        CU(c, cp(wantRgba2 ? out->rgba_analytics : nullptr, oRgba2, 4 * np));
+        CU(c, cp(out->depth_f32, oDf, 4 * np));
+        CU(c, cp(out->sdf_eval_u32, oSu, 4 * np));
+        CU(c, cp(out->depth_f64, oD64, 8 * np));
+        CU(c, cudaStreamSynchronize(c->stream));
+    } else if (np > 0) {
         // one D2H of the whole staging block into pinned memory, then scatter to the caller's planes
+        if ((rc = ensure(c, c->h_frame, total + 256, true))) return rc;
         CU(c, cudaMemcpyAsync(c->h_frame.p, d, total, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
         const uint8_t* h = (const uint8_t*)c->h_frame.p;
@@ -600,6 +624,30 @@ int rm_probe_fp32_peak(rm_ctx* c, double* tflops) {
     int e = probe_fp32_peak(c->n_sms, c->stream, (float*)c->d_frame.p, tflops);
     if (e != 0) return fail(c, RM_ERR_CUDA, "fp32 probe: %s", cudaGetErrorString((cudaError_t)e));
     return RM_OK;
+}
+
+int rm_host_alloc(rm_ctx* c, size_t bytes, void** host_ptr) {
+    if (!c || !host_ptr) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU(c, cudaMallocHost(&p, bytes ? bytes : 1));
+    c->host_allocs.emplace_back((char*)p, bytes ? bytes : 1);
+    *host_ptr = p;
+    return RM_OK;
+}
+int rm_host_free(rm_ctx* c, void* host_ptr) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (size_t i = 0; i < c->host_allocs.size(); ++i)
+        if (c->host_allocs[i].first == (char*)host_ptr) {
+            CU(c, cudaSetDevice(c->device));
+            CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaFreeHost(host_ptr));
+            c->host_allocs.erase(c->host_allocs.begin() + (long)i);
+            return RM_OK;
+        }
+    return fail(c, RM_ERR_ARG, "pointer was not allocated by rm_host_alloc on this context");
 }
 
 int rm_alloc(rm_ctx* c, size_t bytes, void** dev_ptr) {

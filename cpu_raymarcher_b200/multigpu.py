@@ -243,10 +243,10 @@ class FrameSharder:
         d2h = n * (1 + 3 + 2 + 2 + (4 if shader else 0))
         h2d = C.sizeof(_lib.Request)
         if self.world == 1:
-            self.worker.on_message(job, shader=shader)  # warm-up (staging buffers)
+            self.worker.on_message(job, shader=shader, pinned=True)  # warm-up (allocates the page-locked planes)
             t0 = time.perf_counter()
             for _ in range(steps):
-                self.worker.on_message(job, shader=shader)
+                self.worker.on_message(job, shader=shader, pinned=True)
             ms = (time.perf_counter() - t0) * 1e3 / steps
             return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h}
         import torch.distributed as dist

@@ -127,24 +127,41 @@ class Context:
             rq.stripe_rows, rq.stripe_count, rq.stripe_index = stripes
         return rq
 
-    def render(self, rq: _lib.Request, extras: bool = False) -> Frame:
-        """rm_render: host buffers out (the worker path)."""
+    def _pinned_array(self, key: str, n: int, dtype) -> np.ndarray:
+        """A numpy view over page-locked memory owned by this context (rm_host_alloc), reused per plane."""
+        nbytes = max(1, n * np.dtype(dtype).itemsize)
+        pool = self.__dict__.setdefault("_pinned", {})
+        ent = pool.get(key)
+        if ent is None or ent[1] < nbytes:
+            if ent is not None:
+                self._check(self._L.rm_host_free(self._h, ent[0]))
+            p = C.c_void_p()
+            self._check(self._L.rm_host_alloc(self._h, nbytes + nbytes // 8, C.byref(p)))
+            ent = (p.value, nbytes + nbytes // 8)
+            pool[key] = ent
+        buf = (C.c_uint8 * nbytes).from_address(ent[0])
+        return np.frombuffer(buf, dtype=dtype, count=n)
+
+    def render(self, rq: _lib.Request, extras: bool = False, pinned: bool = False) -> Frame:
+        """rm_render: host buffers out (the worker path).  pinned=True returns views over the context's page-locked
+        planes (filled by direct DMA; valid until the next pinned render on this context) instead of fresh arrays."""
         th = max(0, rq.y_end - rq.y_start)
         n = th * rq.width
-        f = Frame(rq.y_start, rq.y_end, np.zeros(n, np.uint8), np.zeros(3 * n, np.uint8), np.zeros(n, np.uint16),
-                  np.zeros(n, np.uint16))
+        new = (lambda key, cnt, dt: self._pinned_array(key, cnt, dt)) if pinned else (lambda key, cnt, dt: np.zeros(cnt, dt))
+        f = Frame(rq.y_start, rq.y_end, new("depth", n, np.uint8), new("normal", 3 * n, np.uint8), new("sdf", n, np.uint16),
+                  new("iters", n, np.uint16))
         res = _lib.Result()
         res.depth, res.normal, res.sdf_eval, res.iters = _ptr(f.depth), _ptr(f.normal), _ptr(f.sdfEval), _ptr(f.iters)
         if rq.shader >= 0:
-            f.rgba = np.zeros(4 * n, np.uint8)
+            f.rgba = new("rgba", 4 * n, np.uint8)
             res.rgba = _ptr(f.rgba)
         if rq.shader_analytics >= 0:
-            f.rgba_analytics = np.zeros(4 * n, np.uint8)
+            f.rgba_analytics = new("rgba2", 4 * n, np.uint8)
             res.rgba_analytics = _ptr(f.rgba_analytics)
         if extras:
-            f.depth_f32 = np.zeros(n, np.float32)
-            f.sdf_u32 = np.zeros(n, np.uint32)
-            f.depth_f64 = np.zeros(n, np.float64)
+            f.depth_f32 = new("depth_f32", n, np.float32)
+            f.sdf_u32 = new("sdf_u32", n, np.uint32)
+            f.depth_f64 = new("depth_f64", n, np.float64)
             res.depth_f32, res.sdf_eval_u32, res.depth_f64 = _ptr(f.depth_f32), _ptr(f.sdf_u32), _ptr(f.depth_f64)
         self._check(self._L.rm_render(self._h, C.byref(rq), C.byref(res)))
         return f

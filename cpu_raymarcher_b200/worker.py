@@ -38,7 +38,7 @@ class RaymarchWorker:
             self._scene_key = key
         return self.scene
 
-    def on_message(self, job: dict, shader=None, shader_analytics=None, extras: bool = False) -> Frame:
+    def on_message(self, job: dict, shader=None, shader_analytics=None, extras: bool = False, pinned: bool = False) -> Frame:
         """self.onmessage (raymarchWorker.ts:33-92).  `shader`/`shader_analytics` optionally fuse the
         main thread's ShadingModel.shade passes (main.ts:493-515) into the same launch."""
         width, height = int(job["width"]), int(job["height"])
@@ -53,7 +53,7 @@ class RaymarchWorker:
             step_size=float(job.get("stepSize", 0.1) if job.get("stepSize") is not None else 0.1),
             overshoot=float(job.get("overshootFactor", 1.2) if job.get("overshootFactor") is not None else 1.2),
             shader=shader, shader_analytics=shader_analytics, time=float(job.get("time", 0.0)))
-        return self.ctx.render(rq, extras=extras)
+        return self.ctx.render(rq, extras=extras, pinned=pinned)
 
     def stats(self) -> dict:
         return self.ctx.stats()

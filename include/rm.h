@@ -190,6 +190,12 @@ int rm_shade(rm_ctx* ctx, int32_t shader, uint8_t* rgba, const uint8_t* depth, c
  * denominator of the raymarch path.  Takes ~50 ms. */
 int rm_probe_fp32_peak(rm_ctx* ctx, double* tflops);
 
+/* Pinned (page-locked) host memory owned by the context.  Result planes that live in it are filled by direct
+ * asynchronous D2H copies (no staging copy on the host); any other host pointer still works through a staging
+ * buffer.  A Node addon would back its ArrayBuffers with this memory (napi_create_external_arraybuffer). */
+int rm_host_alloc(rm_ctx* ctx, size_t bytes, void** host_ptr);
+int rm_host_free(rm_ctx* ctx, void* host_ptr);
+
 /* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "multi-GPU") -------------------- */
 /* Device allocation owned by the context (freed by rm_free / rm_destroy). */
 int rm_alloc(rm_ctx* ctx, size_t bytes, void** dev_ptr);

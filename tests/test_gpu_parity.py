@@ -373,3 +373,17 @@ def test_full_size_no_accel_invariant_4k(fast_worker):
     assert np.array_equal(f.sdf_u32, 7 * (f.iters.astype(np.uint32) + 4 * hit))
     st = fast_worker.stats()
     assert st["evals_by_type"] == [st["sum_sdf_full"], 0, 0]
+
+
+def test_pinned_result_planes_match_pageable(fast_worker):
+    """rm_host_alloc planes are filled by direct DMA; pageable planes go through the staging copy — same bytes."""
+    job = make_job(200, 120, 3, "BVH", "adaptive-step-v3", 0.2, 0.9)
+    a = fast_worker.on_message(job, shader="phong", shader_analytics="iteration-heatmap", extras=True)
+    b = fast_worker.on_message(job, shader="phong", shader_analytics="iteration-heatmap", extras=True, pinned=True)
+    for k in ("depth", "normal", "sdfEval", "iters", "rgba", "rgba_analytics", "depth_f32", "sdf_u32", "depth_f64"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    # a smaller frame afterwards reuses the same page-locked pool
+    job2 = make_job(64, 40, 0, "None")
+    c = fast_worker.on_message(job2, pinned=True)
+    d = fast_worker.on_message(job2)
+    assert np.array_equal(c.normal, d.normal) and c.depth.size == 64 * 40
