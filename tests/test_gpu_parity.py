@@ -387,3 +387,19 @@ def test_pinned_result_planes_match_pageable(fast_worker):
     c = fast_worker.on_message(job2, pinned=True)
     d = fast_worker.on_message(job2)
     assert np.array_equal(c.normal, d.normal) and c.depth.size == 64 * 40
+
+
+def test_multi_gpu_fused_gather_matches_single_gpu():
+    """N >= 2 GPUs only: torchrun, one process per GPU, CUDA-IPC fused gather + NCCL stats all-reduce."""
+    import subprocess
+    import sys
+    from cpu_raymarcher_b200 import _lib
+    n = _lib.lib().rm_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
