@@ -275,6 +275,16 @@ def main():
                      "kernel_ms_per_step": kern_ms / args.steps},
     }
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this exact workload (else null)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic_cfg4.json")) as fh:
+            tr = json.load(fh)
+        if args.workload == tr["workload"] and last["n_prims"] == tr["n_prims"] and (W, H) == (tr["width"], tr["height"]) and world == 1:
+            out["roofline"]["traffic"] = tr["traffic_bytes"]
+            out["roofline"]["traffic_source"] = tr["source"]
+    except Exception:
+        pass
+
     # ---- e2e: through the reference-facing worker call with host buffers (rank 0 band set, N ranks in parallel)
     if not args.no_e2e:
         e2e = sharder.e2e_frames(job, wl["shader"], steps=max(1, min(args.steps, 3)))
