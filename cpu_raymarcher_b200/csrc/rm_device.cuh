@@ -35,12 +35,12 @@ namespace rm {
 
 constexpr unsigned kFull = 0xffffffffu;
 // CTAs (128 threads) per SM the register allocator must leave room for.  Measured on B200: the BVH kernels want
-// registers (the 32-wide unrolled search + interval state; 3 CTAs/SM = 168 registers), everything else wants occupancy.
+// registers (the 32-wide unrolled search + interval state; 4 CTAs/SM = 128 registers), everything else wants occupancy.
 #ifndef RM_INIT_LANES
 #define RM_INIT_LANES 32  // lanes that must be free before a warp refills (32 = retire the whole tile first; measured best)
 #endif
 #ifndef RM_MIN_BLOCKS_BVH
-#define RM_MIN_BLOCKS_BVH 3
+#define RM_MIN_BLOCKS_BVH 4
 #endif
 #ifndef RM_MIN_BLOCKS_OTHER
 #define RM_MIN_BLOCKS_OTHER 8
