@@ -37,6 +37,9 @@ WORKLOADS = {
     "cfg3": ("Dense Sphere Grid, sphere tracing + octree, SDF heatmap, 1920x1080", 3, None, "Octree", "sphere-tracer", "sdf-heatmap", 1920, 1080),
     "cfg4": ("Random Spheres scaled to 100k synthetic primitives, sphere tracing + BVH, iteration heatmap, 3840x2160",
              1, 100000, "BVH", "sphere-tracer", "iteration-heatmap", 3840, 2160),
+    # search-loop microbenchmark: every scene-distance query evaluates all 100 000 spheres (no acceleration structure)
+    "dense100k": ("Random Spheres scaled to 100k synthetic primitives, sphere tracing, NO acceleration structure, normal shader, 384x216",
+                  1, 100000, "None", "sphere-tracer", "normal", 384, 216),
     "cfg5": ("Atom, sphere tracing, no accel, normal shader, 7680x4320 (one frame of the analytics sweep)",
              4, None, "None", "sphere-tracer", "normal", 7680, 4320),
 }

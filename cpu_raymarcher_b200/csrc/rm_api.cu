@@ -204,6 +204,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
 
     const DevStats& s = *c->h_stats;
+    if (s.t_total) fprintf(stderr, "[rm phase timing] warp-cycles total %.3e search %.1f%% barrier %.1f%% stuck %.1f%%\n", (double)s.t_total, 100.0 * s.t_search / s.t_total, 100.0 * s.t_barrier / s.t_total, 100.0 * s.t_stuck / s.t_total);
     rm_stats_t& L = c->last;
     std::memset(&L, 0, sizeof(L));
     L.n_pixels = (uint64_t)rq->width * ownedRows;

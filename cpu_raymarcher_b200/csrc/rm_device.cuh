@@ -1076,6 +1076,14 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
     const int initLanes = RM_INIT_LANES;
     r.pending = false;
 
+#ifdef RM_PHASE_TIMING
+    long long tKernel0 = clock64(), tSearch = 0, tBarrier = 0, tStuck = 0;
+#define RM_T0() long long t0_ = clock64()
+#define RM_T1(acc) acc += clock64() - t0_
+#else
+#define RM_T0()
+#define RM_T1(acc)
+#endif
     for (;;) {
         // ---- (0) CTA rendezvous for the all-primitives pass (cooperative mode only) ----
         if (useQueue) {
@@ -1087,8 +1095,14 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
                 if (go) {
                     // Every warp of the CTA joins: request i <-> lane i in each warp; warp w searches the stages
                     // c = w (mod W) of the primitive stream, partial minima are combined through shared memory.
+#ifdef RM_PHASE_TIMING
+                    long long tb0_ = clock64();
+#endif
                     __syncthreads();
                     const unsigned head = *(volatile unsigned*)&shHead, tail = *(volatile unsigned*)&shTail;
+#ifdef RM_PHASE_TIMING
+                    tBarrier += (clock64() - tb0_) + (long long)(head & 0u);  // the volatile read forces the deferred barrier to resolve first
+#endif
                     const unsigned nBatch = min(32u, tail - head);
                     float rq[3] = {0.f, 0.f, 0.f};
                     if ((unsigned)lane < nBatch) {
@@ -1100,14 +1114,22 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
                     float pbest;
                     int pcode;
                     if constexpr (!NP::kExact) {
+                        RM_T0();
                         search_stages<PK>(P, rq, ws, lane, warpId, kWarpsPerCta, pbest, pcode);
+                        RM_T1(tSearch);
                     } else {
                         pbest = 10.f;
                         pcode = -1;
                     }
                     shPartBest[warpId][lane] = pbest;
                     shPartCode[warpId][lane] = pcode;
+#ifdef RM_PHASE_TIMING
+                    long long tb1_ = clock64();
+#endif
                     __syncthreads();
+#ifdef RM_PHASE_TIMING
+                    tBarrier += (clock64() - tb1_) + (long long)(*(volatile unsigned*)&shHead & 0u);
+#endif
                     // combine: request i is finished by thread i (warp i / 32 ... only the first 32 threads have one)
                     if (threadIdx.x < nBatch) {
                         const float4 v = shReq[(head + threadIdx.x) % kQueueCap];
@@ -1152,7 +1174,11 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
                     leave = true;
                     break;
                 }
-                __nanosleep(128);
+                {
+                    RM_T0();
+                    __nanosleep(128);
+                    RM_T1(tStuck);
+                }
             }
             if (leave) break;
         }
@@ -1591,6 +1617,14 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
         }
     }
 
+#ifdef RM_PHASE_TIMING
+    if (lane == 0) {
+        atomicAdd(&P.stats->t_total, (unsigned long long)(clock64() - tKernel0));
+        atomicAdd(&P.stats->t_search, (unsigned long long)tSearch);
+        atomicAdd(&P.stats->t_barrier, (unsigned long long)tBarrier);
+        atomicAdd(&P.stats->t_stuck, (unsigned long long)tStuck);
+    }
+#endif
     // ---- epilogue: diagnostics (main.ts:527-548) — warp reduce, one atomic set per warp ----
     unsigned long long s0 = warp_sum_u64(st.sum_sdf), s1 = warp_sum_u64(st.sum_iters);
     unsigned long long s2 = warp_sum_u64(st.sum_sdf_full), s3 = warp_sum_u64(st.sum_iters_full);

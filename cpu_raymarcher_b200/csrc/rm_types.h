@@ -59,6 +59,7 @@ struct DevStats {
     unsigned long long n_hit;
     unsigned int max_sdf, min_sdf, max_iters, min_iters;
     unsigned int queue;  // atomic tile counter of the persistent-CTA work queue
+    unsigned long long t_total, t_search, t_barrier, t_stuck;  // RM_PHASE_TIMING builds: warp-cycles by phase
     unsigned int pad_;
 };
 
