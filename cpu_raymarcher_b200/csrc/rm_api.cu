@@ -223,8 +223,8 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     {
         const bool ts = !(c->flags & RM_F_VALIDATE_FP64) && c->scene.prim_kind == PK_TSPHERE;
         // translation-only spheres: 11 FLOP (3 add, 3 mul, 2 add, sqrt, sub, min); the screened search of large scenes
-        // executes 9 per primitive (no sqrt / radius subtraction in the hot loop)
-        const double tsFlops = c->scene.n_chunks >= 16 ? 9.0 : 11.0;
+        // executes 7 per primitive (2 p.t + |t|^2 as 3 FMA, then min; no sqrt / radius subtraction in the hot loop)
+        const double tsFlops = c->scene.n_chunks >= 16 ? 7.0 : 11.0;
         L.algorithmic_flops = ts ? tsFlops * (double)s.evals_sphere
                                  : 26.0 * (double)s.evals_sphere + 38.0 * (double)s.evals_box + 29.0 * (double)s.evals_torus;
     }
@@ -381,12 +381,12 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     std::vector<float4> rec;
     if (allTS) {
         const int32_t nChunks = (n + 31) / 32;
-        rec.resize((size_t)nChunks * 32);  // 32 float4 = 128 floats = tx[32] ty[32] tz[32] r[32]
+        rec.resize((size_t)nChunks * 40);  // 40 float4 = 160 floats = tx[32] ty[32] tz[32] r[32] tt[32]
         float* f = reinterpret_cast<float*>(rec.data());
-        float rmin = 3.0e38f, rmax = -3.0e38f;
+        float rmin = 3.0e38f, rmax = -3.0e38f, ttmax = 0.f;
         std::vector<float> chunkRmax(((size_t)nChunks + 3) / 4 * 4, 0.f);  // padded: the kernel reads one float4 per stage
         for (int32_t i = 0; i < nChunks * 32; ++i) {
-            float* c = f + (size_t)(i >> 5) * 128 + (i & 31);
+            float* c = f + (size_t)(i >> 5) * 160 + (i & 31);
             if (i < n) {
                 const float* m = s->world_to_local + 16 * (size_t)i;
                 const float r = (float)s->params[4 * (size_t)i];
@@ -394,17 +394,21 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
                 c[32] = m[13];
                 c[64] = m[14];
                 c[96] = r;
+                c[128] = (float)((double)m[12] * m[12] + (double)m[13] * m[13] + (double)m[14] * m[14]);
+                ttmax = std::fmax(ttmax, c[128]);
                 rmin = std::fmin(rmin, r);
                 rmax = std::fmax(rmax, r);
                 chunkRmax[(size_t)(i >> 5)] = std::fmax(chunkRmax[(size_t)(i >> 5)], r);
             } else {  // padding: a sphere of radius 0 so far away that it can never be the minimum
                 c[0] = c[32] = c[64] = 1.0e15f;
                 c[96] = 0.f;
+                c[128] = 3.0e30f;
             }
         }
         ds.n_chunks = nChunks;
         ds.r_min = rmin;
         ds.r_max = rmax;
+        ds.tt_max = ttmax;
         std::vector<float4> one((size_t)n);
         for (int32_t i = 0; i < n; ++i) {
             const float* m = s->world_to_local + 16 * (size_t)i;

@@ -175,10 +175,10 @@ RM_DEV float prim_sdf_f32(const float4* __restrict__ rec, int j, const float q[3
 // ------------------------------------------------------------------------------------------
 // TMA bulk staging of primitive records into shared memory (per-warp double buffer)
 // ------------------------------------------------------------------------------------------
-constexpr int kStageBytes = 2048;  // one stage = 128 translation-sphere records or 32 general records
-constexpr int kWarpsPerCta = 4;
+constexpr int kStageBytes = 2560;  // one stage = 4 sphere chunks of 640 B (tx,ty,tz,r,|t|^2 x 32) or 40 general records
+constexpr int kChunkBytes = 640, kChunkF4 = kChunkBytes / 16;
+constexpr int kWarpsPerCtaMax = 8;  // fast BVH kernels run 8 warps per CTA (64-request batches, 2 per lane); all others 4
 constexpr int kChunk = 32;         // argmin granularity of the fp32 search
-constexpr int kQueueCap = kWarpsPerCta * 32;  // each thread has at most one request outstanding
 
 RM_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 RM_DEV void mbar_init(uint32_t bar, unsigned count) {
@@ -239,25 +239,33 @@ RM_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
-// Squared centre distances of the 32 spheres of one chunk-SoA block in shared memory; returns their minimum.
-RM_DEV float chunk_min_sq(uint32_t ch, f32x2 qx, f32x2 qy, f32x2 qz) {
-    float m = 3.0e38f;
-    // unrolled by 4 groups only: the whole screened loop must stay resident in the SM's small L0 instruction cache
-#pragma unroll 4
+// Screening value of the 32 spheres of one chunk-SoA block in shared memory for NQ query points per lane:
+// |p + t|^2 - |p|^2 = 2 p.t + |t|^2 with |t|^2 precomputed per sphere — three FFMA2 per pair of spheres per point,
+// no MUFU, radii not loaded.  Register tiling over NQ points amortises every broadcast LDS.128 (shared-memory
+// wavefronts, not FMAs, are the scarce resource of a one-point loop).  The cancellation error (a few ulp of
+// |p|^2 + |t|^2) is covered by the slack of the screen; winners are re-evaluated with the plain formula.
+template <int NQ>
+RM_DEV void chunk_min_dot(uint32_t ch, const float (&a2)[NQ][3], float (&m)[NQ]) {
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) m[k] = 3.0e38f;
+#pragma unroll 2
     for (int g = 0; g < 8; ++g) {
-        const float4 X = lds128(ch + 16u * g), Y = lds128(ch + 128u + 16u * g), Z = lds128(ch + 256u + 16u * g);
-        f32x2 lx0 = add2(qx, pk2(X.x, X.y)), lx1 = add2(qx, pk2(X.z, X.w));
-        f32x2 ly0 = add2(qy, pk2(Y.x, Y.y)), ly1 = add2(qy, pk2(Y.z, Y.w));
-        f32x2 lz0 = add2(qz, pk2(Z.x, Z.y)), lz1 = add2(qz, pk2(Z.z, Z.w));
-        f32x2 s0 = fma2(lx0, lx0, fma2(ly0, ly0, mul2(lz0, lz0)));
-        f32x2 s1 = fma2(lx1, lx1, fma2(ly1, ly1, mul2(lz1, lz1)));
-        float a, b, c, d;
-        upk2(s0, a, b);
-        upk2(s1, c, d);
-        m = fminf(m, fminf(a, b));
-        m = fminf(m, fminf(c, d));
+        const float4 X = lds128(ch + 16u * g), Y = lds128(ch + 128u + 16u * g), Z = lds128(ch + 256u + 16u * g),
+                     T = lds128(ch + 512u + 16u * g);
+        const f32x2 x0 = pk2(X.x, X.y), x1 = pk2(X.z, X.w), y0 = pk2(Y.x, Y.y), y1 = pk2(Y.z, Y.w);
+        const f32x2 z0 = pk2(Z.x, Z.y), z1 = pk2(Z.z, Z.w), t0 = pk2(T.x, T.y), t1 = pk2(T.z, T.w);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const f32x2 ax = pk2(a2[k][0], a2[k][0]), ay = pk2(a2[k][1], a2[k][1]), az = pk2(a2[k][2], a2[k][2]);
+            f32x2 s0 = fma2(ax, x0, fma2(ay, y0, fma2(az, z0, t0)));
+            f32x2 s1 = fma2(ax, x1, fma2(ay, y1, fma2(az, z1, t1)));
+            float a, b, c, d;
+            upk2(s0, a, b);
+            upk2(s1, c, d);
+            m[k] = fminf(m[k], fminf(a, b));
+            m[k] = fminf(m[k], fminf(c, d));
+        }
     }
-    return m;
 }
 // Exact fp32 SDFs of the 32 spheres of a chunk held in shared memory: running (min, argmin).
 RM_DEV void chunk_exact_smem(uint32_t ch, int base, int valid, const float q[3], float& best, int& idx) {
@@ -280,7 +288,7 @@ RM_DEV void chunk_exact_smem(uint32_t ch, int base, int valid, const float q[3],
 }
 // Same from global memory (per-lane chunk; used to resolve the few screened candidates).
 RM_DEV void chunk_exact_gmem(const float4* __restrict__ rec, int chunk, const float q[3], float& best, int& idx) {
-    const float4* c = rec + (size_t)chunk * 32;
+    const float4* c = rec + (size_t)chunk * kChunkF4;
 #pragma unroll 2
     for (int g = 0; g < 8; ++g) {
         const float4 X = __ldg(c + g), Y = __ldg(c + 8 + g), Z = __ldg(c + 16 + g), R = __ldg(c + 24 + g);
@@ -297,30 +305,40 @@ RM_DEV void chunk_exact_gmem(const float4* __restrict__ rec, int chunk, const fl
     }
 }
 
-// All-primitives search for translation-only spheres over the stages c = first, first + stride, ...
+// All-primitives search for translation-only spheres over the stages c = first, first + stride, ..., for NQ query
+// points per lane (NQ = 2 in the CTA-cooperative pass: 64 requests per batch, lane i takes requests i and i + 32).
 //   n_chunks <  kScreenMinChunks : every sphere's SDF (sqrt) straight from the stage;
-//   otherwise SCREENED            : the hot loop only computes squared centre distances (packed FADD2 / FMUL2 /
-//     FFMA2, no MUFU, radii not even loaded).  With S = min_j |p - c_j|^2 the nearest surface satisfies
-//     d* <= sqrt(S) - r_min, so sphere j can only win if |p - c_j| <= sqrt(S) + (r_max - r_min); chunks whose
-//     minimum squared distance passes that test against the RUNNING S are remembered (a handful per query)
-//     and resolved exactly afterwards.  Same result as evaluating every SDF; ~6 instead of ~10 issue slots.
+//   otherwise SCREENED            : the hot loop only computes squared centre distances (chunk_min_dot).  With
+//     S = min_j |p - c_j|^2 the nearest surface satisfies d* <= sqrt(S) - r_min, so a sphere of chunk C can only win
+//     if |p - c_j| <= sqrt(S) - r_min + r_max(C); chunks passing that test against the RUNNING S are remembered
+//     (a handful per query) and resolved exactly afterwards.  Same result as evaluating every SDF.
 constexpr int kScreenMinChunks = 16;
-constexpr int kCandCap = 48;
-RM_DEV void search_stages_ts(const RenderParams& P, const float q[3], WarpStage& ws, int lane, int first, int stride, float& best,
-                             int& code) {
+constexpr int kCandCap = 40;
+template <int NQ>
+RM_DEV void search_stages_ts(const RenderParams& P, const float (&q)[NQ][3], WarpStage& ws, int lane, int first, int stride,
+                             float (&best)[NQ], int (&code)[NQ]) {
     const float4* __restrict__ rec = P.scene.rec;
     const int nChunks = P.scene.n_chunks;
-    const int nStages = (nChunks + 3) / 4;  // 4 chunks (2 KB) per stage
+    const int nStages = (nChunks + 3) / 4;  // 4 chunks (2.5 KB) per stage
     const int myStages = nStages > first ? (nStages - first + stride - 1) / stride : 0;
     auto issue = [&](int i) {
         const int c = first + i * stride, sgi = i & 1;
         const int cnt = min(4, nChunks - 4 * c);
-        const unsigned bytes = (unsigned)(cnt * 512);
+        const unsigned bytes = (unsigned)(cnt * kChunkBytes);
         mbar_expect_tx(ws.bar[sgi], bytes);
-        bulk_g2s(ws.bufAddr[sgi], rec + (size_t)c * 128, bytes, ws.bar[sgi]);
+        bulk_g2s(ws.bufAddr[sgi], rec + (size_t)c * 4 * kChunkF4, bytes, ws.bar[sgi]);
     };
     const bool resident = ws.resident && first == 0 && stride == 1;
-    const f32x2 qx = pk2(q[0], q[0]), qy = pk2(q[1], q[1]), qz = pk2(q[2], q[2]);
+    float a2[NQ][3], qq[NQ], E[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        a2[k][0] = 2.f * q[k][0];
+        a2[k][1] = 2.f * q[k][1];
+        a2[k][2] = 2.f * q[k][2];
+        qq[k] = fmaf(q[k][0], q[k][0], fmaf(q[k][1], q[k][1], q[k][2] * q[k][2]));
+        // absolute error bound of the screening value: ~4 ulp of the largest intermediate (|p| + |t|max)^2
+        E[k] = 5.0e-7f * (qq[k] + P.scene.tt_max + 2.f * NumFast::sqrt_(qq[k] * P.scene.tt_max)) + 1e-30f;
+    }
     const float rMin = P.scene.r_min;
     // attempt 0: screened (large scenes); attempt 1: plain SDF of every sphere, taken by the whole warp when some
     // lane's candidate list overflowed (radius spread inside the chunks too wide for the screen to be selective)
@@ -330,13 +348,19 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float q[3], WarpStage&
             if (myStages > 0) issue(0);
             if (myStages > 1) issue(1);
         }
-        best = 10.f;
-        code = -1;
-        float sRun = 3.0e38f, rootS = 1.0e19f;  // running min squared centre distance and its square root
-        unsigned short candChunk[kCandCap];
-        float candS[kCandCap];
-        int nCand = 0;
+        float sRun[NQ], rootS[NQ];  // running min squared centre distance and (an upper bound of) its square root
+        unsigned short candChunk[NQ][kCandCap];
+        float candS[NQ][kCandCap];
+        int nCand[NQ];
         bool overflow = false;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            best[k] = 10.f;
+            code[k] = -1;
+            sRun[k] = 3.0e38f;
+            rootS[k] = 1.0e19f;
+            nCand[k] = 0;
+        }
         for (int i = 0; i < myStages; ++i) {
             const int sgi = i & 1;
             if (!resident) {
@@ -352,36 +376,42 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float q[3], WarpStage&
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (c >= cnt) break;
-                const uint32_t ch = st + 512u * (unsigned)c;
+                const uint32_t ch = st + (unsigned)kChunkBytes * (unsigned)c;
                 if (!screened) {
-                    chunk_exact_smem(ch, (chunk0 + c) * 32, min(32, P.scene.n_prims - (chunk0 + c) * 32), q, best, code);
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k)
+                        chunk_exact_smem(ch, (chunk0 + c) * 32, min(32, P.scene.n_prims - (chunk0 + c) * 32), q[k], best[k], code[k]);
                 } else {
-                    const float m = chunk_min_sq(ch, qx, qy, qz);
-                    if (m < sRun) {  // new nearest centre
-                        sRun = m;
-                        rootS = NumFast::sqrt_(m);
-                    }
-                    // a sphere of this chunk can only win if |p - c_j| <= sqrt(S) - r_min + r_max(chunk)  (+ slack)
-                    const float t = rootS + (rmv[c] - rMin);
-                    if (m <= t * t * 1.00001f + 1e-30f) {
-                        if (nCand == kCandCap) {  // compact against the current bound before giving up
-                            int w = 0;
-                            for (int e = 0; e < nCand; ++e) {
-                                const float te = rootS + (__ldg(P.scene.chunk_rmax + candChunk[e]) - rMin);
-                                if (candS[e] <= te * te * 1.00001f + 1e-30f) {
-                                    candChunk[w] = candChunk[e];
-                                    candS[w] = candS[e];
-                                    ++w;
-                                }
-                            }
-                            nCand = w;
+                    float mq[NQ];
+                    chunk_min_dot<NQ>(ch, a2, mq);
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) {
+                        const float m = mq[k] + qq[k];  // min squared centre distance of the chunk, +-E
+                        if (m < sRun[k]) {              // new nearest centre
+                            sRun[k] = m;
+                            rootS[k] = NumFast::sqrt_(fmaxf(m + E[k], 0.f));
                         }
-                        if (nCand < kCandCap) {
-                            candChunk[nCand] = (unsigned short)(chunk0 + c);
-                            candS[nCand] = m;
-                            ++nCand;
-                        } else {
-                            overflow = true;
+                        const float t = rootS[k] + (rmv[c] - rMin);
+                        if (m - E[k] <= t * t * 1.00001f) {
+                            if (nCand[k] == kCandCap) {  // compact against the current bound before giving up
+                                int w = 0;
+                                for (int e = 0; e < nCand[k]; ++e) {
+                                    const float te = rootS[k] + (__ldg(P.scene.chunk_rmax + candChunk[k][e]) - rMin);
+                                    if (candS[k][e] - E[k] <= te * te * 1.00001f) {
+                                        candChunk[k][w] = candChunk[k][e];
+                                        candS[k][w] = candS[k][e];
+                                        ++w;
+                                    }
+                                }
+                                nCand[k] = w;
+                            }
+                            if (nCand[k] < kCandCap) {
+                                candChunk[k][nCand[k]] = (unsigned short)(chunk0 + c);
+                                candS[k][nCand[k]] = m;
+                                ++nCand[k];
+                            } else {
+                                overflow = true;
+                            }
                         }
                     }
                 }
@@ -391,10 +421,12 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float q[3], WarpStage&
         }
         if (!screened) break;
         if (__any_sync(kFull, overflow)) continue;  // rare: redo the pass unscreened, all lanes together
-        for (int e = 0; e < nCand; ++e) {
-            const float te = rootS + (__ldg(P.scene.chunk_rmax + candChunk[e]) - rMin);
-            if (candS[e] <= te * te * 1.00001f + 1e-30f) chunk_exact_gmem(rec, (int)candChunk[e], q, best, code);
-        }
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+            for (int e = 0; e < nCand[k]; ++e) {
+                const float te = rootS[k] + (__ldg(P.scene.chunk_rmax + candChunk[k][e]) - rMin);
+                if (candS[k][e] - E[k] <= te * te * 1.00001f) chunk_exact_gmem(rec, (int)candChunk[k][e], q[k], best[k], code[k]);
+            }
         break;
     }
     // padded dummies can never win (|l| ~ 1e15), so code < n_prims whenever it is set
@@ -443,7 +475,12 @@ template <int PK>
 RM_DEV void search_stages(const RenderParams& P, const float q[3], WarpStage& ws, int lane, int first, int stride, float& best,
                           int& code) {
     if constexpr (PK == PK_TSPHERE) {
-        search_stages_ts(P, q, ws, lane, first, stride, best, code);
+        const float q1[1][3] = {{q[0], q[1], q[2]}};
+        float b1[1];
+        int c1[1];
+        search_stages_ts<1>(P, q1, ws, lane, first, stride, b1, c1);
+        best = b1[0];
+        code = c1[0];
         return;
     }
     constexpr int kF4 = (PK == PK_TSPHERE) ? 1 : 4;     // float4 per primitive
@@ -990,8 +1027,17 @@ RM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
     return v;
 }
 
+template <class NP, int ACCEL>
+struct CtaShape {
+    static constexpr int kWarps = (!NP::kExact && ACCEL == RM_ACCEL_BVH) ? kWarpsPerCtaMax : 4;
+};
 template <class NP, int ACCEL, int PK>
-__global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_BVH : RM_MIN_BLOCKS_OTHER) render_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
+                                  (ACCEL == RM_ACCEL_BVH) ? (RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL>::kWarps : RM_MIN_BLOCKS_OTHER)
+    render_kernel(const __grid_constant__ RenderParams P) {
+    constexpr int kWarpsPerCta = CtaShape<NP, ACCEL>::kWarps;
+    constexpr int kQueueCap = kWarpsPerCta * 32;  // each thread has at most one request outstanding
+    constexpr unsigned kBatch = (kWarpsPerCta == 8) ? 64u : 32u;  // requests served per cooperative pass
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -1015,13 +1061,14 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
     // ---- shared memory: per-warp TMA stages for the primitive stream, and the CTA-wide request queue of
     //      the all-primitives service (requests are just a point, so they can move between warps even
     //      though ray state cannot: any warp that finds 32 of them serves them at full lane occupancy) ----
-    __shared__ __align__(128) float4 shStage[kWarpsPerCta][2][kStageBytes / 16];
+    extern __shared__ __align__(128) float4 shStageDyn[];  // [kWarpsPerCta][2][kStageBytes / 16], sized at launch
+    float4 (*shStage)[2][kStageBytes / 16] = reinterpret_cast<float4 (*)[2][kStageBytes / 16]>(shStageDyn);
     __shared__ __align__(8) unsigned long long shBar[kWarpsPerCta][2];
     __shared__ float4 shReq[kQueueCap];               // ring of requests: x, y, z, owner thread
     __shared__ double shRes[kWarpsPerCta * 32];        // results by owner thread
     __shared__ unsigned shReady[kWarpsPerCta * 32];
-    __shared__ float shPartBest[kWarpsPerCta][32];     // per-warp partial search results of the batch in flight
-    __shared__ int shPartCode[kWarpsPerCta][32];
+    __shared__ float shPartBest[kWarpsPerCta][kBatch];  // per-warp partial search results of the batch in flight
+    __shared__ int shPartCode[kWarpsPerCta][kBatch];
     __shared__ unsigned shTail, shHead, shGo, shStuck, shFinished;
     const int warpId = threadIdx.x >> 5;
     WarpStage ws;
@@ -1042,8 +1089,8 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
         __syncwarp();
         // small scenes: stage the whole primitive array once and keep it resident in shared memory
         constexpr int kPerStage0 = kStageBytes / (16 * ((PK == PK_TSPHERE) ? 1 : 4));
-        if (P.scene.n_prims > 0 && P.scene.n_prims <= kPerStage0) {
-            const unsigned bytes = (PK == PK_TSPHERE) ? (unsigned)(P.scene.n_chunks * 512) : (unsigned)(P.scene.n_prims * 64);
+        if (P.scene.n_prims > 0 && ((PK == PK_TSPHERE) ? P.scene.n_chunks <= 4 : P.scene.n_prims <= kPerStage0)) {
+            const unsigned bytes = (PK == PK_TSPHERE) ? (unsigned)(P.scene.n_chunks * kChunkBytes) : (unsigned)(P.scene.n_prims * 64);
             if (lane == 0) {
                 mbar_expect_tx(ws.bar[0], bytes);
                 bulk_g2s(ws.bufAddr[0], P.scene.rec, bytes, ws.bar[0]);
@@ -1103,26 +1150,45 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
 #ifdef RM_PHASE_TIMING
                     tBarrier += (clock64() - tb0_) + (long long)(head & 0u);  // the volatile read forces the deferred barrier to resolve first
 #endif
-                    const unsigned nBatch = min(32u, tail - head);
-                    float rq[3] = {0.f, 0.f, 0.f};
-                    if ((unsigned)lane < nBatch) {
-                        const float4 v = shReq[(head + (unsigned)lane) % kQueueCap];
-                        rq[0] = v.x;
-                        rq[1] = v.y;
-                        rq[2] = v.z;
+                    const unsigned nBatch = min(kBatch, tail - head);
+                    // lane i takes request i (and request i + 32 in the 64-request form: two points per lane
+                    // halve the shared-memory wavefronts per evaluation)
+                    constexpr int NQ = (int)(kBatch / 32u);
+                    float rq[NQ][3];
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) {
+                        rq[k][0] = rq[k][1] = rq[k][2] = 0.f;
+                        const unsigned ri = (unsigned)lane + 32u * (unsigned)k;
+                        if (ri < nBatch) {
+                            const float4 v = shReq[(head + ri) % kQueueCap];
+                            rq[k][0] = v.x;
+                            rq[k][1] = v.y;
+                            rq[k][2] = v.z;
+                        }
                     }
-                    float pbest;
-                    int pcode;
+                    float pbest[NQ];
+                    int pcode[NQ];
                     if constexpr (!NP::kExact) {
                         RM_T0();
-                        search_stages<PK>(P, rq, ws, lane, warpId, kWarpsPerCta, pbest, pcode);
+                        if constexpr (PK == PK_TSPHERE) {
+                            search_stages_ts<NQ>(P, rq, ws, lane, warpId, kWarpsPerCta, pbest, pcode);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < NQ; ++k) search_stages<PK>(P, rq[k], ws, lane, warpId, kWarpsPerCta, pbest[k], pcode[k]);
+                        }
                         RM_T1(tSearch);
                     } else {
-                        pbest = 10.f;
-                        pcode = -1;
+#pragma unroll
+                        for (int k = 0; k < NQ; ++k) {
+                            pbest[k] = 10.f;
+                            pcode[k] = -1;
+                        }
                     }
-                    shPartBest[warpId][lane] = pbest;
-                    shPartCode[warpId][lane] = pcode;
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) {
+                        shPartBest[warpId][lane + 32 * k] = pbest[k];
+                        shPartCode[warpId][lane + 32 * k] = pcode[k];
+                    }
 #ifdef RM_PHASE_TIMING
                     long long tb1_ = clock64();
 #endif
@@ -1158,7 +1224,7 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
                     }
                     if (threadIdx.x == 0) {
                         shHead = head + nBatch;
-                        shGo = (tail - head - nBatch >= 32u) ? 1u : 0u;
+                        shGo = (tail - head - nBatch >= kBatch) ? 1u : 0u;
                     }
                     __syncthreads();
                     continue;
@@ -1436,7 +1502,7 @@ __global__ void __launch_bounds__(128, (ACCEL == RM_ACCEL_BVH) ? RM_MIN_BLOCKS_B
                 __syncwarp();
                 if (lane == leader) {
                     __threadfence_block();
-                    if (base + (unsigned)__popc(need) - *(volatile unsigned*)&shHead >= 32u) *(volatile unsigned*)&shGo = 1u;  // a full batch is waiting
+                    if (base + (unsigned)__popc(need) - *(volatile unsigned*)&shHead >= kBatch) *(volatile unsigned*)&shGo = 1u;  // a full batch is waiting
                 }
             }
         }

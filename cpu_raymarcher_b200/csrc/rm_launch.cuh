@@ -10,19 +10,24 @@ namespace rm {
 template <class NP, int ACCEL, int PK>
 static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     auto kern = render_kernel<NP, ACCEL, PK>;
+    constexpr int kWarps = CtaShape<NP, ACCEL>::kWarps;
+    constexpr int kThreads = 32 * kWarps;
+    constexpr size_t kDynSmem = (size_t)kWarps * 2 * kStageBytes;  // per-warp double-buffered TMA stages
     static int blocksPerSM = 0;  // per instantiation
     if (blocksPerSM == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+        if (e != cudaSuccess) return (int)e;
         int b = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, 128, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, kDynSmem);
         if (e != cudaSuccess) return (int)e;
         blocksPerSM = std::max(b, 1);
     }
     // persistent grid: a multiple of the SM count, never more warps than there are tiles
     long long warpsWanted = p.n_tiles;
     int maxBlocks = n_sms * blocksPerSM;
-    int blocks = (int)std::min<long long>(maxBlocks, (warpsWanted + 3) / 4);
+    int blocks = (int)std::min<long long>(maxBlocks, (warpsWanted + kWarps - 1) / kWarps);
     if (blocks < 1) blocks = 1;
-    kern<<<blocks, 128, 0, stream>>>(p);
+    kern<<<blocks, kThreads, kDynSmem, stream>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -31,13 +31,14 @@ struct DevScene {
     const double* params;  // [4n]
     // fast-path packed records
     // PK_GENERAL: 4 x float4 per primitive (3 affine rows + params/type).
-    // PK_TSPHERE: structure-of-arrays per 32-primitive chunk: float tx[32], ty[32], tz[32], r[32] (512 B per chunk,
+    // PK_TSPHERE: structure-of-arrays per 32-primitive chunk: float tx[32], ty[32], tz[32], r[32], tt[32] = |t|^2 (640 B per chunk,
     //             the last chunk padded with far-away dummies) so that one LDS.128 feeds two packed f32x2 lanes.
     const float4* rec;
     const float4* rec1;      // PK_TSPHERE: one float4 (tx,ty,tz,r) per primitive for single-primitive evaluations
     const float* chunk_rmax;  // PK_TSPHERE: largest radius inside each 32-primitive chunk
     int32_t n_chunks;        // PK_TSPHERE: number of 32-primitive chunks
     float r_min, r_max;      // PK_TSPHERE: radius range (screening bound of the squared-distance search)
+    float tt_max;            // PK_TSPHERE: largest |translation|^2 (error bound of the screening arithmetic)
     // acceleration structure
     const rm_bvh_node* bvh;
     const rm_octree_node* oct;
