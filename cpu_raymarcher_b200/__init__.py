@@ -3,6 +3,6 @@ hot path, behind the reference's worker Job/Result contract.  The compute lives 
 (hand-written sm_100a CUDA behind the C ABI of include/rm.h); this package is the thin host side."""
 from ._lib import ACCELS, ALGORITHMS, LIB_PATH, SHADERS, RmError  # noqa: F401
 from .camera import Camera  # noqa: F401
-from .renderer import Context, Frame, build_bvh, build_octree  # noqa: F401
+from .renderer import Context, Frame, build_bvh, build_bvh_scene, build_octree, build_octree_scene  # noqa: F401
 from .scene import Scene  # noqa: F401
 from .worker import RaymarchWorker  # noqa: F401

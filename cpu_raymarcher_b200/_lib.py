@@ -36,10 +36,21 @@ class OctreeNode(C.Structure):
                 ("min_distance", C.c_double)]
 
 
+class OpNode(C.Structure):  # rm_op_node, 128 bytes
+    _fields_ = [("kind", C.c_int32), ("child", C.c_int32 * 2), ("prim", C.c_int32), ("p", C.c_double * 4),
+                ("dir", C.c_float * 4), ("transform", C.c_float * 16)]
+
+
+NODE_KINDS = {"primitive": 0, "round": 1, "twist": 2, "smooth-union": 3, "smooth-subtraction": 4, "repetition": 5,
+              "animated-translate": 6}
+RM_MAX_TREE_DEPTH = 16
+
+
 class Scene(C.Structure):
     _fields_ = [("n_prims", C.c_int32), ("type", C.c_void_p), ("world_to_local", C.c_void_p), ("params", C.c_void_p),
                 ("accel_kind", C.c_int32), ("n_nodes", C.c_int32), ("nodes", C.c_void_p), ("n_leaf_prims", C.c_int32),
-                ("leaf_prim_index", C.c_void_p)]
+                ("leaf_prim_index", C.c_void_p), ("n_op_nodes", C.c_int32), ("op_nodes", C.c_void_p),
+                ("n_objects", C.c_int32), ("object_root", C.c_void_p)]
 
 
 class Request(C.Structure):
@@ -60,13 +71,13 @@ class Stats(C.Structure):
     _fields_ = [("n_pixels", C.c_uint64), ("sum_sdf", C.c_uint64), ("sum_iters", C.c_uint64), ("max_sdf", C.c_uint32),
                 ("min_sdf", C.c_uint32), ("max_iters", C.c_uint32), ("min_iters", C.c_uint32),
                 ("sum_sdf_full", C.c_uint64), ("sum_iters_full", C.c_uint64), ("evals_by_type", C.c_uint64 * 3),
-                ("n_hit", C.c_uint64), ("algorithmic_flops", C.c_double), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
+                ("n_hit", C.c_uint64), ("operator_flops", C.c_double), ("algorithmic_flops", C.c_double), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
                 ("device", C.c_int32)]
 
 
 # every symbol include/rm.h declares
 EXPORTS = ["rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_upload_scene",
-           "rm_build_bvh", "rm_build_octree", "rm_render", "rm_render_device", "rm_stats", "rm_shade", "rm_alloc",
+           "rm_build_bvh", "rm_build_octree", "rm_build_bvh_scene", "rm_build_octree_scene", "rm_render", "rm_render_device", "rm_stats", "rm_shade", "rm_alloc",
            "rm_free", "rm_host_alloc", "rm_host_free", "rm_probe_fp32_peak", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
 
 _LIB = None
@@ -90,6 +101,8 @@ def lib():
         L.rm_upload_scene.argtypes = [vp, C.POINTER(Scene)]
         L.rm_build_bvh.argtypes = [i32, vp, vp, vp, u32, vp, C.POINTER(i32), vp, C.POINTER(i32)]
         L.rm_build_octree.argtypes = [i32, vp, vp, vp, u32, vp, C.POINTER(i32), vp, C.POINTER(i32)]
+        L.rm_build_bvh_scene.argtypes = [C.POINTER(Scene), u32, vp, C.POINTER(i32), vp, C.POINTER(i32)]
+        L.rm_build_octree_scene.argtypes = [C.POINTER(Scene), u32, vp, C.POINTER(i32), vp, C.POINTER(i32)]
         L.rm_render.argtypes = [vp, C.POINTER(Request), C.POINTER(Result)]
         L.rm_render_device.argtypes = [vp, C.POINTER(Request), C.POINTER(Result), vp]
         L.rm_stats.argtypes = [vp, C.POINTER(Stats)]

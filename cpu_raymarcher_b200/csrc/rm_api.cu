@@ -41,6 +41,10 @@ struct rm_ctx {
     bool has_scene = false;
     DevScene scene{};
     std::vector<void*> scene_allocs;
+    TreeProgram tree;            // operator-tree scenes: compiled programs (host copy, for the per-frame animation offsets)
+    float* d_anim = nullptr;     // device copy of the AnimatedTranslate offsets (inside scene_allocs)
+    double anim_time = 0.0;
+    bool anim_valid = false;
     // per-launch stats
     DevStats* d_stats = nullptr;
     DevStats* h_stats = nullptr;  // pinned
@@ -74,6 +78,9 @@ void free_scene(rm_ctx* c) {
     for (void* p : c->scene_allocs) cudaFree(p);
     c->scene_allocs.clear();
     c->has_scene = false;
+    c->tree = TreeProgram();
+    c->d_anim = nullptr;
+    c->anim_valid = false;
     std::memset(&c->scene, 0, sizeof(c->scene));
 }
 
@@ -152,6 +159,20 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.shader = rq->shader;
     P.shader2 = rq->shader_analytics;
     P.length_sqrt = (c->flags & RM_F_LENGTH_SQRT) ? 1 : 0;
+    const bool tree = c->scene.n_instrs > 0;
+    // Operator trees always run the exact (fp64, unfused) kernels: B200 has full-rate-class fp64 and these scenes
+    // are a handful of primitives, so there is no reduced-precision variant to disagree with the reference.  A
+    // context created without RM_F_VALIDATE_FP64 only swaps V8's compensated hypot for a plain sqrt.
+    if (tree && !(c->flags & RM_F_VALIDATE_FP64)) P.length_sqrt = 1;
+    if (tree && !c->tree.anims.empty() && (!c->anim_valid || c->anim_time != rq->time)) {
+        // Scene.updateTime (raymarcher.ts:59): AnimatedTranslate's offset vector is a per-job constant
+        std::vector<float> off;
+        eval_anim_offsets(c->tree, rq->time, off);
+        CU(c, cudaMemcpyAsync(c->d_anim, off.data(), off.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CU(c, cudaStreamSynchronize(stream));  // `off` is pageable and goes out of scope
+        c->anim_time = rq->time;
+        c->anim_valid = true;
+    }
     P.tiles_x = (rq->width + kTileW - 1) / kTileW;
     uint64_t ownedRows = (uint64_t)bandH;
     if (rq->stripe_count > 1) {
@@ -193,7 +214,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     int launches = 0;
     CU(c, cudaEventRecord(c->ev0, stream));
     if (P.n_tiles > 0) {
-        int e = (c->flags & RM_F_VALIDATE_FP64) ? launch_render_val(P, c->n_sms, stream) : launch_render_fast(P, c->n_sms, stream);
+        int e = ((c->flags & RM_F_VALIDATE_FP64) || tree) ? launch_render_val(P, c->n_sms, stream) : launch_render_fast(P, c->n_sms, stream);
         if (e != 0) return fail(c, RM_ERR_CUDA, "render launch: %s", cudaGetErrorString((cudaError_t)e));
         launches = 1;
     }
@@ -225,8 +246,9 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
         // translation-only spheres: 11 FLOP (3 add, 3 mul, 2 add, sqrt, sub, min); the screened search of large scenes
         // executes 7 per primitive (2 p.t + |t|^2 as 3 FMA, then min; no sqrt / radius subtraction in the hot loop)
         const double tsFlops = c->scene.n_chunks >= 16 ? 7.0 : 11.0;
+        L.operator_flops = (double)s.op_flops;
         L.algorithmic_flops = ts ? tsFlops * (double)s.evals_sphere
-                                 : 26.0 * (double)s.evals_sphere + 38.0 * (double)s.evals_box + 29.0 * (double)s.evals_torus;
+                                 : 26.0 * (double)s.evals_sphere + 38.0 * (double)s.evals_box + 29.0 * (double)s.evals_torus + L.operator_flops;
     }
     L.kernel_ms = ms;
     L.n_launches = launches;
@@ -342,6 +364,52 @@ int rm_build_octree(int32_t n, const uint8_t* type, const float* w2l, const doub
     return RM_OK;
 }
 
+static int check_scene_arrays(const rm_scene* s) {
+    if (!s || s->n_prims < 0 || (s->n_prims > 0 && (!s->type || !s->world_to_local || !s->params))) return RM_ERR_ARG;
+    for (int32_t i = 0; i < s->n_prims; ++i)
+        if (s->type[i] > RM_PRIM_TORUS) return RM_ERR_UNSUPPORTED_PRIMITIVE;
+    std::string err;
+    return validate_tree(*s, err);
+}
+
+int rm_build_bvh_scene(const rm_scene* s, unsigned flags, rm_bvh_node* nodes, int32_t* n_nodes, int32_t* leaf, int32_t* n_leaf) {
+    if (!n_nodes || !n_leaf) return RM_ERR_ARG;
+    int rc = check_scene_arrays(s);
+    if (rc) return rc;
+    std::vector<PrimGeom> geom;
+    compute_object_geometry(*s, flags, geom);
+    std::vector<rm_bvh_node> nn;
+    std::vector<int32_t> lp;
+    build_bvh(geom, nn, lp);
+    if (nodes) {
+        if (*n_nodes < (int32_t)nn.size() || *n_leaf < (int32_t)lp.size() || (!leaf && !lp.empty())) return RM_ERR_ARG;
+        std::memcpy(nodes, nn.data(), nn.size() * sizeof(rm_bvh_node));
+        if (!lp.empty()) std::memcpy(leaf, lp.data(), lp.size() * sizeof(int32_t));
+    }
+    *n_nodes = (int32_t)nn.size();
+    *n_leaf = (int32_t)lp.size();
+    return RM_OK;
+}
+
+int rm_build_octree_scene(const rm_scene* s, unsigned flags, rm_octree_node* nodes, int32_t* n_nodes, int32_t* leaf, int32_t* n_leaf) {
+    if (!n_nodes || !n_leaf) return RM_ERR_ARG;
+    int rc = check_scene_arrays(s);
+    if (rc) return rc;
+    std::vector<PrimGeom> geom;
+    compute_object_geometry(*s, flags, geom);
+    std::vector<rm_octree_node> nn;
+    std::vector<int32_t> lp;
+    build_octree(geom, nn, lp);
+    if (nodes) {
+        if (*n_nodes < (int32_t)nn.size() || *n_leaf < (int32_t)lp.size() || (!leaf && !lp.empty())) return RM_ERR_ARG;
+        std::memcpy(nodes, nn.data(), nn.size() * sizeof(rm_octree_node));
+        if (!lp.empty()) std::memcpy(leaf, lp.data(), lp.size() * sizeof(int32_t));
+    }
+    *n_nodes = (int32_t)nn.size();
+    *n_leaf = (int32_t)lp.size();
+    return RM_OK;
+}
+
 int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     if (!c) return RM_ERR_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -349,8 +417,16 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     const int32_t n = s->n_prims;
     if (n < 0 || (n > 0 && (!s->type || !s->world_to_local || !s->params))) return fail(c, RM_ERR_ARG, "bad primitive arrays");
     if (s->accel_kind < RM_ACCEL_NONE || s->accel_kind > RM_ACCEL_BVH) return fail(c, RM_ERR_ARG, "bad accel_kind %d", s->accel_kind);
-    // Only sphere / box / torus with hard-min union are on the path: reject the rest loudly.
-    bool allTS = n > 0;
+    // Primitives: sphere / box / torus; scene objects: those, or operator trees over them.
+    // Anything else (mandelbulb, unknown kinds) is rejected loudly.
+    const bool tree = s->n_objects > 0;
+    {
+        std::string terr;
+        int trc = validate_tree(*s, terr);
+        if (trc) return fail(c, trc, "%s", terr.c_str());
+    }
+    const int32_t nObj = tree ? s->n_objects : n;  // Scene.objectSDFs.length
+    bool allTS = n > 0 && !tree;
     uint32_t hist[3] = {0, 0, 0};
     for (int32_t i = 0; i < n; ++i) {
         if (s->type[i] > RM_PRIM_TORUS)
@@ -359,7 +435,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
         const float* m = s->world_to_local + 16 * (size_t)i;
         for (int k = 0; k < 16; ++k)
             if (!std::isfinite(m[k])) return fail(c, RM_ERR_ARG, "primitive %d: non-finite transform", i);
-        if (!(c->flags & RM_F_VALIDATE_FP64) && !is_affine(m))
+        if (!(c->flags & RM_F_VALIDATE_FP64) && !tree && !is_affine(m))
             return fail(c, RM_ERR_UNSUPPORTED_PRIMITIVE, "primitive %d: projective world->local is only supported by the validation build", i);
         allTS = allTS && is_translation_sphere(s->type[i], m);
     }
@@ -368,7 +444,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     free_scene(c);
 
     DevScene ds{};
-    ds.n_prims = n;
+    ds.n_prims = nObj;
     ds.accel_kind = s->accel_kind;
     ds.prim_kind = allTS ? PK_TSPHERE : PK_GENERAL;
     std::memcpy(ds.type_hist, hist, sizeof(hist));
@@ -377,9 +453,38 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     if ((rc = upload(c, s->world_to_local, (size_t)n * 16, &ds.w2l))) return rc;
     if ((rc = upload(c, s->params, (size_t)n * 4, &ds.params))) return rc;
 
-    // fast-path packed records
+    if (tree) {
+        TreeProgram& tp = c->tree;
+        if (!compile_tree(*s, !(c->flags & RM_F_VALIDATE_FP64), tp))
+            return fail(c, RM_ERR_ARG, "an operator tree has more than 255 leaves of one primitive type");
+        ds.n_instrs = (int32_t)tp.instrs.size();
+        if ((rc = upload(c, tp.instrs.data(), tp.instrs.size(), &ds.instrs))) return rc;
+        if ((rc = upload(c, tp.obj_first.data(), tp.obj_first.size(), &ds.obj_first))) return rc;
+        if ((rc = upload(c, tp.mats.data(), tp.mats.size(), &ds.mats))) return rc;
+        if ((rc = upload(c, tp.obj_hist.data(), tp.obj_hist.size(), &ds.obj_hist))) return rc;
+        if ((rc = upload(c, tp.obj_flops.data(), tp.obj_flops.size(), &ds.obj_flops))) return rc;
+        for (int k = 0; k < 3; ++k) ds.type_hist[k] = 0;  // leaf evaluations of one pass over every object
+        for (uint32_t h : tp.obj_hist) {
+            ds.type_hist[0] += h & 255u;
+            ds.type_hist[1] += (h >> 8) & 255u;
+            ds.type_hist[2] += (h >> 16) & 255u;
+        }
+        for (uint32_t f : tp.obj_flops) ds.all_op_flops += f;
+        if (!tp.anims.empty()) {
+            std::vector<float> off;
+            eval_anim_offsets(tp, 0.0, off);
+            if ((rc = upload(c, off.data(), off.size(), &ds.anim))) return rc;
+            CU(c, cudaStreamSynchronize(c->stream));
+            c->d_anim = const_cast<float*>(ds.anim);
+            c->anim_time = 0.0;
+            c->anim_valid = true;
+        }
+    }
+
+    // fast-path packed records (plain primitive lists only)
     std::vector<float4> rec;
-    if (allTS) {
+    if (tree) {
+    } else if (allTS) {
         const int32_t nChunks = (n + 31) / 32;
         rec.resize((size_t)nChunks * 40);  // 40 float4 = 160 floats = tx[32] ty[32] tz[32] r[32] tt[32]
         float* f = reinterpret_cast<float*>(rec.data());
@@ -446,14 +551,14 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             else oct.assign((const rm_octree_node*)s->nodes, (const rm_octree_node*)s->nodes + s->n_nodes);
         } else {
             std::vector<PrimGeom> geom;
-            compute_prim_geometry(n, s->type, s->world_to_local, s->params, c->flags, geom);
+            compute_object_geometry(*s, c->flags, geom);
             if (s->accel_kind == RM_ACCEL_BVH) build_bvh(geom, bvh, leaf);
             else build_octree(geom, oct, leaf);
         }
         // structural validation (indices in range) so a bad host structure cannot fault the GPU
         const int32_t nn = (int32_t)(s->accel_kind == RM_ACCEL_BVH ? bvh.size() : oct.size());
         for (int32_t v : leaf)
-            if (v < 0 || v >= n) return fail(c, RM_ERR_ARG, "leaf primitive index %d out of range", v);
+            if (v < 0 || v >= nObj) return fail(c, RM_ERR_ARG, "leaf primitive index %d out of range", v);
         if (s->accel_kind == RM_ACCEL_BVH) {
             for (const rm_bvh_node& nd : bvh) {
                 if (nd.left >= nn || nd.right >= nn || nd.left < -1 || nd.right < -1) return fail(c, RM_ERR_ARG, "BVH child index out of range");
@@ -468,7 +573,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             }
         }
         ds.n_nodes = nn;
-        if (s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64)) {
+        if (s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) && !tree) {
             // fast path: locate leaf boxes through a uniform grid instead of descending the tree
             LeafGrid grid;
             build_leaf_grid(bvh, grid);

@@ -11,6 +11,7 @@
 // not share sources with oracle/.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -388,6 +389,279 @@ void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>
             if (lo < hi) th.emplace_back(work, lo, hi);
         }
         for (auto& t : th) t.join();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ operator trees
+namespace {
+struct NodeGeom {
+    float pos[3];   // getWorldPosition()
+    double radius;  // getLocalBoundingRadius()
+};
+double js_max(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? std::numeric_limits<double>::quiet_NaN() : std::max(a, b); }
+
+void leaf_geom(const rm_scene& s, int32_t i, bool lengthSqrt, NodeGeom& g) {
+    const float* m = s.world_to_local + 16 * (size_t)i;
+    float inv[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    mat4_invert(m, inv);
+    g.pos[0] = inv[12];
+    g.pos[1] = inv[13];
+    g.pos[2] = inv[14];
+    const double* q = s.params + 4 * (size_t)i;
+    if (s.type[i] == RM_PRIM_SPHERE) g.radius = q[0];
+    else if (s.type[i] == RM_PRIM_BOX) {
+        double hx = (double)f32(q[0]), hy = (double)f32(q[1]), hz = (double)f32(q[2]);
+        g.radius = lengthSqrt ? std::sqrt(hx * hx + hy * hy + hz * hz) : hypot3(hx, hy, hz);
+    } else g.radius = q[0] + q[1];
+}
+
+void node_geom(const rm_scene& s, int32_t ni, bool lengthSqrt, NodeGeom& g) {
+    const rm_op_node& nd = s.op_nodes[ni];
+    switch (nd.kind) {
+        case RM_NODE_PRIMITIVE: leaf_geom(s, nd.prim, lengthSqrt, g); break;
+        case RM_NODE_ROUND:  // round.ts:26-34
+            node_geom(s, nd.child[0], lengthSqrt, g);
+            g.radius = g.radius + nd.p[0];
+            break;
+        case RM_NODE_TWIST:               // twist.ts:38-46
+        case RM_NODE_SMOOTH_SUBTRACTION:  // smoothSubstraction.ts:36-44: prim1 only
+            node_geom(s, nd.child[0], lengthSqrt, g);
+            break;
+        case RM_NODE_REPETITION:  // repetition.ts:31-39
+            node_geom(s, nd.child[0], lengthSqrt, g);
+            g.radius = std::numeric_limits<double>::infinity();
+            break;
+        case RM_NODE_ANIMATED_TRANSLATE:  // animatedTranslate.ts:50-57
+            node_geom(s, nd.child[0], lengthSqrt, g);
+            g.radius = g.radius + nd.p[0];
+            break;
+        default: {  // smoothUnion.ts:37-59
+            NodeGeom a, b;
+            node_geom(s, nd.child[0], lengthSqrt, a);
+            node_geom(s, nd.child[1], lengthSqrt, b);
+            double dx = (double)b.pos[0] - (double)a.pos[0], dy = (double)b.pos[1] - (double)a.pos[1], dz = (double)b.pos[2] - (double)a.pos[2];
+            double centerDist = lengthSqrt ? std::sqrt(dx * dx + dy * dy + dz * dz) : hypot3(dx, dy, dz);  // vec3.distance
+            g.radius = js_max(a.radius, b.radius) + centerDist * 0.5;
+            for (int k = 0; k < 3; ++k) g.pos[k] = f32(((double)a.pos[k] + (double)b.pos[k]) / 2);
+            break;
+        }
+    }
+}
+
+// BoundingBox.fromPrimitive (boundingBox.ts:133-154) from (worldPos, localRadius, Primitive.transform)
+void padded_box(const NodeGeom& ng, const float* m, PrimGeom& g) {
+    float inv[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const bool ok = mat4_invert(m, inv);
+    const float* sm = ok ? inv : m;
+    double scaleX = hypot3(sm[0], sm[1], sm[2]), scaleY = hypot3(sm[4], sm[5], sm[6]), scaleZ = hypot3(sm[8], sm[9], sm[10]);
+    double maxScale = js_max(js_max(scaleX, scaleY), scaleZ);
+    double r = ng.radius * maxScale * 1.5;
+    for (int k = 0; k < 3; ++k) {
+        g.world[k] = ng.pos[k];
+        g.bmin[k] = f32((double)ng.pos[k] - r);
+        g.bmax[k] = f32((double)ng.pos[k] + r);
+    }
+}
+
+int check_node(const rm_scene& s, int32_t ni, int depth, std::vector<uint8_t>& onPath, std::string& err) {
+    char buf[160];
+    if (ni < 0 || ni >= s.n_op_nodes) {
+        snprintf(buf, sizeof(buf), "operator node index %d out of range [0,%d)", ni, s.n_op_nodes);
+        err = buf;
+        return RM_ERR_ARG;
+    }
+    if (depth > RM_MAX_TREE_DEPTH) {
+        snprintf(buf, sizeof(buf), "operator tree deeper than RM_MAX_TREE_DEPTH = %d", RM_MAX_TREE_DEPTH);
+        err = buf;
+        return RM_ERR_ARG;
+    }
+    if (onPath[(size_t)ni]) {
+        err = "operator nodes form a cycle";
+        return RM_ERR_ARG;
+    }
+    const rm_op_node& nd = s.op_nodes[ni];
+    if (nd.kind < RM_NODE_PRIMITIVE || nd.kind > RM_NODE_ANIMATED_TRANSLATE) {
+        snprintf(buf, sizeof(buf), "operator node %d has kind %d: not one of the supported SDF operators (no CPU fallback)", ni, nd.kind);
+        err = buf;
+        return RM_ERR_UNSUPPORTED_PRIMITIVE;
+    }
+    if (nd.kind == RM_NODE_PRIMITIVE) {
+        if (nd.prim < 0 || nd.prim >= s.n_prims) {
+            snprintf(buf, sizeof(buf), "operator node %d references primitive %d out of range [0,%d)", ni, nd.prim, s.n_prims);
+            err = buf;
+            return RM_ERR_ARG;
+        }
+        return RM_OK;
+    }
+    for (int k = 0; k < 16; ++k)
+        if (!std::isfinite(nd.transform[k])) {
+            snprintf(buf, sizeof(buf), "operator node %d: non-finite transform", ni);
+            err = buf;
+            return RM_ERR_ARG;
+        }
+    const int arity = (nd.kind == RM_NODE_SMOOTH_UNION || nd.kind == RM_NODE_SMOOTH_SUBTRACTION) ? 2 : 1;
+    onPath[(size_t)ni] = 1;
+    for (int k = 0; k < arity; ++k) {
+        int rc = check_node(s, nd.child[k], depth + 1, onPath, err);
+        if (rc) return rc;
+    }
+    onPath[(size_t)ni] = 0;
+    return RM_OK;
+}
+
+bool is_identity(const float* m) {
+    static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int k = 0; k < 16; ++k)
+        if (m[k] != I[k]) return false;
+    return true;
+}
+
+struct Compiler {
+    const rm_scene& s;
+    bool elide;
+    TreeProgram& out;
+    uint32_t hist[3] = {0, 0, 0};
+    uint32_t flops = 0;
+
+    void emit(int32_t op, int32_t a = 0, double c = 0.0, const float* v = nullptr) {
+        DevInstr in{};
+        in.op = op;
+        in.a = a;
+        in.c = c;
+        if (v) std::memcpy(in.v, v, 3 * sizeof(float));
+        out.instrs.push_back(in);
+    }
+    int xform(const float* m) {  // returns the number of points pushed (0 when elided)
+        if (elide && is_identity(m)) return 0;
+        const int32_t mi = (int32_t)(out.mats.size() / 16);
+        out.mats.insert(out.mats.end(), m, m + 16);
+        emit(I_XFORM, mi);
+        flops += 27;
+        return 1;
+    }
+    // `Primitive.sdf` prologue of an operator (primitive.ts:33-39) followed by its "back to world" step
+    // (round.ts:17-20 etc.): local = T p, world = inv(T) local.
+    int prologue(const rm_op_node& nd, bool backToWorld) {
+        int pushed = xform(nd.transform);
+        if (backToWorld) {
+            float inv[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // mat4.create(): untouched when singular
+            mat4_invert(nd.transform, inv);
+            pushed += xform(inv);
+        }
+        return pushed;
+    }
+    void node(int32_t ni) {
+        const rm_op_node& nd = s.op_nodes[ni];
+        int pushed = 0;
+        switch (nd.kind) {
+            case RM_NODE_PRIMITIVE:
+                emit(I_PRIM, nd.prim);
+                hist[s.type[nd.prim]]++;
+                return;
+            case RM_NODE_ROUND:
+                pushed = prologue(nd, true);
+                node(nd.child[0]);
+                if (pushed) emit(I_POP, pushed);
+                emit(I_SUBC, 0, nd.p[0]);
+                flops += 1;
+                return;
+            case RM_NODE_TWIST:
+                pushed = prologue(nd, true);
+                emit(I_TWIST, 0, nd.p[0]);
+                flops += 9;
+                node(nd.child[0]);
+                emit(I_POP, pushed + 1);
+                return;
+            case RM_NODE_REPETITION: {
+                pushed = prologue(nd, true);
+                const float sp[3] = {f32(nd.p[0]), f32(nd.p[1]), f32(nd.p[2])};
+                emit(I_REPEAT, 0, 0.0, sp);
+                flops += 12;
+                node(nd.child[0]);
+                emit(I_POP, pushed + 1);
+                return;
+            }
+            case RM_NODE_ANIMATED_TRANSLATE: {
+                pushed = prologue(nd, false);
+                AnimSlot a{};
+                std::memcpy(a.dir, nd.dir, sizeof(a.dir));
+                a.amplitude = nd.p[0];
+                a.speed = nd.p[1];
+                out.anims.push_back(a);
+                emit(I_SUBV, (int32_t)out.anims.size() - 1);
+                flops += 3;
+                node(nd.child[0]);
+                emit(I_POP, pushed + 1);
+                return;
+            }
+            default:
+                pushed = prologue(nd, true);
+                node(nd.child[0]);
+                node(nd.child[1]);
+                if (pushed) emit(I_POP, pushed);
+                emit(nd.kind == RM_NODE_SMOOTH_UNION ? I_SUNION : I_SSUB, 0, nd.p[0]);
+                flops += 10;
+                return;
+        }
+    }
+};
+}  // namespace
+
+int validate_tree(const rm_scene& s, std::string& err) {
+    if (s.n_objects < 0 || s.n_op_nodes < 0) {
+        err = "negative operator-tree counts";
+        return RM_ERR_ARG;
+    }
+    if (s.n_objects == 0) return RM_OK;
+    if (!s.op_nodes || !s.object_root || s.n_op_nodes == 0) {
+        err = "n_objects > 0 needs op_nodes and object_root";
+        return RM_ERR_ARG;
+    }
+    std::vector<uint8_t> onPath((size_t)s.n_op_nodes, 0);
+    for (int32_t i = 0; i < s.n_objects; ++i) {
+        int rc = check_node(s, s.object_root[i], 1, onPath, err);
+        if (rc) return rc;
+    }
+    return RM_OK;
+}
+
+void compute_object_geometry(const rm_scene& s, unsigned flags, std::vector<PrimGeom>& out) {
+    if (s.n_objects == 0) {
+        compute_prim_geometry(s.n_prims, s.type, s.world_to_local, s.params, flags, out);
+        return;
+    }
+    const bool lengthSqrt = (flags & RM_F_LENGTH_SQRT) != 0;
+    out.resize((size_t)s.n_objects);
+    for (int32_t i = 0; i < s.n_objects; ++i) {
+        const rm_op_node& root = s.op_nodes[s.object_root[i]];
+        NodeGeom ng;
+        node_geom(s, s.object_root[i], lengthSqrt, ng);
+        const float* m = (root.kind == RM_NODE_PRIMITIVE) ? s.world_to_local + 16 * (size_t)root.prim : root.transform;
+        padded_box(ng, m, out[(size_t)i]);
+    }
+}
+
+bool compile_tree(const rm_scene& s, bool elide_identity, TreeProgram& out) {
+    out = TreeProgram();
+    bool ok = true;
+    for (int32_t i = 0; i < s.n_objects; ++i) {
+        Compiler cc{s, elide_identity, out};
+        out.obj_first.push_back((int32_t)out.instrs.size());
+        cc.node(s.object_root[i]);
+        ok = ok && cc.hist[0] <= 255u && cc.hist[1] <= 255u && cc.hist[2] <= 255u;  // packed 8-bit leaf counts
+        out.obj_hist.push_back(std::min(cc.hist[0], 255u) | (std::min(cc.hist[1], 255u) << 8) | (std::min(cc.hist[2], 255u) << 16));
+        out.obj_flops.push_back(cc.flops);
+    }
+    out.obj_first.push_back((int32_t)out.instrs.size());
+    return ok;
+}
+
+void eval_anim_offsets(const TreeProgram& prog, double time, std::vector<float>& out4) {
+    out4.assign(prog.anims.size() * 4, 0.f);
+    for (size_t i = 0; i < prog.anims.size(); ++i) {
+        const AnimSlot& a = prog.anims[i];
+        const double offset = std::sin(time * a.speed) * a.amplitude;  // Math.sin (animatedTranslate.ts:36)
+        for (int k = 0; k < 3; ++k) out4[4 * i + k] = f32((double)a.dir[k] * offset);  // vec3.scale -> f32
     }
 }
 

@@ -63,8 +63,8 @@ enum Phase : int {
 // Primitive SDFs
 // ------------------------------------------------------------------------------------------
 
-// Exact model: Primitive.sdf (primitive.ts:33-39) = f32(transformMat4(p, M)) then localSdf.
-RM_DEV double prim_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt) {
+// Exact model: Primitive.sdf (primitive.ts:33-39) = f32(transformMat4(p, M)) then localSdf, for leaf primitive j.
+RM_DEV double leaf_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt) {
     const float* m = sc.w2l + 16 * (size_t)j;
     double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7];
     double m8 = m[8], m9 = m[9], m10 = m[10], m11 = m[11], m12 = m[12], m13 = m[13], m14 = m[14], m15 = m[15];
@@ -93,6 +93,94 @@ RM_DEV double prim_sdf_exact(const DevScene& sc, int j, double x, double y, doub
         double qy = ly;
         return sqrt(qx * qx + qy * qy) - prm[1];
     }
+}
+
+// Math.round: ties toward +Infinity, keeps -0 (V8 Float64Round).
+RM_DEV double js_round(double x) {
+    const double r = ceil(x);
+    return (r - 0.5 > x) ? r - 1.0 : r;
+}
+
+// Operator trees (src/util/primitive_operations/*.ts): scene object j's compiled program on the point / distance
+// stack machine described in rm_types.h.  Everything in JS-number arithmetic (fp64, f32 vector stores, unfused);
+// Math.sin / Math.cos are CUDA's double-precision routines (<= 1-2 ulp; the result is consumed through an f32
+// store, twist.ts:27-31).  Stack depths are bounded by the RM_MAX_TREE_DEPTH check at upload.
+static __device__ __noinline__ double object_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt) {
+    double px[kMaxPointStack], py[kMaxPointStack], pz[kMaxPointStack];
+    double ds[kMaxDistStack];
+    int sp = 0, dp = 0;
+    px[0] = x;
+    py[0] = y;
+    pz[0] = z;
+    ds[0] = 10.0;
+    const int end = sc.obj_first[j + 1];
+    for (int pc = sc.obj_first[j]; pc < end; ++pc) {
+        const DevInstr in = sc.instrs[pc];
+        const double X = px[sp], Y = py[sp], Z = pz[sp];
+        switch (in.op) {
+            case I_PRIM: ds[dp++] = leaf_sdf_exact(sc, in.a, X, Y, Z, length_sqrt); break;
+            case I_XFORM: {  // vec3.transformMat4 into a Float32Array
+                const float* m = sc.mats + 16 * (size_t)in.a;
+                double w = (double)m[3] * X + (double)m[7] * Y + (double)m[11] * Z + (double)m[15];
+                if (w == 0.0 || w != w) w = 1.0;
+                ++sp;
+                px[sp] = (double)f32r(((double)m[0] * X + (double)m[4] * Y + (double)m[8] * Z + (double)m[12]) / w);
+                py[sp] = (double)f32r(((double)m[1] * X + (double)m[5] * Y + (double)m[9] * Z + (double)m[13]) / w);
+                pz[sp] = (double)f32r(((double)m[2] * X + (double)m[6] * Y + (double)m[10] * Z + (double)m[14]) / w);
+                break;
+            }
+            case I_POP: sp -= in.a; break;
+            case I_TWIST: {  // twist.ts:22-33
+                const double k = in.c;
+                const double c = cos(k * Y), sn = sin(k * Y);
+                ++sp;
+                px[sp] = (double)f32r(c * X - sn * Z);
+                py[sp] = Y;
+                pz[sp] = (double)f32r(sn * X + c * Z);
+                break;
+            }
+            case I_REPEAT: {  // repetition.ts:21-26
+                const double s0 = (double)in.v[0], s1 = (double)in.v[1], s2 = (double)in.v[2];
+                ++sp;
+                px[sp] = (double)f32r(X - s0 * js_round(X / s0));
+                py[sp] = (double)f32r(Y - s1 * js_round(Y / s1));
+                pz[sp] = (double)f32r(Z - s2 * js_round(Z / s2));
+                break;
+            }
+            case I_SUBV: {  // animatedTranslate.ts:42-44
+                const float* o = sc.anim + 4 * (size_t)in.a;
+                ++sp;
+                px[sp] = (double)f32r(X - (double)o[0]);
+                py[sp] = (double)f32r(Y - (double)o[1]);
+                pz[sp] = (double)f32r(Z - (double)o[2]);
+                break;
+            }
+            case I_SUBC: ds[dp - 1] = ds[dp - 1] - in.c; break;  // round.ts:23
+            case I_SUNION: {                                     // smoothUnion.ts:26-34
+                const double d1 = ds[dp - 2], d2 = ds[dp - 1];
+                const double k = in.c * 4.0;
+                const double h = jsmax(k - fabs(d1 - d2), 0.0);
+                ds[dp - 2] = jsmin(d1, d2) - h * h * 0.25 / k;
+                --dp;
+                break;
+            }
+            default: {  // I_SSUB, smoothSubstraction.ts:25-33
+                const double d1 = ds[dp - 2], d2 = ds[dp - 1];
+                const double k = in.c * 4.0;
+                const double h = jsmax(k - fabs(d1 + d2), 0.0);
+                ds[dp - 2] = jsmax(d1, -d2) + h * h * 0.25 / k;
+                --dp;
+                break;
+            }
+        }
+    }
+    return ds[0];
+}
+
+// Scene object j (Scene.objectSDFs[j].sdf(p)): a primitive, or an operator tree over primitives.
+RM_DEV double prim_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt) {
+    if (sc.n_instrs > 0) return object_sdf_exact(sc, j, x, y, z, length_sqrt);
+    return leaf_sdf_exact(sc, j, x, y, z, length_sqrt);
 }
 
 // Fast model, general affine record: rows of the 3x4 world->local + (p0,p1,p2,type).
@@ -126,13 +214,34 @@ RM_DEV float prim_sdf_fast_tsphere(const float4* __restrict__ rec1, int j, float
     return NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - s.w;
 }
 
-// One primitive evaluation at the f32 sample point q; nSphere/nBox count evaluations by type.
+template <class NP>
+struct Ray;
+// Exact-build-only evaluation counters (the fast kernels derive the torus count and have no operator trees).
+template <bool kExact>
+struct EvalExtra {};
+template <>
+struct EvalExtra<true> {
+    unsigned nTorus, opFlops;
+};
+
+// One scene-object evaluation at the f32 sample point q; r.nSphere / r.nBox (/ r.ex) count primitive evaluations by type.
 template <class NP, int PK>
-RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], unsigned& nSphere, unsigned& nBox) {
+RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], Ray<NP>& r) {
+    unsigned& nSphere = r.nSphere;
+    unsigned& nBox = r.nBox;
     if constexpr (NP::kExact) {
-        int type = P.scene.type[j];
-        nSphere += (type == RM_PRIM_SPHERE);
-        nBox += (type == RM_PRIM_BOX);
+        if (P.scene.n_instrs > 0) {
+            const unsigned h = P.scene.obj_hist[j];
+            nSphere += h & 255u;
+            nBox += (h >> 8) & 255u;
+            r.ex.nTorus += (h >> 16) & 255u;
+            r.ex.opFlops += P.scene.obj_flops[j];
+        } else {
+            int type = P.scene.type[j];
+            nSphere += (type == RM_PRIM_SPHERE);
+            nBox += (type == RM_PRIM_BOX);
+            r.ex.nTorus += (type == RM_PRIM_TORUS);
+        }
         return prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt);
     } else if constexpr (PK == PK_TSPHERE) {
         nSphere += 1;
@@ -157,7 +266,7 @@ RM_DEV double prim_sdf_polish(const DevScene& sc, int j, const float q[3]) {
         const double lx = (double)__fadd_rn(q[0], s.x), ly = (double)__fadd_rn(q[1], s.y), lz = (double)__fadd_rn(q[2], s.z);
         return sqrt(lx * lx + ly * ly + lz * lz) - sc.params[4 * (size_t)j];
     } else {
-        return prim_sdf_exact(sc, j, (double)q[0], (double)q[1], (double)q[2], 1);
+        return leaf_sdf_exact(sc, j, (double)q[0], (double)q[1], (double)q[2], 1);
     }
 }
 
@@ -585,13 +694,13 @@ RM_DEV double scene_all_prims(const RenderParams& P, const float q[3], WarpStage
 // Candidate-list evaluation (octree leaf / BVH leaf): running (min, argmin) in the field model.
 template <class NP, int PK>
 RM_DEV void leaf_prims(const RenderParams& P, const int32_t* __restrict__ lp, int pc, const float q[3], double& distExact,
-                       float& distF32, int& argmin, unsigned& nSphere, unsigned& nBox) {
+                       float& distF32, int& argmin, Ray<NP>& r) {
     for (int k = 0; k < pc; ++k) {
         const int j = lp[k];
         if constexpr (NP::kExact) {
-            distExact = jsmin(prim_sdf<NP, PK>(P, j, q, nSphere, nBox), distExact);
+            distExact = jsmin(prim_sdf<NP, PK>(P, j, q, r), distExact);
         } else {
-            float d = (float)prim_sdf<NP, PK>(P, j, q, nSphere, nBox);
+            float d = (float)prim_sdf<NP, PK>(P, j, q, r);
             if (d < distF32) {
                 distF32 = d;
                 argmin = j;
@@ -649,7 +758,8 @@ struct Ray {
     double nd;                 // getNormal: d = scene distance at the hit position
     float n0, n1, n2;          // normal (f32 values)
     unsigned sdf, iters;       // un-wrapped counters
-    unsigned nSphere, nBox;    // evaluations by type (torus = sdf - nSphere - nBox)
+    unsigned nSphere, nBox;    // evaluations by type (fast kernels: torus = sdf - nSphere - nBox)
+    EvalExtra<NP::kExact> ex;   // exact kernels: explicit torus count + operator FLOPs
     int i;                     // march loop index
     int phase;
     int px, py;  // pixel (x, band-local y)
@@ -1017,7 +1127,7 @@ __global__ void shade_kernel(ShadeParams P) {
 // ------------------------------------------------------------------------------------------
 struct LaneStats {
     unsigned long long sum_sdf = 0, sum_iters = 0, sum_sdf_full = 0, sum_iters_full = 0;
-    unsigned long long ev_sphere = 0, ev_box = 0, ev_torus = 0, n_hit = 0;
+    unsigned long long ev_sphere = 0, ev_box = 0, ev_torus = 0, n_hit = 0, op_flops = 0;
     unsigned max_sdf = 0, min_sdf = 0xffffffffu, max_iters = 0, min_iters = 0xffffffffu;
 };
 
@@ -1313,6 +1423,10 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
             r.iters = 0;
             r.nSphere = 0;
             r.nBox = 0;
+            if constexpr (NP::kExact) {
+                r.ex.nTorus = 0;
+                r.ex.opFlops = 0;
+            }
             r.i = 0;
             r.done = false;
             r.cur = 0;
@@ -1409,7 +1523,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                     const rm_octree_node* nd = P.scene.oct + ni;
                     int pc = nd->prim_count;
                     if (pc > 0) {
-                        leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
+                        leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);
                         cnt = (unsigned)pc;
                         polish = true;
                     } else if (nd->is_empty) {
@@ -1430,7 +1544,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                             const rm_bvh_node* nd = nodes + P.scene.grid_leaves[P.scene.grid_cell_leaf[e]].x;
                             if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
                             const int pc = nd->prim_count;
-                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
+                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);
                             cnt += (unsigned)pc;
                         }
                     }
@@ -1445,7 +1559,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                         int left = nd->left, right = nd->right;
                         if (left < 0 && right < 0) {
                             int pc = nd->prim_count;
-                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r.nSphere, r.nBox);
+                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);
                             cnt += (unsigned)pc;
                         } else {
                             if (right >= 0 && sp < kBvhStack) stack[sp++] = right;  // popped after left
@@ -1473,6 +1587,10 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                     cnt = (unsigned)P.scene.n_prims;
                     r.nSphere += P.scene.type_hist[0];
                     r.nBox += P.scene.type_hist[1];
+                    if constexpr (NP::kExact) {
+                        r.ex.nTorus += P.scene.type_hist[2];
+                        r.ex.opFlops += P.scene.all_op_flops;
+                    }
                 }
             }
         } else {
@@ -1651,7 +1769,12 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
             st.sum_iters_full += r.iters;
             st.ev_sphere += r.nSphere;
             st.ev_box += r.nBox;
-            st.ev_torus += r.sdf - r.nSphere - r.nBox;
+            if constexpr (NP::kExact) {
+                st.ev_torus += r.ex.nTorus;
+                st.op_flops += r.ex.opFlops;
+            } else {
+                st.ev_torus += r.sdf - r.nSphere - r.nBox;
+            }
             st.n_hit += (r.depth < MAX_DIST) ? 1u : 0u;
             st.max_sdf = max(st.max_sdf, sdf16);
             st.min_sdf = min(st.min_sdf, sdf16);
@@ -1696,6 +1819,8 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
     unsigned long long s2 = warp_sum_u64(st.sum_sdf_full), s3 = warp_sum_u64(st.sum_iters_full);
     unsigned long long s4 = warp_sum_u64(st.ev_sphere), s5 = warp_sum_u64(st.ev_box), s6 = warp_sum_u64(st.ev_torus);
     unsigned long long s7 = warp_sum_u64(st.n_hit);
+    unsigned long long s8 = 0;
+    if constexpr (NP::kExact) s8 = warp_sum_u64(st.op_flops);
     unsigned mx0 = __reduce_max_sync(kFull, st.max_sdf), mn0 = __reduce_min_sync(kFull, st.min_sdf);
     unsigned mx1 = __reduce_max_sync(kFull, st.max_iters), mn1 = __reduce_min_sync(kFull, st.min_iters);
     if (lane == 0) {
@@ -1708,6 +1833,9 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
         atomicAdd(&g->evals_box, s5);
         atomicAdd(&g->evals_torus, s6);
         atomicAdd(&g->n_hit, s7);
+        if constexpr (NP::kExact) {
+            if (s8) atomicAdd(&g->op_flops, s8);
+        }
         atomicMax(&g->max_sdf, mx0);
         atomicMin(&g->min_sdf, mn0);
         atomicMax(&g->max_iters, mx1);

@@ -3,7 +3,10 @@
 #include <cstdint>
 #include <vector>
 
+#include <string>
+
 #include "../../include/rm.h"
+#include "rm_types.h"
 
 namespace rm {
 
@@ -15,6 +18,32 @@ struct PrimGeom {
 
 void compute_prim_geometry(int32_t n, const uint8_t* type, const float* w2l, const double* params, unsigned flags,
                            std::vector<PrimGeom>& out);
+// Scene objects of an rm_scene: the primitives themselves, or operator trees over them (ABI v2).
+// Geometry follows the operator overrides of getWorldPosition / getLocalBoundingRadius and uses the root
+// node's own transform for BoundingBox.fromPrimitive's scale estimate.
+void compute_object_geometry(const rm_scene& s, unsigned flags, std::vector<PrimGeom>& out);
+// Structural check of the node arrays (indices, kinds, arity, depth <= RM_MAX_TREE_DEPTH, no sharing cycles).
+// Returns RM_OK or an rm_status with a message.
+int validate_tree(const rm_scene& s, std::string& err);
+
+// One AnimatedTranslate node: offsetVec(time) = f32(direction * (sin(time * speed) * amplitude))  (animatedTranslate.ts:35-40)
+struct AnimSlot {
+    float dir[3];
+    double amplitude, speed;
+};
+struct TreeProgram {
+    std::vector<DevInstr> instrs;
+    std::vector<int32_t> obj_first;   // [n_objects + 1]
+    std::vector<float> mats;          // 16 floats per XFORM operand
+    std::vector<AnimSlot> anims;
+    std::vector<uint32_t> obj_hist, obj_flops;
+};
+// elide_identity: drop XFORM instructions whose matrix is exactly the identity (the smooth operators' transform):
+// f32(I * p) == p for every finite f32-valued p up to the sign of zero, which no consumer can observe.
+// Returns false when one object has more than 255 leaves of one primitive type.
+bool compile_tree(const rm_scene& s, bool elide_identity, TreeProgram& out);
+void eval_anim_offsets(const TreeProgram& prog, double time, std::vector<float>& out4);
+
 void build_bvh(const std::vector<PrimGeom>& geom, std::vector<rm_bvh_node>& nodes, std::vector<int32_t>& leafPrims);
 void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>& nodes, std::vector<int32_t>& leafPrims);
 

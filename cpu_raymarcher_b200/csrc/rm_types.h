@@ -1,6 +1,7 @@
 // rm_types.h — structures shared between the host side of librm_b200.so and its sm_100a kernels.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>  // float4 / uint3 (CUDA toolkit header, host-safe)
 
 #include "../../include/rm.h"
 
@@ -18,6 +19,26 @@ enum PrimKind {
     PK_GENERAL = 0,  // any mix of sphere/box/torus with a general affine world->local
     PK_TSPHERE = 1   // every primitive is a sphere whose world->local is a pure translation
 };
+
+// Operator trees (src/util/primitive_operations/*.ts) are compiled at upload into one linear program per scene
+// object for a small stack machine: sample points only flow down the tree (point stack), distances only flow up
+// (distance stack), so `Primitive.sdf` recursion becomes a straight instruction sequence.
+//   Round(c, r)       : XFORM T, XFORM inv(T), <c>, POP 2, SUBC r           (round.ts:15-24)
+//   Twist(c, k)       : XFORM T, XFORM inv(T), TWIST k, <c>, POP 3          (twist.ts:14-36)
+//   Repetition(c, s)  : XFORM T, XFORM inv(T), REPEAT s, <c>, POP 3         (repetition.ts:14-29)
+//   AnimatedTranslate : XFORM T, SUBV offset(time), <c>, POP 2              (animatedTranslate.ts:34-48)
+//   SmoothUnion(a, b) : XFORM T, XFORM inv(T), <a>, <b>, POP 2, SUNION k    (smoothUnion.ts:18-35)
+//   SmoothSubtraction : ... SSUB k                                          (smoothSubstraction.ts:17-34)
+//   leaf primitive    : PRIM i  (Primitive.sdf of leaf i at the top point)
+enum InstrOp : int32_t { I_PRIM = 0, I_XFORM, I_POP, I_TWIST, I_REPEAT, I_SUBV, I_SUBC, I_SUNION, I_SSUB };
+struct DevInstr {
+    int32_t op;
+    int32_t a;   // PRIM: leaf index | XFORM: matrix index | POP: count | SUBV: animation slot
+    double c;    // TWIST: amount | SUBC: radius | SUNION / SSUB: smoothness
+    float v[4];  // REPEAT: spacing
+};
+constexpr int kMaxPointStack = 3 * RM_MAX_TREE_DEPTH + 2;
+constexpr int kMaxDistStack = RM_MAX_TREE_DEPTH + 2;
 
 // Device-resident scene (all pointers are device pointers).
 struct DevScene {
@@ -44,6 +65,15 @@ struct DevScene {
     const rm_octree_node* oct;
     const int32_t* leaf_prims;
     uint32_t type_hist[3];  // number of sphere / box / torus primitives in the scene
+    // operator trees (n_instrs > 0): n_prims counts scene OBJECTS; type / w2l / params hold the trees' leaves
+    int32_t n_instrs;
+    const DevInstr* instrs;
+    const int32_t* obj_first;    // [n_prims + 1] program range of each object
+    const float* mats;           // [16 * n_mats] column-major mat4 operands of XFORM
+    const float* anim;           // [4 * n_anim] AnimatedTranslate offset vectors of the current frame (f32)
+    const uint32_t* obj_hist;    // per object: leaf evaluations per call, sphere | box << 8 | torus << 16
+    const uint32_t* obj_flops;   // per object: FLOPs of its operator instructions per call
+    uint32_t all_op_flops;       // sum of obj_flops (one pass over every object)
     // uniform grid over the BVH leaf boxes (fast path; see rm_host.h LeafGrid)
     const uint3* grid_leaves;         // per leaf ordinal: x = node index, y = packed lo cell, z = packed hi cell
     const uint32_t* grid_cell_start;  // [nx*ny*nz + 1]
@@ -58,6 +88,7 @@ struct DevStats {
     unsigned long long sum_sdf_full, sum_iters_full;  // un-wrapped
     unsigned long long evals_sphere, evals_box, evals_torus;
     unsigned long long n_hit;
+    unsigned long long op_flops;  // operator-tree scenes: FLOPs of the operator instructions executed
     unsigned int max_sdf, min_sdf, max_iters, min_iters;
     unsigned int queue;  // atomic tile counter of the persistent-CTA work queue
     unsigned long long t_total, t_search, t_barrier, t_stuck;  // RM_PHASE_TIMING builds: warp-cycles by phase

@@ -66,6 +66,57 @@ def build_octree(types, w2l, params, flags: int = 0):
     return nodes, nn.value, leaf[: nl.value]
 
 
+# numpy view of rm_op_node (include/rm.h)
+OP_NODE_DTYPE = np.dtype([("kind", np.int32), ("child", np.int32, 2), ("prim", np.int32), ("p", np.float64, 4),
+                          ("dir", np.float32, 4), ("transform", np.float32, 16)])
+assert OP_NODE_DTYPE.itemsize == C.sizeof(_lib.OpNode) == 128
+
+
+def _fill_scene(types, w2l, params, op_nodes=None, object_root=None):
+    """rm_scene over numpy arrays; returns (struct, keep-alive tuple)."""
+    types = np.ascontiguousarray(types, np.uint8)
+    w2l = np.ascontiguousarray(w2l, np.float32)
+    params = np.ascontiguousarray(params, np.float64)
+    s = _lib.Scene()
+    s.n_prims = len(types)
+    s.type, s.world_to_local, s.params = _ptr(types), _ptr(w2l), _ptr(params)
+    keep = [types, w2l, params]
+    if object_root is not None and len(object_root) > 0:
+        op_nodes = np.ascontiguousarray(op_nodes, OP_NODE_DTYPE)
+        object_root = np.ascontiguousarray(object_root, np.int32)
+        s.n_op_nodes, s.op_nodes = len(op_nodes), _ptr(op_nodes)
+        s.n_objects, s.object_root = len(object_root), _ptr(object_root)
+        keep += [op_nodes, object_root]
+    return s, keep
+
+
+def _build_scene(fn_name, node_type, types, w2l, params, op_nodes, object_root, flags):
+    L = _lib.lib()
+    s, keep = _fill_scene(types, w2l, params, op_nodes, object_root)
+    fn = getattr(L, fn_name)
+    nn, nl = C.c_int32(0), C.c_int32(0)
+    rc = fn(C.byref(s), flags, None, C.byref(nn), None, C.byref(nl))
+    if rc:
+        raise RmError(rc, fn_name)
+    nodes = (node_type * max(nn.value, 1))()
+    leaf = np.zeros(max(nl.value, 1), np.int32)
+    rc = fn(C.byref(s), flags, nodes, C.byref(nn), _ptr(leaf), C.byref(nl))
+    if rc:
+        raise RmError(rc, fn_name)
+    del keep
+    return nodes, nn.value, leaf[: nl.value]
+
+
+def build_bvh_scene(types, w2l, params, op_nodes=None, object_root=None, flags: int = 0):
+    """rm_build_bvh_scene: the BVH over scene OBJECTS (primitives or operator trees).  No GPU needed."""
+    return _build_scene("rm_build_bvh_scene", _lib.BvhNode, types, w2l, params, op_nodes, object_root, flags)
+
+
+def build_octree_scene(types, w2l, params, op_nodes=None, object_root=None, flags: int = 0):
+    """rm_build_octree_scene: the octree over scene OBJECTS (primitives or operator trees)."""
+    return _build_scene("rm_build_octree_scene", _lib.OctreeNode, types, w2l, params, op_nodes, object_root, flags)
+
+
 class Context:
     def __init__(self, device: int = 0, validate_fp64: bool = False, length_sqrt: bool = False):
         self._L = _lib.lib()
@@ -92,13 +143,12 @@ class Context:
             raise RmError(rc, (self._L.rm_last_error(self._h) or b"").decode())
 
     # ---- scene ----
-    def upload_scene(self, types, w2l, params, accel="None", nodes=None, n_nodes=0, leaf=None):
-        types = np.ascontiguousarray(types, np.uint8)
-        w2l = np.ascontiguousarray(w2l, np.float32)
-        params = np.ascontiguousarray(params, np.float64)
-        s = _lib.Scene()
-        s.n_prims = len(types)
-        s.type, s.world_to_local, s.params = _ptr(types), _ptr(w2l), _ptr(params)
+    def upload_scene(self, types, w2l, params, accel="None", nodes=None, n_nodes=0, leaf=None, op_nodes=None,
+                     object_root=None):
+        """rm_upload_scene.  `op_nodes` / `object_root` (OP_NODE_DTYPE array, root indices) describe operator
+        trees over the primitives; without them every primitive is a scene object."""
+        s, keep = _fill_scene(types, w2l, params, op_nodes, object_root)
+        types = keep[0]
         s.accel_kind = ACCELS[accel] if isinstance(accel, str) else int(accel)
         if nodes is not None:
             leaf = np.ascontiguousarray(leaf, np.int32)
@@ -107,6 +157,7 @@ class Context:
             s.n_leaf_prims = len(leaf)
             s.leaf_prim_index = _ptr(leaf)
         self._check(self._L.rm_upload_scene(self._h, C.byref(s)))
+        del keep
         self.n_prims = len(types)
 
     # ---- render ----

@@ -1,7 +1,7 @@
-"""Scene presets — host-side mirror of src/util/sceneManager.ts restricted to the hot path's
-primitives (sphere / box / torus, hard-min union): presets 0-5 and 7-9.  Presets built from SDF
-operator trees or the mandelbulb (6, 10-18) are outside the path and raise
-UnsupportedPreset — there is no CPU fallback to route them to."""
+"""Scene presets — host-side mirror of src/util/sceneManager.ts: sphere / box / torus primitives, the six SDF
+operators of src/util/primitive_operations/ (Round, Twist, SmoothUnion, SmoothSubtraction, Repetition,
+AnimatedTranslate) and presets 0-12, 14-18.  Preset 13 (Mandelbulb) is outside the path
+and raises UnsupportedPreset — there is no CPU fallback to route it to."""
 from __future__ import annotations
 
 import math
@@ -18,7 +18,14 @@ PRESET_NAMES = [
     "Sphere and Cube", "Pyramid of Boxes", "Smooth Union", "Smooth Subtraction", "Smooth Union [A]", "Mandelbulb [A]",
     "Twisted Torus", "Infinite Spheres", "Screw", "Chicken", "67",
 ]
-SUPPORTED_PRESETS = (0, 1, 2, 3, 4, 5, 7, 8, 9)
+SUPPORTED_PRESETS = (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18)
+OPERATOR_PRESETS = (6, 10, 11, 12, 14, 15, 16, 17, 18)
+
+# numpy view of rm_op_node (include/rm.h)
+OP_NODE_DTYPE = np.dtype([("kind", np.int32), ("child", np.int32, 2), ("prim", np.int32), ("p", np.float64, 4),
+                          ("dir", np.float32, 4), ("transform", np.float32, 16)])
+NODE_KINDS = {"primitive": 0, "round": 1, "twist": 2, "smooth-union": 3, "smooth-subtraction": 4, "repetition": 5,
+              "animated-translate": 6}
 
 
 class UnsupportedPreset(ValueError):
@@ -31,9 +38,16 @@ class PrimitiveList:
     type: list = field(default_factory=list)
     world_to_local: list = field(default_factory=list)
     params: list = field(default_factory=list)
+    # operator trees (rm_scene.op_nodes / object_root); None = every primitive is a scene object
+    op_nodes: np.ndarray | None = None
+    object_root: np.ndarray | None = None
 
     def __len__(self):
         return len(self.type)
+
+    @property
+    def n_objects(self) -> int:
+        return len(self.object_root) if self.object_root is not None else len(self.type)
 
     def arrays(self):
         n = len(self.type)
@@ -71,8 +85,136 @@ def add_torus(pl: PrimitiveList, x, y, z, radius, rotation=None):  # sceneManage
     pl.params.append([float(radius), float(radius) / 4, 0.0, 0.0])
 
 
+# ---- operator trees: one Node per reference Primitive object --------------------------------------------
+@dataclass
+class Node:
+    kind: str                 # key of NODE_KINDS
+    transform: list           # Primitive.transform (primitive.ts:10)
+    children: tuple = ()
+    type: int = -1            # leaves: SPHERE / BOX / TORUS
+    params: tuple = (0.0, 0.0, 0.0, 0.0)
+    p: tuple = (0.0, 0.0, 0.0, 0.0)
+    dir: tuple = (0.0, 0.0, 0.0)
+
+
+def create_sphere(x, y, z, radius, rotation=None) -> Node:  # sceneManager.ts:39-41
+    return Node("primitive", get_transform(x, y, z, rotation), type=SPHERE, params=(float(radius), 0.0, 0.0, 0.0))
+
+
+def create_box(x, y, z, half_size, rotation=None) -> Node:  # sceneManager.ts:43-45
+    return Node("primitive", get_transform(x, y, z, rotation), type=BOX,
+                params=(gm.f32(half_size[0]), gm.f32(half_size[1]), gm.f32(half_size[2]), 0.0))
+
+
+def create_torus(x, y, z, radius, rotation=None) -> Node:  # sceneManager.ts:47-49
+    return Node("primitive", get_transform(x, y, z, rotation), type=TORUS, params=(float(radius), float(radius) / 4, 0.0, 0.0))
+
+
+def create_smooth_union(prim1: Node, prim2: Node, k: float) -> Node:  # smoothUnion.ts:9-15: super(mat4.create())
+    return Node("smooth-union", gm.mat4_create(), (prim1, prim2), p=(float(k), 0.0, 0.0, 0.0))
+
+
+def create_smooth_subtract(prim1: Node, prim2: Node, k: float) -> Node:  # smoothSubstraction.ts:9-14
+    return Node("smooth-subtraction", gm.mat4_create(), (prim1, prim2), p=(float(k), 0.0, 0.0, 0.0))
+
+
+def create_twist(prim: Node, twist_amount: float = 10.0) -> Node:  # twist.ts:8-12: super(primitive.transform)
+    return Node("twist", prim.transform, (prim,), p=(float(twist_amount), 0.0, 0.0, 0.0))
+
+
+def create_round(prim: Node, radius: float) -> Node:  # round.ts:8-12
+    return Node("round", prim.transform, (prim,), p=(float(radius), 0.0, 0.0, 0.0))
+
+
+def create_repetition(prim: Node, spacing) -> Node:  # repetition.ts:8-12 (spacing is a vec3: f32)
+    return Node("repetition", prim.transform, (prim,), p=(gm.f32(spacing[0]), gm.f32(spacing[1]), gm.f32(spacing[2]), 0.0))
+
+
+def create_animated_translate(prim: Node, direction=(1, 0, 0), amplitude: float = 2.0, speed: float = 0.5) -> Node:
+    """animatedTranslate.ts:15-28: direction = vec3.normalize(direction) (double math, f32 stores)."""
+    x, y, z = (gm.f32(direction[0]), gm.f32(direction[1]), gm.f32(direction[2]))
+    ln = x * x + y * y + z * z
+    if ln > 0:
+        ln = 1 / math.sqrt(ln)
+    return Node("animated-translate", prim.transform, (prim,), p=(float(amplitude), float(speed), 0.0, 0.0),
+                dir=(gm.f32(x * ln), gm.f32(y * ln), gm.f32(z * ln)))
+
+
+def flatten(objects) -> PrimitiveList:
+    """Scene.objectSDFs -> the arrays of rm_scene.  Nodes are laid out in pre-order per object and leaves are
+    numbered in encounter order.  A list of plain primitives needs no node array."""
+    pl = PrimitiveList()
+    nodes = []
+
+    def visit(n: Node) -> int:
+        me = len(nodes)
+        rec = dict(kind=NODE_KINDS[n.kind], child=[-1, -1], prim=-1, p=list(n.p), dir=list(n.dir) + [0.0],
+                   transform=list(n.transform))
+        nodes.append(rec)
+        if n.kind == "primitive":
+            rec["prim"] = len(pl.type)
+            pl.type.append(n.type)
+            pl.world_to_local.append(list(n.transform))
+            pl.params.append(list(n.params))
+            rec["p"] = [0.0] * 4
+        else:
+            for k, c in enumerate(n.children):
+                rec["child"][k] = visit(c)
+        return me
+
+    roots = [visit(o) for o in objects]
+    if any(o.kind != "primitive" for o in objects):
+        arr = np.zeros(len(nodes), OP_NODE_DTYPE)
+        for i, rec in enumerate(nodes):
+            arr[i] = (rec["kind"], rec["child"], rec["prim"], rec["p"], rec["dir"], rec["transform"])
+        pl.op_nodes = arr
+        pl.object_root = np.array(roots, np.int32)
+    return pl
+
+
+_CHICKEN_BOXES = ((0, 0, 0, 0.6, 0.6, 0.8), (0, -0.2, 0, 0.8, 0.4, 0.6), (0, -0.8, 0.8, 0.4, 0.6, 0.3),
+                  (0, -0.8, 1.2, 0.4, 0.2, 0.2), (0, -0.4, 1.0, 0.2, 0.2, 0.2), (0.3, 1, 0, 0.1, 0.6, 0.01),
+                  (-0.3, 1, 0, 0.1, 0.6, 0.01), (0, 1.6, 0.2, 0.6, 0.01, 0.2), (0.3, 1.6, 0.5, 0.1, 0.01, 0.1),
+                  (-0.3, 1.6, 0.5, 0.1, 0.01, 0.1))
+
+
+def _operator_preset(index: int):
+    """sceneManager.ts:177-186, 209-246, 254-356."""
+    if index == 6:
+        return [create_round(create_box(0, 0, 0, (0.4, 0.4, 0.4)), 0.3)]
+    if index == 10:
+        return [create_smooth_union(create_sphere(0, 0, 0, 0.5), create_box(0, 0.5, 0, (1, 0.2, 1)), 0.2)]
+    if index == 11:
+        return [create_smooth_subtract(create_round(create_box(0, 0, 0, (1, 1, 1), (0, math.pi / 4, 0)), 0.1),
+                                       create_sphere(0, 0, 0, 0.9), 0.2)]
+    if index == 12:
+        return [create_smooth_union(create_animated_translate(create_sphere(0, 0, 0, 1), (1, 0, 0), 3.0, 0.005),
+                                    create_sphere(0, 0, 0, 1), 0.2)]
+    if index == 14:
+        return [create_twist(create_torus(0, 0, 0, 1.3, (-math.pi / 2, 0, 0)), 3)]
+    if index == 15:
+        return [create_repetition(create_sphere(0, 0, 0, 0.3), (1.5, 1.5, 1.5))]
+    if index == 16:
+        return [create_round(create_twist(create_box(0, 0, 0, (0.4, 1.5, 0.4)), 4.0), 0.1)]
+    if index == 17:
+        acc = create_box(*_CHICKEN_BOXES[0][:3], _CHICKEN_BOXES[0][3:])
+        for b in _CHICKEN_BOXES[1:]:
+            acc = create_smooth_union(acc, create_box(*b[:3], b[3:]), 0.0001)
+        return [acc]
+    if index == 18:
+        return [
+            create_smooth_union(create_round(create_box(-1.25, -0.8, 0, (0.05, 0.7, 0.05), (0, 0, math.pi / 5)), 0.20),
+                                create_round(create_torus(-1.25, 0.5, 0, 0.8, (-math.pi / 2, 0, 0)), 0.05), 0.0001),
+            create_smooth_union(create_round(create_box(1.35, 0, 0, (0.05, 1.5, 0.05), (0, 0, math.pi / 7)), 0.20),
+                                create_round(create_box(1.25, -1.4, 0, (0.05, 0.8, 0.05), (0, 0, math.pi / 2)), 0.20), 0.0001),
+        ]
+    raise IndexError(index)
+
+
 def get_preset(index: int) -> PrimitiveList:
-    """SceneManager.getPreset(index).objects (sceneManager.ts:102-207,359-361)."""
+    """SceneManager.getPreset(index).objects (sceneManager.ts:102-356,359-361)."""
+    if index in OPERATOR_PRESETS:
+        return flatten(_operator_preset(index))
     pl = PrimitiveList()
     if index == 0:
         add_sphere(pl, 0, 0, 0, 1.5)
@@ -107,8 +249,8 @@ def get_preset(index: int) -> PrimitiveList:
         add_box(pl, 0, 0, 0, (0.6, 0.25, 0.6))
         add_box(pl, 0, -0.5, 0, (0.3, 0.25, 0.3))
     elif 0 <= index < len(PRESET_NAMES):
-        raise UnsupportedPreset(f"preset {index} ({PRESET_NAMES[index]!r}) uses SDF operators / mandelbulb, which are "
-                                "outside the B200 hot path (sphere/box/torus unions only)")
+        raise UnsupportedPreset(f"preset {index} ({PRESET_NAMES[index]!r}) is the Mandelbulb fractal, which is outside the "
+                                "B200 hot path (sphere/box/torus primitives and the six SDF operators)")
     else:
         raise IndexError(index)
     return pl

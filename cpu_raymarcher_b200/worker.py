@@ -33,7 +33,8 @@ class RaymarchWorker:
             else:
                 sc.load_preset(preset_index)
             t, m, q = sc.primitives.arrays()
-            self.ctx.upload_scene(t, m, q, accel)  # rm_upload_scene builds the BVH / octree natively
+            # rm_upload_scene compiles operator trees and builds the BVH / octree natively
+            self.ctx.upload_scene(t, m, q, accel, op_nodes=sc.primitives.op_nodes, object_root=sc.primitives.object_root)
             self.scene = sc
             self._scene_key = key
         return self.scene

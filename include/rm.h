@@ -26,14 +26,14 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 1
+#define RM_ABI_VERSION 2 /* v2: operator trees (rm_op_node, rm_scene.n_objects...), rm_build_*_scene, rm_stats_t.operator_flops */
 
 typedef struct rm_ctx rm_ctx; /* opaque: one CUDA device, its stream, device-resident scene + frame buffers */
 
 typedef enum rm_status {
     RM_OK = 0,
     RM_ERR_ARG = -1,                   /* null pointer, bad size, bad enum */
-    RM_ERR_UNSUPPORTED_PRIMITIVE = -2, /* operator trees / mandelbulb (reference components outside the path) */
+    RM_ERR_UNSUPPORTED_PRIMITIVE = -2, /* mandelbulb or unknown primitive / operator kinds (outside the path) */
     RM_ERR_CUDA = -3,                  /* no device, launch or copy failure (message in rm_last_error) */
     RM_ERR_STATE = -4,                 /* e.g. rm_render before rm_upload_scene */
     RM_ERR_NOMEM = -5
@@ -45,6 +45,29 @@ typedef enum rm_status {
 
 /* src/util/primitives/{sphere,box,torus}.ts */
 typedef enum rm_prim_type { RM_PRIM_SPHERE = 0, RM_PRIM_BOX = 1, RM_PRIM_TORUS = 2 } rm_prim_type;
+/* SDF operators (the classes under src/util/primitive_operations/).  A scene object is either a primitive or a tree of these
+ * over primitives; trees are passed as a flat node array (any order, children referenced by index). */
+typedef enum rm_node_kind {
+    RM_NODE_PRIMITIVE = 0,          /* leaf: rm_op_node.prim indexes the scene's primitive arrays           */
+    RM_NODE_ROUND = 1,              /* round.ts:15-24              p[0] = radius                            */
+    RM_NODE_TWIST = 2,              /* twist.ts:14-36              p[0] = twistAmount                       */
+    RM_NODE_SMOOTH_UNION = 3,       /* smoothUnion.ts:18-35        p[0] = smoothness, children prim1, prim2 */
+    RM_NODE_SMOOTH_SUBTRACTION = 4, /* smoothSubstraction.ts:17-34 p[0] = smoothness, children prim1, prim2 */
+    RM_NODE_REPETITION = 5,         /* repetition.ts:14-29         p[0..2] = spacing (the vec3's f32 values) */
+    RM_NODE_ANIMATED_TRANSLATE = 6  /* animatedTranslate.ts:34-48  p[0] = amplitude, p[1] = speed, dir      */
+} rm_node_kind;
+#define RM_MAX_TREE_DEPTH 16 /* deeper operator nesting is rejected with RM_ERR_ARG */
+
+typedef struct rm_op_node {
+    int32_t kind;        /* rm_node_kind */
+    int32_t child[2];    /* node indices of primitive / prim1 and prim2; -1 = none */
+    int32_t prim;        /* RM_NODE_PRIMITIVE only, else -1 */
+    double p[4];         /* see rm_node_kind */
+    float dir[4];        /* ANIMATED_TRANSLATE: this.direction as stored (already normalised, f32); [3] unused */
+    float transform[16]; /* the node's own Primitive.transform (primitive.ts:10): the wrapped primitive's for
+                            Round/Twist/Repetition/AnimatedTranslate, identity for the smooth operators; ignored for leaves */
+} rm_op_node; /* 128 bytes */
+
 /* Scene.accelerationStructure: "None" | "Octree" | "BVH"  (src/util/scene.ts:20,32-36) */
 typedef enum rm_accel_kind { RM_ACCEL_NONE = 0, RM_ACCEL_OCTREE = 1, RM_ACCEL_BVH = 2 } rm_accel_kind;
 /* Job.algorithm (raymarchWorker.ts:49-68); unknown strings map to the sphere tracer on the host side */
@@ -99,6 +122,13 @@ typedef struct rm_scene {
     const void* nodes; /* rm_bvh_node[n_nodes] or rm_octree_node[n_nodes] */
     int32_t n_leaf_prims;
     const int32_t* leaf_prim_index;
+    /* Operator trees (ABI v2).  n_objects == 0: Scene.objectSDFs = the n_prims primitives, in order.
+     * n_objects > 0: Scene.objectSDFs[i] = the tree rooted at op_nodes[object_root[i]]; the primitive arrays above
+     * then hold the trees' leaves, and acceleration-structure leaf lists index OBJECTS. */
+    int32_t n_op_nodes;
+    const rm_op_node* op_nodes;
+    int32_t n_objects;
+    const int32_t* object_root;
 } rm_scene;
 
 /* One frame-band request = one worker Job (raymarchWorker.ts:10-22).  The host evaluates the camera
@@ -107,7 +137,7 @@ typedef struct rm_scene {
 typedef struct rm_request {
     int32_t width, height;  /* full frame size */
     int32_t y_start, y_end; /* rows of this band; outputs are tile-local ((y-y_start)*width + x) */
-    double time;            /* Job.time; unused by sphere/box/torus (primitive.ts:42-44) */
+    double time;            /* Job.time -> Scene.updateTime (raymarcher.ts:59): drives AnimatedTranslate */
     float rot3[9];          /* column-major mat3 */
     float origin[3];
     int32_t algorithm;       /* rm_algorithm */
@@ -146,6 +176,7 @@ typedef struct rm_stats_t {
     uint64_t sum_sdf_full, sum_iters_full;
     uint64_t evals_by_type[3]; /* un-wrapped primitive evaluations split sphere/box/torus */
     uint64_t n_hit;            /* pixels with depth < MAX_DIST */
+    double operator_flops;     /* operator-tree scenes: FLOPs of the operator nodes executed (transforms, twist, smooth min...) */
     double algorithmic_flops;  /* sum over evals of the executed variant's FLOP count: general affine sphere 26 / box 38 /
                                   torus 29; translation-only sphere fast path 11 */
     double kernel_ms;          /* CUDA-event time of the render kernel(s) */
@@ -173,6 +204,14 @@ int rm_build_bvh(int32_t n_prims, const uint8_t* type, const float* world_to_loc
 int rm_build_octree(int32_t n_prims, const uint8_t* type, const float* world_to_local, const double* params,
                     unsigned flags /* RM_F_LENGTH_SQRT */, rm_octree_node* nodes, int32_t* n_nodes,
                     int32_t* leaf_prim_index, int32_t* n_leaf_prims);
+
+/* The same builders over a whole rm_scene (ABI v2): works for plain primitive lists and for operator trees, where
+ * every object's getWorldPosition / getLocalBoundingRadius / transform follow the operator overrides
+ * (round.ts:26-34, smoothUnion.ts:37-59, repetition.ts:31-34 ...).  scene->accel_kind / nodes are ignored. */
+int rm_build_bvh_scene(const rm_scene* scene, unsigned flags, rm_bvh_node* nodes, int32_t* n_nodes, int32_t* leaf_prim_index,
+                       int32_t* n_leaf_prims);
+int rm_build_octree_scene(const rm_scene* scene, unsigned flags, rm_octree_node* nodes, int32_t* n_nodes,
+                          int32_t* leaf_prim_index, int32_t* n_leaf_prims);
 
 /* ---- render ------------------------------------------------------------------------------- */
 int rm_render(rm_ctx* ctx, const rm_request* rq, const rm_result* host_out);

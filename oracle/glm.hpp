@@ -76,6 +76,12 @@ inline void v3_subtract(vec3& out, const vec3& a, const vec3& b) {
     out.e[1] = js::f32(r1);
     out.e[2] = js::f32(r2);
 }
+// gl-matrix 3.4.4 vec3.distance: Math.hypot of the component differences (same caveat as vec3.length)
+inline double v3_distance(const vec3& a, const vec3& b) {
+    double x = b[0] - a[0], y = b[1] - a[1], z = b[2] - a[2];
+    if (length_uses_hypot()) return js::hypot3(x, y, z);
+    return std::sqrt(x * x + y * y + z * z);
+}
 inline void v3_transform_mat3(vec3& out, const vec3& a, const mat3& m) {
     double x = a[0], y = a[1], z = a[2];
     double r0 = x * (double)m.e[0] + y * (double)m.e[3] + z * (double)m.e[6];

@@ -84,6 +84,18 @@ inline uint8_t to_u8_clamp(double x) {
     return (uint8_t)((fi % 2 == 0) ? fi : fi + 1);
 }
 
+// Math.round: nearest integer, ties toward +Infinity, keeps -0 (V8 Float64Round: ceil, then step down).
+inline double round(double x) {
+    double r = std::ceil(x);
+    return (r - 0.5 > x) ? r - 1.0 : r;
+}
+// Math.sin / Math.cos.  Current V8 builds route these to the glibc dbl-64 routines it vendors
+// (v8_use_libm_trig_functions, third_party/glibc); this container's libm is the same family, so the
+// oracle calls it directly.  (Older V8: fdlibm, < 1 ulp as well — a last-bit difference survives the
+// float32 store that follows every use in the reference with probability ~2^-29.)
+inline double sin(double x) { return std::sin(x); }
+inline double cos(double x) { return std::cos(x); }
+
 // float32 store
 inline float f32(double x) { return (float)x; }
 

@@ -70,6 +70,120 @@ void orc_scene_get_prims(orc_scene* s, uint8_t* type, float* w2l, double* params
         }
     }
 }
+// ---- operator trees as flat node arrays (same layout as rm_op_node in include/rm.h; restated here so the
+// oracle stays independent of the product headers)
+struct orc_op_node {
+    int32_t kind;      // 0 = primitive leaf, 1 round, 2 twist, 3 smooth union, 4 smooth subtraction, 5 repetition, 6 animated translate
+    int32_t child[2];  // node indices, -1 = none
+    int32_t prim;      // leaf: index into the primitive arrays
+    double p[4];       // round: radius | twist: amount | smooth: k | repetition: spacing xyz | animated: amplitude, speed
+    float dir[4];      // animated: normalised direction
+    float transform[16];
+};
+static_assert(sizeof(orc_op_node) == 128, "orc_op_node layout");
+
+static Primitive prim_from_node(const orc_op_node* nodes, int i, const uint8_t* type, const float* w2l, const double* params) {
+    const orc_op_node& nd = nodes[i];
+    if (nd.kind == 0) return prim_from_flat(type[nd.prim], w2l + 16 * nd.prim, params + 4 * nd.prim);
+    Primitive p;
+    static const int kinds[7] = {-1, ROUND, TWIST, SMOOTH_UNION, SMOOTH_SUBTRACTION, REPETITION, ANIMATED_TRANSLATE};
+    p.type = kinds[nd.kind];
+    for (int k = 0; k < 16; ++k) p.transform.e[k] = nd.transform[k];
+    p.a = std::make_shared<Primitive>(prim_from_node(nodes, nd.child[0], type, w2l, params));
+    if (nd.child[1] >= 0) p.b = std::make_shared<Primitive>(prim_from_node(nodes, nd.child[1], type, w2l, params));
+    switch (p.type) {
+        case ROUND: p.radius = nd.p[0]; break;
+        case TWIST: p.twistAmount = nd.p[0]; break;
+        case SMOOTH_UNION: case SMOOTH_SUBTRACTION: p.smoothness = nd.p[0]; break;
+        case REPETITION: p.spacing = glm::v3_from(nd.p[0], nd.p[1], nd.p[2]); break;
+        default:
+            p.amplitude = nd.p[0];
+            p.speed = nd.p[1];
+            for (int k = 0; k < 3; ++k) p.direction.e[k] = nd.dir[k];
+            break;
+    }
+    return p;
+}
+void orc_scene_set_tree(orc_scene* s, const uint8_t* type, const float* w2l, const double* params, const void* nodes,
+                        int n_objects, const int32_t* roots) {
+    std::vector<Primitive> objs;
+    for (int i = 0; i < n_objects; ++i) objs.push_back(prim_from_node((const orc_op_node*)nodes, roots[i], type, w2l, params));
+    s->scene.setObjects(std::move(objs));
+}
+static void tree_count(const Primitive& p, int& nNodes, int& nPrims) {
+    nNodes++;
+    if (p.type <= TORUS) nPrims++;
+    if (p.a) tree_count(*p.a, nNodes, nPrims);
+    if (p.b) tree_count(*p.b, nNodes, nPrims);
+}
+void orc_scene_tree_counts(orc_scene* s, int* nNodes, int* nPrims) {
+    *nNodes = *nPrims = 0;
+    for (auto& p : s->scene.objects) tree_count(p, *nNodes, *nPrims);
+}
+static void flat_prim(const Primitive& p, uint8_t* type, float* w2l, double* q) {
+    *type = (uint8_t)p.type;
+    std::memcpy(w2l, p.transform.e, 16 * sizeof(float));
+    q[0] = q[1] = q[2] = q[3] = 0;
+    if (p.type == SPHERE) q[0] = p.radius;
+    else if (p.type == BOX) {
+        q[0] = p.halfSize[0];
+        q[1] = p.halfSize[1];
+        q[2] = p.halfSize[2];
+    } else if (p.type == TORUS) {
+        q[0] = p.majorRadius;
+        q[1] = p.minorRadius;
+    }
+}
+static int tree_flat(const Primitive& p, orc_op_node* nodes, uint8_t* type, float* w2l, double* params, int& nextNode, int& nextPrim) {
+    const int me = nextNode++;
+    orc_op_node& nd = nodes[me];
+    std::memset(&nd, 0, sizeof(nd));
+    nd.child[0] = nd.child[1] = nd.prim = -1;
+    std::memcpy(nd.transform, p.transform.e, sizeof(nd.transform));
+    if (p.type <= TORUS) {
+        nd.kind = 0;
+        nd.prim = nextPrim++;
+        flat_prim(p, type + nd.prim, w2l + 16 * nd.prim, params + 4 * nd.prim);
+        return me;
+    }
+    switch (p.type) {
+        case ROUND: nd.kind = 1; nd.p[0] = p.radius; break;
+        case TWIST: nd.kind = 2; nd.p[0] = p.twistAmount; break;
+        case SMOOTH_UNION: nd.kind = 3; nd.p[0] = p.smoothness; break;
+        case SMOOTH_SUBTRACTION: nd.kind = 4; nd.p[0] = p.smoothness; break;
+        case REPETITION: nd.kind = 5; nd.p[0] = p.spacing[0]; nd.p[1] = p.spacing[1]; nd.p[2] = p.spacing[2]; break;
+        default:
+            nd.kind = 6;
+            nd.p[0] = p.amplitude;
+            nd.p[1] = p.speed;
+            for (int k = 0; k < 3; ++k) nd.dir[k] = p.direction.e[k];
+            break;
+    }
+    int c0 = tree_flat(*p.a, nodes, type, w2l, params, nextNode, nextPrim);
+    int c1 = p.b ? tree_flat(*p.b, nodes, type, w2l, params, nextNode, nextPrim) : -1;
+    nodes[me].child[0] = c0;
+    nodes[me].child[1] = c1;
+    return me;
+}
+// pre-order per object; leaf primitives numbered in encounter order
+void orc_scene_get_tree(orc_scene* s, uint8_t* type, float* w2l, double* params, void* nodes, int32_t* roots) {
+    int nn = 0, np = 0;
+    for (size_t i = 0; i < s->scene.objects.size(); ++i)
+        roots[i] = tree_flat(s->scene.objects[i], (orc_op_node*)nodes, type, w2l, params, nn, np);
+}
+void orc_scene_set_time(orc_scene* s, double time) { s->scene.updateTime(time); }  // raymarcher.ts:59
+// Primitive.getWorldPosition / getLocalBoundingRadius / BoundingBox.fromPrimitive of scene object i
+void orc_object_geometry(orc_scene* s, int i, float* worldPos, double* radius, float* bmin, float* bmax) {
+    const Primitive& p = s->scene.objects[(size_t)i];
+    vec3 w = p.getWorldPosition();
+    std::memcpy(worldPos, w.e, sizeof(w.e));
+    *radius = p.getLocalBoundingRadius();
+    BoundingBox b = BoundingBox::fromPrimitive(p);
+    std::memcpy(bmin, b.min.e, sizeof(b.min.e));
+    std::memcpy(bmax, b.max.e, sizeof(b.max.e));
+}
+double orc_js_round(double x) { return js::round(x); }
+
 void orc_scene_build_accel(orc_scene* s, int kind) { s->scene.buildAccel(kind); }
 void orc_scene_set_camera(orc_scene* s, double pitch, double yaw) { s->scene.camera.setAngles(pitch, yaw); }
 // raymarcher.ts:62-67 : rot3 = mat3.fromMat4(camera.getRotationMatrix()), origin = camera.getPosition()

@@ -70,6 +70,13 @@ def lib():
         L.orc_mulberry32.restype = f64
         L.orc_mulberry32.argtypes = [u32, i32]
         L.orc_set_length_mode.argtypes = [i32]
+        L.orc_scene_set_tree.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+        L.orc_scene_tree_counts.argtypes = [vp, vp, vp]
+        L.orc_scene_get_tree.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orc_scene_set_time.argtypes = [vp, f64]
+        L.orc_object_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.orc_js_round.restype = f64
+        L.orc_js_round.argtypes = [f64]
         _LIB = L
     return _LIB
 
@@ -104,7 +111,7 @@ class OracleScene:
 
     def load_preset(self, idx: int):
         if self._L.orc_scene_load_preset(self._h, idx) != 0:
-            raise ValueError(f"preset {idx} is outside the hot-path scope")
+            raise ValueError(f"preset {idx} is outside the hot-path scope (Mandelbulb)")
         return self
 
     def load_synthetic(self, n: int, seed: int = 0x5EED0001):
@@ -129,6 +136,43 @@ class OracleScene:
         q = np.zeros((n, 4), np.float64)
         self._L.orc_scene_get_prims(self._h, _p(t), _p(m), _p(q))
         return t, m, q
+
+    # ---- operator trees: flat node arrays in the layout of rm_op_node (include/rm.h)
+    NODE_DTYPE = np.dtype([("kind", np.int32), ("child", np.int32, 2), ("prim", np.int32), ("p", np.float64, 4),
+                           ("dir", np.float32, 4), ("transform", np.float32, 16)])
+
+    def set_tree(self, types, w2l, params, nodes, roots):
+        types = np.ascontiguousarray(types, np.uint8)
+        w2l = np.ascontiguousarray(w2l, np.float32).reshape(-1)
+        params = np.ascontiguousarray(params, np.float64).reshape(-1)
+        nodes = np.ascontiguousarray(nodes, self.NODE_DTYPE)
+        roots = np.ascontiguousarray(roots, np.int32)
+        self._L.orc_scene_set_tree(self._h, _p(types), _p(w2l), _p(params), _p(nodes), len(roots), _p(roots))
+        return self
+
+    def get_tree(self):
+        nn, npr = C.c_int(0), C.c_int(0)
+        self._L.orc_scene_tree_counts(self._h, C.byref(nn), C.byref(npr))
+        t = np.zeros(npr.value, np.uint8)
+        m = np.zeros((npr.value, 16), np.float32)
+        q = np.zeros((npr.value, 4), np.float64)
+        nodes = np.zeros(nn.value, self.NODE_DTYPE)
+        roots = np.zeros(self.n_prims, np.int32)
+        self._L.orc_scene_get_tree(self._h, _p(t), _p(m), _p(q), _p(nodes), _p(roots))
+        return t, m, q, nodes, roots
+
+    def set_time(self, time: float):
+        """Scene.updateTime (scene.ts:135-140), which raymarcher.ts:59 calls once per job."""
+        self._L.orc_scene_set_time(self._h, float(time))
+        return self
+
+    def object_geometry(self, i: int):
+        w = np.zeros(3, np.float32)
+        r = C.c_double(0)
+        bmin = np.zeros(3, np.float32)
+        bmax = np.zeros(3, np.float32)
+        self._L.orc_object_geometry(self._h, i, _p(w), C.byref(r), _p(bmin), _p(bmax))
+        return w, r.value, bmin, bmax
 
     def build_accel(self, kind):
         self._L.orc_scene_build_accel(self._h, ACCELS[kind] if isinstance(kind, str) else kind)

@@ -10,7 +10,8 @@
 //   src/acceleration_structures/bvh.ts          whole file
 //   src/acceleration_structures/octree.ts       whole file
 //   src/util/camera.ts:38-44,58-69,81-88        Camera
-//   src/util/sceneManager.ts:21-49,102-207      getTransform / create* / presets 0-5,7-9
+//   src/util/sceneManager.ts:21-49,73-100,102-356 getTransform / create* / presets 0-12,14-18
+//   src/util/primitive_operations/*.ts          Round, Twist, SmoothUnion, SmoothSubtraction, Repetition, AnimatedTranslate
 //   src/util/scene.ts:24-85,144-190             Scene
 #pragma once
 #include <algorithm>
@@ -25,30 +26,77 @@ using glm::mat3;
 using glm::mat4;
 using glm::vec3;
 
-enum PrimType { SPHERE = 0, BOX = 1, TORUS = 2 };
+// Leaf kinds, then the operator kinds of src/util/primitive_operations/*.ts.
+enum PrimType {
+    SPHERE = 0,
+    BOX = 1,
+    TORUS = 2,
+    ROUND = 3,               // round.ts
+    TWIST = 4,               // twist.ts
+    SMOOTH_UNION = 5,        // smoothUnion.ts
+    SMOOTH_SUBTRACTION = 6,  // smoothSubstraction.ts
+    REPETITION = 7,          // repetition.ts
+    ANIMATED_TRANSLATE = 8   // animatedTranslate.ts
+};
 
-// primitive.ts:3-44 + sphere.ts / box.ts / torus.ts
+// primitive.ts:3-44 + sphere.ts / box.ts / torus.ts + the six operator classes.  One tagged struct instead
+// of a class hierarchy; operators hold their wrapped primitives in `a` (primitive / prim1) and `b` (prim2).
 struct Primitive {
     int type = SPHERE;
     int index = 0;    // position in Scene.objectSDFs (identity, used when flattening)
-    mat4 transform;   // world -> local (primitive.ts:4)
-    double radius = 0;                       // sphere.ts:5 (JS number = f64)
+    mat4 transform;   // world -> local (primitive.ts:4).  Operators: super(primitive.transform) or identity.
+    double radius = 0;                       // sphere.ts:5 (JS number = f64) | round.ts:6 radius
     vec3 halfSize = glm::v3_create();        // box.ts:10 (vec3.clone -> f32)
     double majorRadius = 0, minorRadius = 0;  // torus.ts:5-6 (f64)
+    std::shared_ptr<Primitive> a, b;          // wrapped primitive(s)
+    double twistAmount = 0;                   // twist.ts:6
+    double smoothness = 0;                    // smoothUnion.ts:7 / smoothSubstraction.ts:7
+    vec3 spacing = glm::v3_create();          // repetition.ts:6 (the caller's vec3, f32)
+    vec3 direction = glm::v3_create();        // animatedTranslate.ts:9 (normalised, f32)
+    double amplitude = 0, speed = 0, time = 0;  // animatedTranslate.ts:10-12
 
-    // primitive.ts:20-30
+    // primitive.ts:20-30 and the operator overrides
     vec3 getWorldPosition() const {
+        switch (type) {
+            case ROUND: case TWIST: case REPETITION: case ANIMATED_TRANSLATE:  // round.ts:31-34, twist.ts:43-46, ...
+            case SMOOTH_SUBTRACTION:                                            // smoothSubstraction.ts:41-44
+                return a->getWorldPosition();
+            case SMOOTH_UNION: {  // smoothUnion.ts:50-59
+                vec3 pos1 = a->getWorldPosition(), pos2 = b->getWorldPosition();
+                return glm::v3_from((pos1[0] + pos2[0]) / 2, (pos1[1] + pos2[1]) / 2, (pos1[2] + pos2[2]) / 2);
+            }
+            default: break;
+        }
         mat4 localToWorld = glm::m4_create();
         glm::m4_invert(localToWorld, transform);
         return glm::v3_from(localToWorld[12], localToWorld[13], localToWorld[14]);
     }
-    // sphere.ts:16, box.ts:32-34, torus.ts:27-29
+    // sphere.ts:16, box.ts:32-34, torus.ts:27-29 and the operator overrides
     double getLocalBoundingRadius() const {
         switch (type) {
             case SPHERE: return radius;
             case BOX: return glm::v3_length(halfSize);
-            default: return majorRadius + minorRadius;
+            case TORUS: return majorRadius + minorRadius;
+            case ROUND: return a->getLocalBoundingRadius() + radius;              // round.ts:26-29
+            case TWIST: return a->getLocalBoundingRadius();                       // twist.ts:38-41
+            case SMOOTH_SUBTRACTION: return a->getLocalBoundingRadius();          // smoothSubstraction.ts:36-39
+            case REPETITION: return js::kInf;                                     // repetition.ts:31-34
+            case ANIMATED_TRANSLATE: return a->getLocalBoundingRadius() + amplitude;  // animatedTranslate.ts:50-53
+            default: {                                                            // smoothUnion.ts:37-48
+                double r1 = a->getLocalBoundingRadius(), r2 = b->getLocalBoundingRadius();
+                vec3 pos1 = a->getWorldPosition(), pos2 = b->getWorldPosition();
+                double centerDist = glm::v3_distance(pos1, pos2);
+                return js::max2(r1, r2) + centerDist * 0.5;
+            }
         }
+    }
+    // The operators' common prologue: "convert local position back to world space" (round.ts:17-20 etc.).
+    vec3 backToWorld(const vec3& localPos) const {
+        vec3 worldPos = glm::v3_create();
+        mat4 localToWorld = glm::m4_create();
+        glm::m4_invert(localToWorld, transform);
+        glm::v3_transform_mat4(worldPos, localPos, localToWorld);
+        return worldPos;
     }
     double localSdf(const vec3& l) const {
         switch (type) {
@@ -62,11 +110,51 @@ struct Primitive {
                 double insideDist = js::min2(js::max2(q[0], js::max2(q[1], q[2])), 0);
                 return outsideDist + insideDist;
             }
-            default: {  // torus.ts:14-25
+            case TORUS: {  // torus.ts:14-25
                 double x = l[0], y = l[1], z = l[2];
                 double qx = std::sqrt(x * x + z * z) - majorRadius;
                 double qy = y;
                 return std::sqrt(qx * qx + qy * qy) - minorRadius;
+            }
+            case ROUND:  // round.ts:15-24
+                return a->sdf(backToWorld(l)) - radius;
+            case TWIST: {  // twist.ts:14-36
+                vec3 worldPos = backToWorld(l);
+                const double k = twistAmount;
+                const double c = js::cos(k * worldPos[1]);
+                const double s = js::sin(k * worldPos[1]);
+                vec3 twistedPos = glm::v3_from(c * worldPos[0] - s * worldPos[2], worldPos[1], s * worldPos[0] + c * worldPos[2]);
+                return a->sdf(twistedPos);
+            }
+            case SMOOTH_UNION: {  // smoothUnion.ts:18-35
+                vec3 worldPos = backToWorld(l);
+                const double d1 = a->sdf(worldPos), d2 = b->sdf(worldPos);
+                const double k = smoothness * 4.0;
+                const double h = js::max2(k - std::fabs(d1 - d2), 0.0);
+                return js::min2(d1, d2) - h * h * 0.25 / k;
+            }
+            case SMOOTH_SUBTRACTION: {  // smoothSubstraction.ts:17-34
+                vec3 worldPos = backToWorld(l);
+                const double d1 = a->sdf(worldPos), d2 = b->sdf(worldPos);
+                const double k = smoothness * 4.0;
+                const double h = js::max2(k - std::fabs(d1 + d2), 0.0);
+                return js::max2(d1, -d2) + h * h * 0.25 / k;
+            }
+            case REPETITION: {  // repetition.ts:14-29
+                vec3 worldPos = backToWorld(l);
+                vec3 q = glm::v3_create();
+                q.e[0] = js::f32(worldPos[0] - spacing[0] * js::round(worldPos[0] / spacing[0]));
+                q.e[1] = js::f32(worldPos[1] - spacing[1] * js::round(worldPos[1] / spacing[1]));
+                q.e[2] = js::f32(worldPos[2] - spacing[2] * js::round(worldPos[2] / spacing[2]));
+                return a->sdf(q);
+            }
+            default: {  // animatedTranslate.ts:34-48 (no back-to-world step: the child re-applies the transform)
+                const double offset = js::sin(time * speed) * amplitude;
+                vec3 offsetVec = glm::v3_create();
+                glm::v3_scale(offsetVec, direction, offset);
+                vec3 adjustedPos = glm::v3_create();
+                glm::v3_subtract(adjustedPos, l, offsetVec);
+                return a->sdf(adjustedPos);
             }
         }
     }
@@ -75,6 +163,15 @@ struct Primitive {
         vec3 localPos = glm::v3_create();
         glm::v3_transform_mat4(localPos, pos, transform);
         return localSdf(localPos);
+    }
+    // primitive.ts:42-44 and the overrides (animatedTranslate.ts:30-32 does NOT forward to its child)
+    void setTime(double t) {
+        switch (type) {
+            case ANIMATED_TRANSLATE: time = t; break;
+            case ROUND: case TWIST: case REPETITION: a->setTime(t); break;
+            case SMOOTH_UNION: case SMOOTH_SUBTRACTION: a->setTime(t); b->setTime(t); break;
+            default: break;
+        }
     }
 };
 
@@ -486,8 +583,59 @@ inline Primitive createTorus(double x, double y, double z, double radius, const 
     return p;
 }
 
-// presets 0-5, 7-9 (sceneManager.ts:102-207).  Returns false for presets outside the hot-path scope
-// (operator trees / mandelbulb: 6, 10-18).
+// sceneManager.ts:73-100 : operator factories
+inline std::shared_ptr<Primitive> boxed(const Primitive& p) { return std::make_shared<Primitive>(p); }
+inline Primitive createSmoothUnion(const Primitive& prim1, const Primitive& prim2, double k) {  // smoothUnion.ts:9-15
+    Primitive p;
+    p.type = SMOOTH_UNION;
+    p.transform = glm::m4_create();
+    p.a = boxed(prim1);
+    p.b = boxed(prim2);
+    p.smoothness = k;
+    return p;
+}
+inline Primitive createSmoothSubtract(const Primitive& prim1, const Primitive& prim2, double k) {  // smoothSubstraction.ts:9-14
+    Primitive p = createSmoothUnion(prim1, prim2, k);
+    p.type = SMOOTH_SUBTRACTION;
+    return p;
+}
+inline Primitive createTwist(const Primitive& prim, double twistAmount) {  // twist.ts:8-12
+    Primitive p;
+    p.type = TWIST;
+    p.transform = prim.transform;
+    p.a = boxed(prim);
+    p.twistAmount = twistAmount;
+    return p;
+}
+inline Primitive createRound(const Primitive& prim, double radius) {  // round.ts:8-12
+    Primitive p;
+    p.type = ROUND;
+    p.transform = prim.transform;
+    p.a = boxed(prim);
+    p.radius = radius;
+    return p;
+}
+inline Primitive createRepetition(const Primitive& prim, const vec3& spacing) {  // repetition.ts:8-12
+    Primitive p;
+    p.type = REPETITION;
+    p.transform = prim.transform;
+    p.a = boxed(prim);
+    p.spacing = spacing;
+    return p;
+}
+inline Primitive createAnimatedTranslate(const Primitive& prim, const vec3& direction, double amplitude, double speed) {
+    Primitive p;  // animatedTranslate.ts:15-28
+    p.type = ANIMATED_TRANSLATE;
+    p.transform = prim.transform;
+    p.a = boxed(prim);
+    glm::v3_normalize(p.direction, direction);
+    p.amplitude = amplitude;
+    p.speed = speed;
+    p.time = 0;
+    return p;
+}
+
+// presets 0-12, 14-18 (sceneManager.ts:102-356).  Returns false for preset 13 (Mandelbulb: SURVEY.md §8f row 4).
 inline bool makePreset(int idx, std::vector<Primitive>& out) {
     out.clear();
     switch (idx) {
@@ -539,6 +687,55 @@ inline bool makePreset(int idx, std::vector<Primitive>& out) {
             out.push_back(createBox(0, 0, 0, glm::v3_from(0.6, 0.25, 0.6)));
             out.push_back(createBox(0, -0.5, 0, glm::v3_from(0.3, 0.25, 0.3)));
             break;
+        case 6:  // :178-186 Rounded Box
+            out.push_back(createRound(createBox(0, 0, 0, glm::v3_from(0.4, 0.4, 0.4)), 0.3));
+            break;
+        case 10:  // :209-218 Smooth Union
+            out.push_back(createSmoothUnion(createSphere(0, 0, 0, 0.5), createBox(0, 0.5, 0, glm::v3_from(1, 0.2, 1)), 0.2));
+            break;
+        case 11: {  // :219-231 Smooth Subtraction
+            vec3 rot = glm::v3_from(0, M_PI / 4, 0);
+            out.push_back(createSmoothSubtract(createRound(createBox(0, 0, 0, glm::v3_from(1, 1, 1), &rot), 0.1),
+                                               createSphere(0, 0, 0, 0.9), 0.2));
+            break;
+        }
+        case 12:  // :233-246 Smooth Union [A]
+            out.push_back(createSmoothUnion(createAnimatedTranslate(createSphere(0, 0, 0, 1), glm::v3_from(1, 0, 0), 3.0, 0.005),
+                                            createSphere(0, 0, 0, 1), 0.2));
+            break;
+        case 14: {  // :254-262 Twisted Torus
+            vec3 rot = glm::v3_from(-M_PI / 2, 0, 0);
+            out.push_back(createTwist(createTorus(0, 0, 0, 1.3, &rot), 3));
+            break;
+        }
+        case 15:  // :263-271 Infinite Spheres
+            out.push_back(createRepetition(createSphere(0, 0, 0, 0.3), glm::v3_from(1.5, 1.5, 1.5)));
+            break;
+        case 16:  // :272-283 Screw
+            out.push_back(createRound(createTwist(createBox(0, 0, 0, glm::v3_from(0.4, 1.5, 0.4)), 4.0), 0.1));
+            break;
+        case 17: {  // :284-325 Chicken: a left-deep chain of nine smooth unions over ten boxes
+            struct B { double x, y, z, hx, hy, hz; };
+            static const B boxes[10] = {{0, 0, 0, 0.6, 0.6, 0.8},      {0, -0.2, 0, 0.8, 0.4, 0.6},   {0, -0.8, 0.8, 0.4, 0.6, 0.3},
+                                        {0, -0.8, 1.2, 0.4, 0.2, 0.2}, {0, -0.4, 1.0, 0.2, 0.2, 0.2}, {0.3, 1, 0, 0.1, 0.6, 0.01},
+                                        {-0.3, 1, 0, 0.1, 0.6, 0.01},  {0, 1.6, 0.2, 0.6, 0.01, 0.2}, {0.3, 1.6, 0.5, 0.1, 0.01, 0.1},
+                                        {-0.3, 1.6, 0.5, 0.1, 0.01, 0.1}};
+            Primitive acc = createBox(boxes[0].x, boxes[0].y, boxes[0].z, glm::v3_from(boxes[0].hx, boxes[0].hy, boxes[0].hz));
+            for (int i = 1; i < 10; ++i)
+                acc = createSmoothUnion(acc, createBox(boxes[i].x, boxes[i].y, boxes[i].z, glm::v3_from(boxes[i].hx, boxes[i].hy, boxes[i].hz)),
+                                        0.0001);
+            out.push_back(acc);
+            break;
+        }
+        case 18: {  // :326-356 "67"
+            vec3 r5 = glm::v3_from(0, 0, M_PI / 5), r7 = glm::v3_from(0, 0, M_PI / 7), r2 = glm::v3_from(0, 0, M_PI / 2);
+            vec3 rt = glm::v3_from(-M_PI / 2, 0, 0);
+            out.push_back(createSmoothUnion(createRound(createBox(-1.25, -0.8, 0, glm::v3_from(0.05, 0.7, 0.05), &r5), 0.20),
+                                            createRound(createTorus(-1.25, 0.5, 0, 0.8, &rt), 0.05), 0.0001));
+            out.push_back(createSmoothUnion(createRound(createBox(1.35, 0, 0, glm::v3_from(0.05, 1.5, 0.05), &r7), 0.20),
+                                            createRound(createBox(1.25, -1.4, 0, glm::v3_from(0.05, 0.8, 0.05), &r2), 0.20), 0.0001));
+            break;
+        }
         default: return false;
     }
     for (size_t i = 0; i < out.size(); ++i) out[i].index = (int)i;
@@ -603,6 +800,10 @@ struct Scene {
         } else if (kind == ACCEL_BVH) {
             bvh = std::make_unique<BVH>(objectSDFs);
         }
+    }
+    // scene.ts:135-140 (called once per job by raymarcher.ts:59)
+    void updateTime(double time) {
+        for (auto& p : objects) p.setTime(time);
     }
     // scene.ts:144-190
     double getDistance(const vec3& position, uint32_t& count) const {

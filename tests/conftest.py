@@ -56,7 +56,7 @@ def fast_worker():
 
 
 def make_job(W, H, preset=0, accel="None", alg="sphere-tracer", pitch=0.0, yaw=0.0, y0=0, y1=None, synthetic=None,
-             step=0.1, over=1.2):
-    return dict(width=W, height=H, time=0.0, yStart=y0, yEnd=H if y1 is None else y1, camera=dict(pitch=pitch, yaw=yaw),
+             step=0.1, over=1.2, time=0.0):
+    return dict(width=W, height=H, time=time, yStart=y0, yEnd=H if y1 is None else y1, camera=dict(pitch=pitch, yaw=yaw),
                 algorithm=alg, scenePresetIndex=preset, accelerationStructure=accel, overshootFactor=over, stepSize=step,
                 synthetic=synthetic)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/rm.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert L.rm_abi_version() == 1
+    assert L.rm_abi_version() == 2
 
 
 def test_struct_layouts_match_c_abi():
@@ -37,6 +37,9 @@ def test_struct_layouts_match_c_abi():
     assert C.sizeof(_lib.OctreeNode) == 48
     assert _lib.OctreeNode.min_distance.offset == 40
     assert C.sizeof(_lib.Request) % 8 == 0
+    assert C.sizeof(_lib.OpNode) == 128 == sm.OP_NODE_DTYPE.itemsize
+    assert _lib.OpNode.transform.offset == 64 and _lib.OpNode.p.offset == 16
+    assert _lib.Scene.object_root.offset == C.sizeof(_lib.Scene) - 8
 
 
 @pytest.mark.skipif(HAVE_GPU, reason="only meaningful on a machine without a GPU")
@@ -58,17 +61,24 @@ def test_product_never_imports_oracle():
 
 @pytest.mark.parametrize("idx", sm.SUPPORTED_PRESETS)
 def test_presets_match_oracle_bitwise(oracle, idx):
-    t, m, q = sm.get_preset(idx).arrays()
-    ot, om, oq = oracle.OracleScene().load_preset(idx).get_prims()
+    pl = sm.get_preset(idx)
+    t, m, q = pl.arrays()
+    if idx in sm.OPERATOR_PRESETS:  # operator trees: leaves + the flat node array, same pre-order on both sides
+        ot, om, oq, onodes, oroots = oracle.OracleScene().load_preset(idx).get_tree()
+        assert pl.op_nodes.tobytes() == onodes.tobytes()
+        assert np.array_equal(pl.object_root, oroots)
+    else:
+        ot, om, oq = oracle.OracleScene().load_preset(idx).get_prims()
+        assert pl.op_nodes is None
     assert np.array_equal(t, ot)
     assert np.array_equal(bits(m), bits(om))
     assert np.array_equal(bits(q), bits(oq))
 
 
-@pytest.mark.parametrize("idx", [6, 10, 11, 12, 13, 14, 15, 16, 17, 18])
-def test_operator_presets_are_rejected(idx):
+def test_mandelbulb_preset_is_rejected():
     with pytest.raises(sm.UnsupportedPreset):
-        sm.get_preset(idx)
+        sm.get_preset(13)
+    assert 13 not in sm.SUPPORTED_PRESETS and len(sm.SUPPORTED_PRESETS) == 18
 
 
 def test_synthetic_scene_matches_oracle_bitwise(oracle):
@@ -117,33 +127,41 @@ def _scene_cases():
 @pytest.mark.parametrize("kind,arg", _scene_cases())
 def test_native_bvh_builder_matches_oracle(oracle, kind, arg):
     if kind == "preset":
-        t, m, q = sm.get_preset(arg).arrays()
+        pl = sm.get_preset(arg)
         osc = oracle.OracleScene().load_preset(arg)
     else:
-        t, m, q = sm.synthetic_spheres(arg).arrays()
+        pl = sm.synthetic_spheres(arg)
         osc = oracle.OracleScene().load_synthetic(arg)
+    t, m, q = pl.arrays()
     ob, ol, oleaf = osc.build_accel("BVH").bvh_flat()
-    nodes, nn, leaf = rb.build_bvh(t, m, q)
+    nodes, nn, leaf = rb.build_bvh_scene(t, m, q, pl.op_nodes, pl.object_root)
+    if pl.op_nodes is None:  # the array form of the entry point gives the same bytes
+        n2, nn2, leaf2 = rb.build_bvh(t, m, q)
+        assert nn2 == nn and bytes(n2) == bytes(nodes) and np.array_equal(leaf, leaf2)
     a = np.frombuffer(nodes, dtype=BVH_DT, count=nn)
     assert nn == len(ob)
     assert np.array_equal(bits(a["bmin"]), bits(ob[:, :3])) and np.array_equal(bits(a["bmax"]), bits(ob[:, 3:]))
     assert np.array_equal(a["l"], ol[:, 0]) and np.array_equal(a["r"], ol[:, 1])
     assert np.array_equal(a["pf"], ol[:, 2]) and np.array_equal(a["pc"], ol[:, 3])
     assert np.array_equal(leaf, oleaf)
-    # every primitive lives in exactly one leaf (so the reference's Set de-duplication never matters)
-    assert sorted(leaf.tolist()) == list(range(len(t)))
+    # every scene object lives in exactly one leaf (so the reference's Set de-duplication never matters)
+    assert sorted(leaf.tolist()) == list(range(pl.n_objects))
 
 
 @pytest.mark.parametrize("kind,arg", _scene_cases())
 def test_native_octree_builder_matches_oracle(oracle, kind, arg):
     if kind == "preset":
-        t, m, q = sm.get_preset(arg).arrays()
+        pl = sm.get_preset(arg)
         osc = oracle.OracleScene().load_preset(arg)
     else:
-        t, m, q = sm.synthetic_spheres(arg).arrays()
+        pl = sm.synthetic_spheres(arg)
         osc = oracle.OracleScene().load_synthetic(arg)
+    t, m, q = pl.arrays()
     ob, ol, lvl, emp, mind, oleaf = osc.build_accel("Octree").octree_flat()
-    nodes, nn, leaf = rb.build_octree(t, m, q)
+    nodes, nn, leaf = rb.build_octree_scene(t, m, q, pl.op_nodes, pl.object_root)
+    if pl.op_nodes is None:
+        n2, nn2, leaf2 = rb.build_octree(t, m, q)
+        assert nn2 == nn and bytes(n2) == bytes(nodes) and np.array_equal(leaf, leaf2)
     a = np.frombuffer(nodes, dtype=OCT_DT, count=nn)
     assert nn == len(ob)
     assert np.array_equal(bits(a["bmin"]), bits(ob[:, :3])) and np.array_equal(bits(a["bmax"]), bits(ob[:, 3:]))
