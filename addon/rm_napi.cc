@@ -1,7 +1,8 @@
 // rm_napi.cc — Node N-API addon over the C ABI of include/rm.h (COMPILE-ONLY in this image: no Node.js).
 //
 // Exposes to JavaScript exactly what the reference's worker did (src/workers/raymarchWorker.ts):
-//   addon.uploadScene({type: Uint8Array, worldToLocal: Float32Array, params: Float64Array, accel: 'None'|'Octree'|'BVH'})
+//   addon.uploadScene({type: Uint8Array, worldToLocal: Float32Array, params: Float64Array, accel: 'None'|'Octree'|'BVH',
+//                      opNodes?: Uint8Array (rm_op_node records, 128 B each), objectRoot?: Int32Array})
 //       -> rm_upload_scene          (replaces `new Scene(accel); scene.loadPreset(i)`, raymarchWorker.ts:37-38)
 //   addon.render(job, camera{rot3: Float32Array(9), origin: Float32Array(3)}) : Promise<Result>
 //       -> rm_render on a libuv worker thread (the JS event loop never blocks on CUDA); Result carries the
@@ -77,6 +78,20 @@ napi_value UploadScene(napi_env env, napi_callback_info info) {
     if (nm != 16 * nt || np != 4 * nt) {
         napi_throw_error(env, "RM_ERR_ARG", "worldToLocal must hold 16 and params 4 values per primitive");
         return nullptr;
+    }
+    // operator trees (src/util/primitive_operations): flat rm_op_node records + the root node of every scene object
+    size_t nb = 0, nr = 0;
+    const void* opn = get_ta(env, arg, "opNodes", &nb);
+    const void* roots = get_ta(env, arg, "objectRoot", &nr);
+    if (opn && roots && nr > 0) {
+        if (nb % sizeof(rm_op_node) != 0) {
+            napi_throw_error(env, "RM_ERR_ARG", "opNodes must be a whole number of 128-byte rm_op_node records");
+            return nullptr;
+        }
+        s.op_nodes = (const rm_op_node*)opn;
+        s.n_op_nodes = (int32_t)(nb / sizeof(rm_op_node));
+        s.object_root = (const int32_t*)roots;
+        s.n_objects = (int32_t)nr;
     }
     if (rm_upload_scene(g_ctx, &s) != RM_OK) napi_throw_error(env, "RM_ERR", rm_last_error(g_ctx));
     return nullptr;
