@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -226,6 +227,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
 
     const DevStats& s = *c->h_stats;
     if (s.t_total) fprintf(stderr, "[rm phase timing] warp-cycles total %.3e search %.1f%% barrier %.1f%% stuck %.1f%%\n", (double)s.t_total, 100.0 * s.t_search / s.t_total, 100.0 * s.t_barrier / s.t_total, 100.0 * s.t_stuck / s.t_total);
+    if (s.n_pass) fprintf(stderr, "[rm phase timing] passes %llu, requests/pass %.1f, tc_pass cycles/pass (thread 0): tmem-wait %.0f B-tile wait %.0f mma+tma issue %.0f rest %.0f; re-arms by thread 0 per pass: %.1f\n", s.n_pass, (double)s.n_req / s.n_pass, (double)s.t_tc[0] / s.n_pass, (double)s.t_tc[1] / s.n_pass, (double)s.t_tc[2] / s.n_pass, (double)s.t_tc[3] / s.n_pass, (double)s.n_rearm / s.n_pass);
     rm_stats_t& L = c->last;
     std::memset(&L, 0, sizeof(L));
     L.n_pixels = (uint64_t)rq->width * ownedRows;
@@ -518,6 +520,43 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
         for (int32_t i = 0; i < n; ++i) {
             const float* m = s->world_to_local + 16 * (size_t)i;
             one[(size_t)i] = make_float4(m[12], m[13], m[14], (float)s->params[4 * (size_t)i]);
+        }
+        // B tiles of the tensor-core search (rm_device.cuh tc_pass): split-TF32 rows, pre-tiled as shared-memory images
+        if (n >= 256 && s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) && !std::getenv("RM_DISABLE_TC")) {
+            auto rna = [](float x) {  // cvt.rna.tf32.f32
+                uint32_t u;
+                std::memcpy(&u, &x, 4);
+                u = (u + 0x1000u) & ~0x1FFFu;
+                float r;
+                std::memcpy(&r, &u, 4);
+                return r;
+            };
+            const int32_t nBlocks = (n + 127) / 128;
+            std::vector<float> tiles((size_t)nBlocks * 1024, 0.f);
+            for (int32_t i = 0; i < nBlocks * 128; ++i) {
+                float t[3] = {1.0e15f, 1.0e15f, 1.0e15f}, tt = 3.0e30f;  // padding: can never be the minimum
+                if (i < n) {
+                    const float* m = s->world_to_local + 16 * (size_t)i;
+                    t[0] = m[12];
+                    t[1] = m[13];
+                    t[2] = m[14];
+                    tt = (float)((double)m[12] * m[12] + (double)m[13] * m[13] + (double)m[14] * m[14]);
+                }
+                float* tile = tiles.data() + (size_t)(i >> 7) * 1024;
+                const int j = i & 127;
+                auto at = [&](int k) -> float& { return tile[(k >> 2) * 512 + (j >> 3) * 32 + (j & 7) * 4 + (k & 3)]; };
+                for (int k = 0; k < 3; ++k) {
+                    const float hi = rna(t[k]);
+                    at(k) = hi;
+                    at(4 + k) = rna(t[k] - hi);
+                }
+                const float h = rna(tt);
+                at(3) = h;
+                at(7) = rna(tt - h);
+            }
+            if ((rc = upload(c, tiles.data(), tiles.size(), &ds.tc_tiles))) return rc;
+            CU(c, cudaStreamSynchronize(c->stream));  // `tiles` goes out of scope
+            ds.n_tc_blocks = nBlocks;
         }
         if ((rc = upload(c, one.data(), one.size(), &ds.rec1))) return rc;
         if ((rc = upload(c, chunkRmax.data(), chunkRmax.size(), &ds.chunk_rmax))) return rc;

@@ -286,7 +286,8 @@ RM_DEV float prim_sdf_f32(const float4* __restrict__ rec, int j, const float q[3
 // ------------------------------------------------------------------------------------------
 constexpr int kStageBytes = 2560;  // one stage = 4 sphere chunks of 640 B (tx,ty,tz,r,|t|^2 x 32) or 40 general records
 constexpr int kChunkBytes = 640, kChunkF4 = kChunkBytes / 16;
-constexpr int kWarpsPerCtaMax = 8;  // fast BVH kernels run 8 warps per CTA (64-request batches, 2 per lane); all others 4
+constexpr int kWarpsPerCtaMax = 16;  // fast BVH kernels: 16 warps per CTA for translation-only spheres (tensor-core pass, 128-request batches),
+                                     // 8 for general primitives (64-request batches, 2 per lane); all other kernels 4
 constexpr int kChunk = 32;         // argmin granularity of the fp32 search
 
 RM_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -539,6 +540,322 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float (&q)[NQ][3], War
         break;
     }
     // padded dummies can never win (|l| ~ 1e15), so code < n_prims whenever it is set
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core search (tcgen05 + TMEM) for translation-only spheres in the CTA-cooperative pass.
+//
+// The screening value of the search is a distance matrix: S[i][j] = |p_i + t_j|^2 - |p_i|^2 = 2 p_i . t_j + |t_j|^2 for
+// 128 query points x all spheres — a GEMM with K = 4.  It runs on the 5th-generation tensor cores in TF32 with the
+// fp32 operands SPLIT into hi + lo TF32 terms (hi.hi + lo.hi + hi.lo + lo.lo per coordinate, |t|^2 in three terms:
+// K = 16), so the products are exact in the fp32 accumulator and the result is good to ~1e-7 of (|p| + |t|)^2 — the same
+// error class as the FFMA version it replaces, covered by the screen's slack.  Operands are K-major, no swizzle:
+// the B tiles (128 spheres x 16) are pre-tiled in HBM as exact shared-memory images and arrive by TMA bulk copy;
+// accumulators live in TMEM (2 x 128 columns, double buffered); the epilogue pulls them with tcgen05.ld and keeps
+// one minimum per 32-sphere chunk (FMNMX3), feeding the same candidate screen as before.  Results are unchanged:
+// candidates are still resolved with the plain fp32 SDF and the winner polished in fp64.
+// ------------------------------------------------------------------------------------------
+constexpr int kTcGroups = 4;            // warpgroups of the CTA = TMEM accumulator buffers (4 x 128 columns = all of TMEM)
+constexpr int kTcStages = 16;           // B-tile ring (4 KB each)
+constexpr int kTcBlock = 128;           // spheres per MMA (N) = query rows per batch (M)
+constexpr uint32_t kTcTileBytes = 4096;  // B tile: 128 rows x 8 tf32
+constexpr uint32_t kTcATileBytes = 8192;  // A tile: 128 rows x 16 tf32
+constexpr uint32_t kTcLBO = 2048, kTcSBO = 128;  // canonical no-swizzle K-major: 8-row core matrices of 128 B
+
+RM_DEV uint64_t umma_desc(uint32_t saddr) {  // shared-memory matrix descriptor (sm_100, version 1, SWIZZLE_NONE)
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(kTcLBO >> 4) << 16) | ((uint64_t)(kTcSBO >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: kind::tf32, fp32 accumulate, A and B K-major, M = N = 128
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBlock >> 3) << 17) | ((uint32_t)(kTcBlock >> 4) << 24);
+RM_DEV void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate) {  // SASS: UTCHMMA
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(kTcIdesc), "r"(accumulate)
+        : "memory");
+}
+RM_DEV void umma_commit(uint32_t bar) {  // SASS: UTCBAR — the mbarrier completes when every MMA issued so far has
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+RM_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+RM_DEV void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {  // SASS: LDTM.x32 — 32 columns of this thread's TMEM lane
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+        "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+}
+RM_DEV void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {  // SASS: LDTM.x16
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+// min3 as a volatile asm: keeps its place between the (volatile) TMEM loads in program order, so the reduction of one
+// register set sits between the issue of the next loads — the hardware scoreboard releases each set as it lands.
+RM_DEV float min3v(float a, uint32_t b, uint32_t c) {
+    float r;
+    asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "r"(b), "r"(c));
+    return r;
+}
+// minimum of 32 accumulators held in two 16-register sets; every instruction mixes both sets
+RM_DEV float min16x2(const uint32_t (&a)[16], const uint32_t (&b)[16]) {
+    float m0 = min3v(__uint_as_float(a[0]), b[0], a[1]);
+    float m1 = min3v(__uint_as_float(b[1]), a[2], b[2]);
+    float m2 = min3v(__uint_as_float(a[3]), b[3], a[4]);
+    float m3 = min3v(__uint_as_float(b[4]), a[5], b[5]);
+    m0 = min3v(m0, a[6], b[6]);
+    m1 = min3v(m1, a[7], b[7]);
+    m2 = min3v(m2, a[8], b[8]);
+    m3 = min3v(m3, a[9], b[9]);
+    m0 = min3v(m0, a[10], b[10]);
+    m1 = min3v(m1, a[11], b[11]);
+    m2 = min3v(m2, a[12], b[12]);
+    m3 = min3v(m3, a[13], b[13]);
+    m0 = min3v(m0, a[14], b[14]);
+    m1 = min3v(m1, a[15], b[15]);
+    return fminf(fminf(m0, m1), fminf(m2, m3));
+}
+RM_DEV float min3(float a, float b, float c) {  // SASS: FMNMX3
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+RM_DEV float min32(const uint32_t (&v)[32]) {
+    float a = min3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    float b = min3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    float c = min3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+    float d = min3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+#pragma unroll
+    for (int j = 12; j < 28; j += 8) {
+        a = min3(a, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        b = min3(b, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        c = min3(c, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+        d = min3(d, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+    }
+    a = min3(a, __uint_as_float(v[28]), __uint_as_float(v[29]));
+    b = min3(b, __uint_as_float(v[30]), __uint_as_float(v[31]));
+    return fminf(min3(a, b, c), d);
+}
+RM_DEV float tf32_rna(float x) {  // round to TF32 (nearest, ties away): the low 13 mantissa bits end up zero
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// Per-CTA tensor-core state (shared-memory addresses + the running block counter that fixes every mbarrier parity).
+struct TcCtx {
+    uint32_t tmem;       // TMEM base: 512 columns = four 128-column accumulator buffers (one per warpgroup)
+    uint32_t sA, sB;     // shared-memory addresses: A tile (8 KB), B ring (kTcStages x 4 KB)
+    uint32_t barFull;    // kTcStages mbarriers: B tile landed
+    uint32_t barTmemFull;  // 4 mbarriers: accumulator buffer written
+    uint32_t drainCnt;     // 4 counters: warps of the owning group that have drained the buffer
+    unsigned g;          // blocks processed by this CTA so far (uniform across the CTA)
+};
+
+// One cooperative pass: up to 128 requests against every sphere.  Called convergently by all 512 threads of the CTA.
+// Thread `row` = threadIdx.x & 127 owns TMEM lane / query `row`; `grp` = threadIdx.x >> 7 selects (block parity, column
+// half), see below.  Partial results go to partBest / partCode [grp * 128 + row].  The single-thread jobs (MMA issue,
+// B-tile refill) rotate over the warps of a group.
+//
+// Operand packing (K = 16 in two MMAs that read the SAME 8-wide B tile):
+//   B row (8 tf32)   : t_hi.x t_hi.y t_hi.z |t|^2_hi   t_lo.x t_lo.y t_lo.z |t|^2_lo
+//   A row, MMA 1     : 2p_hi.x 2p_hi.y 2p_hi.z 1        2p_hi.x 2p_hi.y 2p_hi.z 1      -> 2 p_hi.(t_hi + t_lo) + |t|^2
+//   A row, MMA 2     : 2p_lo.x 2p_lo.y 2p_lo.z 0        2p_lo.x 2p_lo.y 2p_lo.z 0      -> 2 p_lo.(t_hi + t_lo)
+static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef, const float4* shReq, unsigned head, unsigned nBatch, int qcap,
+                                            float* partBest, int* partCode) {
+    const TcCtx tc = tcRef;  // registers: the asm memory clobbers below would otherwise force reloads from local memory
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wq = warp & 3;
+    const int row = tid & 127, grp = tid >> 7;
+    const bool valid = (unsigned)row < nBatch;
+#ifdef RM_PHASE_TIMING
+    long long tcT[4] = {0, 0, 0, 0}, tcMark = clock64();
+#define RM_TC_MARK(i)                     \
+    do {                                  \
+        const long long now_ = clock64(); \
+        tcT[i] += now_ - tcMark;          \
+        tcMark = now_;                    \
+    } while (0)
+#else
+#define RM_TC_MARK(i)
+#endif
+    float q[3] = {0.f, 0.f, 0.f};
+    if (valid) {
+        const float4 v = shReq[(head + (unsigned)row) % (unsigned)qcap];
+        q[0] = v.x;
+        q[1] = v.y;
+        q[2] = v.z;
+    }
+    if (grp == 0) {  // A tile, canonical no-swizzle K-major: (row, K chunk c) at c * LBO + (row / 8) * SBO + (row % 8) * 16
+        float hi[3], lo[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p2 = 2.f * q[c];
+            hi[c] = tf32_rna(p2);
+            lo[c] = tf32_rna(p2 - hi[c]);
+        }
+        const float one = valid ? 1.f : 0.f;
+        const uint32_t base = tc.sA + (uint32_t)(row >> 3) * kTcSBO + (uint32_t)(row & 7) * 16u;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(one) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + kTcLBO), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(one) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + 2u * kTcLBO), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(0.f) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + 3u * kTcLBO), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(0.f) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncthreads();
+
+    const int nB = P.scene.n_tc_blocks;
+    const unsigned g0 = tc.g;
+    const char* tiles = reinterpret_cast<const char*>(P.scene.tc_tiles);
+    auto tma = [&](int b) {  // B tile b -> its ring stage
+        const unsigned sidx = (g0 + (unsigned)b) % kTcStages;
+        mbar_expect_tx(tc.barFull + 8u * sidx, kTcTileBytes);
+        bulk_g2s(tc.sB + sidx * kTcTileBytes, tiles + (size_t)b * kTcTileBytes, kTcTileBytes, tc.barFull + 8u * sidx);
+    };
+    auto mma = [&](int b) {  // S[128 x 128] of block b -> the accumulator buffer of its group
+        const unsigned g = g0 + (unsigned)b, sidx = g % kTcStages;
+        // (the accumulator buffer is free: the caller is the last of the group's warps to have drained block g - 4)
+        mbar_wait(tc.barFull + 8u * sidx, (g / kTcStages) & 1u);
+        RM_TC_MARK(1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tc.tmem + (g % kTcGroups) * (uint32_t)kTcBlock;
+        const uint64_t db = umma_desc(tc.sB + sidx * kTcTileBytes);
+        umma_tf32(d, umma_desc(tc.sA), db, 0u);
+        umma_tf32(d, umma_desc(tc.sA + 2u * kTcLBO), db, 1u);
+        umma_commit(tc.barTmemFull + 8u * (g % kTcGroups));
+    };
+    if (tid == 0) {
+        for (int b = 0; b < kTcStages && b < nB; ++b) tma(b);
+        for (int b = 0; b < kTcGroups && b < nB; ++b) mma(b);
+    }
+    __syncwarp();
+
+    // ---- per-thread screen state (this thread's blocks).  Granule = 64 spheres (two chunks).
+    const float qq = fmaf(q[0], q[0], fmaf(q[1], q[1], q[2] * q[2]));
+    // error bound of the split-TF32 value: measured ~1e-7 of (|p| + |t|)^2 (tools/tc_test.cu); 2e-6 budgeted
+    const float E = 2.0e-6f * (qq + P.scene.tt_max + 2.f * NumFast::sqrt_(qq * P.scene.tt_max)) + 1e-30f;
+    const float rMin = P.scene.r_min;
+    float sRun = 3.0e38f, rootS = 1.0e19f;
+    unsigned short candPair[kCandCap];
+    float candS[kCandCap];
+    int nCand = 0;
+    bool overflow = false;
+    const float2* __restrict__ pairRmax = reinterpret_cast<const float2*>(P.scene.chunk_rmax);
+    auto passes = [&](float m, float rmaxP) {  // can a sphere of a granule with min squared centre distance m still win?
+        const float t = rootS + (rmaxP - rMin);
+        return m - E <= t * t * 1.00001f;
+    };
+    auto screen = [&](float mraw, int pair, float rmaxP) {
+        const float m = mraw + qq;  // min squared centre distance of the granule, +-E
+        if (m < sRun) {
+            sRun = m;
+            rootS = NumFast::sqrt_(fmaxf(m + E, 0.f));
+        }
+        if (passes(m, rmaxP)) {
+            if (nCand == kCandCap) {  // compact against the current bound before giving up
+                int w = 0;
+                for (int e = 0; e < nCand; ++e) {
+                    const float2 r2 = __ldg(pairRmax + candPair[e]);
+                    if (passes(candS[e], fmaxf(r2.x, r2.y))) {
+                        candPair[w] = candPair[e];
+                        candS[w] = candS[e];
+                        ++w;
+                    }
+                }
+                nCand = w;
+            }
+            if (nCand < kCandCap) {
+                candPair[nCand] = (unsigned short)pair;
+                candS[nCand] = m;
+                ++nCand;
+            } else {
+                overflow = true;
+            }
+        }
+    };
+
+    // Four 4-warp groups: group `grp` drains the blocks with (g0 + b) % 4 == grp out of accumulator buffer `grp`
+    // (all 128 columns per thread), so four blocks are in flight per CTA at any time.
+    const int b0 = (int)(((unsigned)grp - g0) % (unsigned)kTcGroups);
+    float4 rmNext = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b0 < nB) rmNext = __ldg(reinterpret_cast<const float4*>(P.scene.chunk_rmax) + b0);
+    const uint32_t taddr = tc.tmem + (uint32_t)grp * (uint32_t)kTcBlock + ((uint32_t)(wq * 32) << 16);
+    const uint32_t barTFullG = tc.barTmemFull + 8u * (unsigned)grp, drainG = tc.drainCnt + 4u * (unsigned)grp;
+    RM_TC_MARK(3);
+    for (int b = b0; b < nB; b += kTcGroups) {
+        const unsigned u = (g0 + (unsigned)b) / kTcGroups;
+        const float4 rm4 = rmNext;
+        if (b + kTcGroups < nB) rmNext = __ldg(reinterpret_cast<const float4*>(P.scene.chunk_rmax) + b + kTcGroups);
+        mbar_wait(barTFullG, u & 1u);
+        RM_TC_MARK(0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32u, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float mA = fminf(min32(v0), min32(v1));
+        tmem_ld32(taddr + 64u, v0);
+        tmem_ld32(taddr + 96u, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float mB = fminf(min32(v0), min32(v1));
+        // the accumulator buffer is free as soon as its values are in registers
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            // whichever of the group's four warps drains the buffer LAST re-arms it: no warp ever waits for a straggler
+            unsigned old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(drainG) : "memory");
+            RM_TC_MARK(3);
+            if (old == 3u) {
+                asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(drainG), "r"(0u) : "memory");
+                if (b + kTcGroups < nB) mma(b + kTcGroups);    // next block of this buffer
+                if (b + kTcStages < nB) tma(b + kTcStages);  // MMA b has completed: its B stage is free
+                RM_TC_MARK(2);
+#ifdef RM_PHASE_TIMING
+                if (tid == 0) atomicAdd(&P.stats->n_rearm, 1ull);
+#endif
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            screen(mA, 2 * b, fmaxf(rm4.x, rm4.y));
+            screen(mB, 2 * b + 1, fmaxf(rm4.z, rm4.w));
+        }
+        RM_TC_MARK(3);
+    }
+    __syncthreads();  // all groups are through: every MMA of the pass has completed and been drained
+    tcRef.g = g0 + (unsigned)nB;
+#ifdef RM_PHASE_TIMING
+    if (tid == 0) {
+        atomicAdd(&P.stats->n_pass, 1ull);
+        atomicAdd(&P.stats->n_req, (unsigned long long)nBatch);
+        for (int i = 0; i < 4; ++i) atomicAdd(&P.stats->t_tc[i], (unsigned long long)tcT[i]);
+    }
+#endif
+
+    // ---- resolve: plain fp32 SDFs of the few candidate granules (or of every block of this group when the list overflowed)
+    float best = 10.f;
+    int code = -1;
+    if (valid) {
+        if (overflow) {
+            for (int c = 0; c < P.scene.n_chunks; ++c)
+                if (((((unsigned)c >> 2) + g0) % (unsigned)kTcGroups) == (unsigned)grp) chunk_exact_gmem(P.scene.rec, c, q, best, code);
+        } else {
+            for (int e = 0; e < nCand; ++e) {
+                const float2 r2 = __ldg(pairRmax + candPair[e]);
+                if (passes(candS[e], fmaxf(r2.x, r2.y))) {
+                    const int c = 2 * (int)candPair[e];
+                    chunk_exact_gmem(P.scene.rec, c, q, best, code);
+                    if (c + 1 < P.scene.n_chunks) chunk_exact_gmem(P.scene.rec, c + 1, q, best, code);
+                }
+            }
+        }
+    }
+    partBest[grp * 128 + row] = best;
+    partCode[grp * 128 + row] = code;
 }
 
 template <int PK>
@@ -1137,17 +1454,20 @@ RM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
     return v;
 }
 
-template <class NP, int ACCEL>
+template <class NP, int ACCEL, int PK>
 struct CtaShape {
-    static constexpr int kWarps = (!NP::kExact && ACCEL == RM_ACCEL_BVH) ? kWarpsPerCtaMax : 4;
+    static constexpr int kWarps = (!NP::kExact && ACCEL == RM_ACCEL_BVH) ? (PK == PK_TSPHERE ? 16 : 8) : 4;
 };
 template <class NP, int ACCEL, int PK>
-__global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
-                                  (ACCEL == RM_ACCEL_BVH) ? (RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL>::kWarps : RM_MIN_BLOCKS_OTHER)
+__global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
+                                  (ACCEL == RM_ACCEL_BVH) ? (RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL, PK>::kWarps : RM_MIN_BLOCKS_OTHER)
     render_kernel(const __grid_constant__ RenderParams P) {
-    constexpr int kWarpsPerCta = CtaShape<NP, ACCEL>::kWarps;
+    constexpr int kWarpsPerCta = CtaShape<NP, ACCEL, PK>::kWarps;
     constexpr int kQueueCap = kWarpsPerCta * 32;  // each thread has at most one request outstanding
-    constexpr unsigned kBatch = (kWarpsPerCta == 8) ? 64u : 32u;  // requests served per cooperative pass
+    constexpr unsigned kBatch = (kWarpsPerCta >= 8) ? 64u : 32u;  // requests served per cooperative pass (FFMA search)
+    // translation-only spheres behind a BVH: the pass runs on the tensor cores, 128 requests at a time (tc_pass)
+    constexpr bool kTC = !NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE && kWarpsPerCta == 16;
+    constexpr unsigned kBatchMax = kTC ? (unsigned)kTcBlock : kBatch;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -1177,9 +1497,12 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
     __shared__ float4 shReq[kQueueCap];               // ring of requests: x, y, z, owner thread
     __shared__ double shRes[kWarpsPerCta * 32];        // results by owner thread
     __shared__ unsigned shReady[kWarpsPerCta * 32];
-    __shared__ float shPartBest[kWarpsPerCta][kBatch];  // per-warp partial search results of the batch in flight
-    __shared__ int shPartCode[kWarpsPerCta][kBatch];
+    __shared__ float shPartBest[kWarpsPerCta * kBatch];  // partial search results of the batch in flight: [warp][request] (FFMA) or [half][row] (TC)
+    __shared__ int shPartCode[kWarpsPerCta * kBatch];
     __shared__ unsigned shTail, shHead, shGo, shStuck, shFinished;
+    __shared__ __align__(8) unsigned long long shTcBar[kTcStages + kTcGroups];
+    __shared__ unsigned shTcDrain[kTcGroups];
+    __shared__ uint32_t shTmemBase;
     const int warpId = threadIdx.x >> 5;
     WarpStage ws;
     ws.phase = 0u;
@@ -1222,6 +1545,37 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
     bool wasStuck = false, wasFinished = false;  // this warp's contribution to shStuck / shFinished
     // the shared queue pays off when one all-primitives pass is much more expensive than a march step
     const bool useQueue = !NP::kExact && (ACCEL == RM_ACCEL_BVH) && P.scene.n_prims >= 256;
+    const bool useTC = kTC && useQueue && P.scene.tc_tiles != nullptr;
+    const unsigned batchCap = useTC ? kBatchMax : kBatch;
+    TcCtx tc;
+    if constexpr (kTC) {
+        if (useTC) {  // CTA-uniform
+            // the dynamic shared memory (per-warp stages of the FFMA search) is re-used as A tile + B-tile ring
+            static_assert((size_t)kWarpsPerCta * 2 * kStageBytes >= (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes, "TC tiles do not fit");
+            tc.sA = smem_u32(shStageDyn);
+            tc.sB = tc.sA + kTcATileBytes;
+            tc.barFull = smem_u32(&shTcBar[0]);
+            tc.barTmemFull = smem_u32(&shTcBar[kTcStages]);
+            tc.drainCnt = smem_u32(&shTcDrain[0]);
+            tc.g = 0u;
+            if (warpId == 0) {  // all 512 TMEM columns of the SM: one CTA per SM
+                asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&shTmemBase)), "r"(512u) : "memory");
+                asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+            }
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < kTcStages; ++i) mbar_init(tc.barFull + 8u * i, 1);
+                for (int i = 0; i < kTcGroups; ++i) {
+                    mbar_init(tc.barTmemFull + 8u * i, 1);
+                    shTcDrain[i] = 0u;
+                }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc.tmem = *(volatile uint32_t*)&shTmemBase;
+        }
+    }
 
     // warp-uniform work-queue cursor
     int tile = -1, tilePos = kTileW * kTileH;
@@ -1260,11 +1614,21 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
 #ifdef RM_PHASE_TIMING
                     tBarrier += (clock64() - tb0_) + (long long)(head & 0u);  // the volatile read forces the deferred barrier to resolve first
 #endif
-                    const unsigned nBatch = min(kBatch, tail - head);
+                    const unsigned nBatch = min(batchCap, tail - head);
+                    bool tcDone = false;
+                    if constexpr (kTC) {
+                        if (useTC) {
+                            RM_T0();
+                            tc_pass(P, tc, shReq, head, nBatch, kQueueCap, shPartBest, shPartCode);
+                            RM_T1(tSearch);
+                            tcDone = true;
+                        }
+                    }
                     // lane i takes request i (and request i + 32 in the 64-request form: two points per lane
                     // halve the shared-memory wavefronts per evaluation)
                     constexpr int NQ = (int)(kBatch / 32u);
                     float rq[NQ][3];
+                    if (!tcDone) {
 #pragma unroll
                     for (int k = 0; k < NQ; ++k) {
                         rq[k][0] = rq[k][1] = rq[k][2] = 0.f;
@@ -1296,9 +1660,10 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                     }
 #pragma unroll
                     for (int k = 0; k < NQ; ++k) {
-                        shPartBest[warpId][lane + 32 * k] = pbest[k];
-                        shPartCode[warpId][lane + 32 * k] = pcode[k];
+                        shPartBest[warpId * (int)kBatch + lane + 32 * k] = pbest[k];
+                        shPartCode[warpId * (int)kBatch + lane + 32 * k] = pcode[k];
                     }
+                    }  // !tcDone
 #ifdef RM_PHASE_TIMING
                     long long tb1_ = clock64();
 #endif
@@ -1313,14 +1678,14 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                         const int owner = __float_as_int(v.w);
                         double res;
                         if constexpr (!NP::kExact) {
-                            float bb = shPartBest[0][threadIdx.x];
-                            int bc = shPartCode[0][threadIdx.x];
-#pragma unroll
-                            for (int w = 1; w < kWarpsPerCta; ++w) {
-                                const float ob = shPartBest[w][threadIdx.x];
+                            float bb = shPartBest[threadIdx.x];
+                            int bc = shPartCode[threadIdx.x];
+                            const int nPart = tcDone ? kTcGroups : kWarpsPerCta, pStride = tcDone ? kTcBlock : (int)kBatch;
+                            for (int w = 1; w < nPart; ++w) {
+                                const float ob = shPartBest[w * pStride + (int)threadIdx.x];
                                 if (ob < bb) {
                                     bb = ob;
-                                    bc = shPartCode[w][threadIdx.x];
+                                    bc = shPartCode[w * pStride + (int)threadIdx.x];
                                 }
                             }
                             res = finish_search<PK>(P, q3, bc);
@@ -1334,7 +1699,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                     }
                     if (threadIdx.x == 0) {
                         shHead = head + nBatch;
-                        shGo = (tail - head - nBatch >= kBatch) ? 1u : 0u;
+                        shGo = (tail - head - nBatch >= batchCap) ? 1u : 0u;
                     }
                     __syncthreads();
                     continue;
@@ -1620,7 +1985,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
                 __syncwarp();
                 if (lane == leader) {
                     __threadfence_block();
-                    if (base + (unsigned)__popc(need) - *(volatile unsigned*)&shHead >= kBatch) *(volatile unsigned*)&shGo = 1u;  // a full batch is waiting
+                    if (base + (unsigned)__popc(need) - *(volatile unsigned*)&shHead >= batchCap) *(volatile unsigned*)&shGo = 1u;  // a full batch is waiting
                 }
             }
         }
@@ -1814,6 +2179,13 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL>::kWarps,
         atomicAdd(&P.stats->t_stuck, (unsigned long long)tStuck);
     }
 #endif
+    if constexpr (kTC) {
+        if (useTC) {  // every warp of the CTA leaves the loop together (shFinished == all): release the TMEM columns
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (warpId == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(512u) : "memory");
+        }
+    }
     // ---- epilogue: diagnostics (main.ts:527-548) — warp reduce, one atomic set per warp ----
     unsigned long long s0 = warp_sum_u64(st.sum_sdf), s1 = warp_sum_u64(st.sum_iters);
     unsigned long long s2 = warp_sum_u64(st.sum_sdf_full), s3 = warp_sum_u64(st.sum_iters_full);

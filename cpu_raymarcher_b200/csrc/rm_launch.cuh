@@ -10,7 +10,7 @@ namespace rm {
 template <class NP, int ACCEL, int PK>
 static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     auto kern = render_kernel<NP, ACCEL, PK>;
-    constexpr int kWarps = CtaShape<NP, ACCEL>::kWarps;
+    constexpr int kWarps = CtaShape<NP, ACCEL, PK>::kWarps;
     constexpr int kThreads = 32 * kWarps;
     constexpr size_t kDynSmem = (size_t)kWarps * 2 * kStageBytes;  // per-warp double-buffered TMA stages
     static int blocksPerSM = 0;  // per instantiation
@@ -21,6 +21,8 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, kDynSmem);
         if (e != cudaSuccess) return (int)e;
         blocksPerSM = std::max(b, 1);
+        // the tensor-core search allocates all 512 TMEM columns of the SM: exactly one (16-warp) CTA per SM
+        if (!NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE) blocksPerSM = 1;
     }
     // persistent grid: a multiple of the SM count, never more warps than there are tiles
     long long warpsWanted = p.n_tiles;

@@ -60,6 +60,10 @@ struct DevScene {
     int32_t n_chunks;        // PK_TSPHERE: number of 32-primitive chunks
     float r_min, r_max;      // PK_TSPHERE: radius range (screening bound of the squared-distance search)
     float tt_max;            // PK_TSPHERE: largest |translation|^2 (error bound of the screening arithmetic)
+    // PK_TSPHERE tensor-core search: per 128 spheres one 4 KB shared-memory image [2 K-chunks][16 row groups][8 rows][4 tf32] of
+    // rows (t_hi, |t|^2_hi | t_lo, |t|^2_lo) — the K-major, no-swizzle B operand of tcgen05.mma.kind::tf32 (null = FFMA search)
+    const float* tc_tiles;
+    int32_t n_tc_blocks;
     // acceleration structure
     const rm_bvh_node* bvh;
     const rm_octree_node* oct;
@@ -92,6 +96,8 @@ struct DevStats {
     unsigned int max_sdf, min_sdf, max_iters, min_iters;
     unsigned int queue;  // atomic tile counter of the persistent-CTA work queue
     unsigned long long t_total, t_search, t_barrier, t_stuck;  // RM_PHASE_TIMING builds: warp-cycles by phase
+    unsigned long long n_pass, n_req, n_rearm, t_tc[4];        // RM_PHASE_TIMING builds: cooperative passes, requests served, buffer re-arms and
+                                                               // tc_pass cycles by step as seen by thread 0
     unsigned int pad_;
 };
 
