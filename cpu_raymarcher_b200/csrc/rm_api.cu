@@ -6,6 +6,7 @@
 // file: if the CUDA runtime reports no device, rm_create fails with RM_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -227,7 +228,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
 
     const DevStats& s = *c->h_stats;
     if (s.t_total) fprintf(stderr, "[rm phase timing] warp-cycles total %.3e search %.1f%% barrier %.1f%% stuck %.1f%%\n", (double)s.t_total, 100.0 * s.t_search / s.t_total, 100.0 * s.t_barrier / s.t_total, 100.0 * s.t_stuck / s.t_total);
-    if (s.n_pass) fprintf(stderr, "[rm phase timing] passes %llu, requests/pass %.1f, tc_pass cycles/pass (thread 0): tmem-wait %.0f B-tile wait %.0f mma+tma issue %.0f rest %.0f; re-arms by thread 0 per pass: %.1f\n", s.n_pass, (double)s.n_req / s.n_pass, (double)s.t_tc[0] / s.n_pass, (double)s.t_tc[1] / s.n_pass, (double)s.t_tc[2] / s.n_pass, (double)s.t_tc[3] / s.n_pass, (double)s.n_rearm / s.n_pass);
+    if (s.n_pass) fprintf(stderr, "[rm phase timing] passes %llu, requests/pass %.1f, tc_pass cycles/pass (thread 0): sweep %.0f publish %.0f drain %.0f setup %.0f; work items per pass: %.1f\n", s.n_pass, (double)s.n_req / s.n_pass, (double)s.t_tc[0] / s.n_pass, (double)s.t_tc[1] / s.n_pass, (double)s.t_tc[2] / s.n_pass, (double)s.t_tc[3] / s.n_pass, (double)s.n_rearm / s.n_pass);
     rm_stats_t& L = c->last;
     std::memset(&L, 0, sizeof(L));
     L.n_pixels = (uint64_t)rq->width * ownedRows;
@@ -521,7 +522,13 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             const float* m = s->world_to_local + 16 * (size_t)i;
             one[(size_t)i] = make_float4(m[12], m[13], m[14], (float)s->params[4 * (size_t)i]);
         }
-        // B tiles of the tensor-core search (rm_device.cuh tc_pass): split-TF32 rows, pre-tiled as shared-memory images
+        // Cluster screen of the cooperative pass (rm_device.cuh tc_pass).  The spheres are put in a balanced kd order and cut
+        // into clusters of 128 (= four chunks of a second, sorted chunk-SoA copy).  Each cluster j gets a centre C_j and two bounds
+        //   R_j = max_i(|c_i - C_j| + r_i)   ->  every member's SDF at p is >= |p - C_j| - R_j
+        //   u_j = min_i(|c_i - C_j| - r_i)   ->  some member's SDF at p is  <= |p - C_j| + u_j
+        // The kernel computes |p - C_j|^2 for 128 queries x all clusters on the tensor cores (split-TF32 B tiles, pre-tiled as
+        // shared-memory images) and evaluates only the clusters whose lower
+        // bound does not exceed the best upper bound (work items spread over the CTA's warps).  The minimum over ALL spheres is unchanged.
         if (n >= 256 && s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) && !std::getenv("RM_DISABLE_TC")) {
             auto rna = [](float x) {  // cvt.rna.tf32.f32
                 uint32_t u;
@@ -531,32 +538,117 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
                 std::memcpy(&r, &u, 4);
                 return r;
             };
-            const int32_t nBlocks = (n + 127) / 128;
-            std::vector<float> tiles((size_t)nBlocks * 1024, 0.f);
-            for (int32_t i = 0; i < nBlocks * 128; ++i) {
-                float t[3] = {1.0e15f, 1.0e15f, 1.0e15f}, tt = 3.0e30f;  // padding: can never be the minimum
-                if (i < n) {
-                    const float* m = s->world_to_local + 16 * (size_t)i;
-                    t[0] = m[12];
-                    t[1] = m[13];
-                    t[2] = m[14];
-                    tt = (float)((double)m[12] * m[12] + (double)m[13] * m[13] + (double)m[14] * m[14]);
+            // Balanced kd ordering of the centres: split the longest axis at the position that keeps every leaf a whole
+            // cluster; consecutive runs of kClSize spheres are then compact boxes.
+            std::vector<std::pair<uint32_t, int32_t>> order((size_t)n);
+            for (int32_t i = 0; i < n; ++i) order[(size_t)i] = {0u, i};
+            {
+                constexpr int32_t kLeaf = 128;
+                std::vector<std::pair<int32_t, int32_t>> stack{{0, n}};
+                while (!stack.empty()) {
+                    const auto [lo_, hi_] = stack.back();
+                    stack.pop_back();
+                    if (hi_ - lo_ <= kLeaf) continue;
+                    float bl[3] = {3e38f, 3e38f, 3e38f}, bh[3] = {-3e38f, -3e38f, -3e38f};
+                    for (int32_t i = lo_; i < hi_; ++i)
+                        for (int k = 0; k < 3; ++k) {
+                            const float v = s->world_to_local[16 * (size_t)order[(size_t)i].second + 12 + k];
+                            bl[k] = std::fmin(bl[k], v);
+                            bh[k] = std::fmax(bh[k], v);
+                        }
+                    int ax = 0;
+                    if (bh[1] - bl[1] > bh[ax] - bl[ax]) ax = 1;
+                    if (bh[2] - bl[2] > bh[ax] - bl[ax]) ax = 2;
+                    const int32_t leaves = (hi_ - lo_ + kLeaf - 1) / kLeaf, mid = lo_ + (leaves / 2) * kLeaf;
+                    std::nth_element(order.begin() + lo_, order.begin() + mid, order.begin() + hi_, [&](const auto& a, const auto& b2) {
+                        const float va = s->world_to_local[16 * (size_t)a.second + 12 + ax], vb = s->world_to_local[16 * (size_t)b2.second + 12 + ax];
+                        return va < vb || (va == vb && a.second < b2.second);
+                    });
+                    stack.push_back({lo_, mid});
+                    stack.push_back({mid, hi_});
                 }
-                float* tile = tiles.data() + (size_t)(i >> 7) * 1024;
-                const int j = i & 127;
-                auto at = [&](int k) -> float& { return tile[(k >> 2) * 512 + (j >> 3) * 32 + (j & 7) * 4 + (k & 3)]; };
+            }
+            constexpr int32_t kClSize = 128;  // spheres per cluster = 4 chunks of the sorted chunk-SoA copy
+            const int32_t nCl = (n + kClSize - 1) / kClSize, nBlocks = (nCl + 127) / 128, nChunksS = nCl * (kClSize / 32);
+            std::vector<int32_t> perm((size_t)nChunksS * 32, 0);
+            std::vector<float4> clRec((size_t)nChunksS * 40);  // sorted chunk-SoA copy (same layout as `rec`)
+            float* cf = reinterpret_cast<float*>(clRec.data());
+            for (int32_t i = 0; i < nChunksS * 32; ++i) {
+                float* cc = cf + (size_t)(i >> 5) * 160 + (i & 31);
+                if (i < n) {
+                    const int32_t o = order[(size_t)i].second;
+                    perm[(size_t)i] = o;
+                    const float* m = s->world_to_local + 16 * (size_t)o;
+                    cc[0] = m[12];
+                    cc[32] = m[13];
+                    cc[64] = m[14];
+                    cc[96] = (float)s->params[4 * (size_t)o];
+                    cc[128] = (float)((double)m[12] * m[12] + (double)m[13] * m[13] + (double)m[14] * m[14]);
+                } else {  // padding: a sphere of radius 0 so far away that it can never be the minimum
+                    cc[0] = cc[32] = cc[64] = 1.0e15f;
+                    cc[96] = 0.f;
+                    cc[128] = 3.0e30f;
+                }
+            }
+            constexpr size_t kBlockFloats = 1024;  // 4 KB tile
+            std::vector<float> tiles((size_t)nBlocks * kBlockFloats, 0.f);
+            std::vector<float2> bounds((size_t)nBlocks * 128);  // (R_j, u_j)
+            std::vector<float> blockRmax((size_t)nBlocks, 0.f);   // largest R_j of each 128-cluster block
+            for (int32_t j = 0; j < nBlocks * 128; ++j) {
+                float* blk = tiles.data() + (size_t)(j >> 7) * kBlockFloats;
+                const int jr = j & 127;
+                double C[3] = {-1.0e15, -1.0e15, -1.0e15};  // padding cluster: infinitely far away
+                float R = 0.f, U = 0.f;
+                if (j < nCl) {
+                    const int32_t i0 = j * kClSize, i1 = std::min(n, i0 + kClSize);
+                    double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
+                    for (int32_t i = i0; i < i1; ++i) {
+                        const int32_t o = order[(size_t)i].second;
+                        for (int k = 0; k < 3; ++k) {
+                            const double ck = -(double)s->world_to_local[16 * (size_t)o + 12 + k];  // centre = -translation
+                            bl[k] = std::min(bl[k], ck);
+                            bh[k] = std::max(bh[k], ck);
+                        }
+                    }
+                    for (int k = 0; k < 3; ++k) C[k] = (double)(float)(0.5 * (bl[k] + bh[k]));
+                    double Rd = -1e300, Ud = 1e300;
+                    for (int32_t i = i0; i < i1; ++i) {
+                        const int32_t o = order[(size_t)i].second;
+                        double d2 = 0;
+                        for (int k = 0; k < 3; ++k) {
+                            const double dk = -(double)s->world_to_local[16 * (size_t)o + 12 + k] - C[k];
+                            d2 += dk * dk;
+                        }
+                        const double d = std::sqrt(d2), r = (double)(float)s->params[4 * (size_t)o];
+                        Rd = std::max(Rd, d + r);
+                        Ud = std::min(Ud, d - r);
+                    }
+                    // conservative roundings: the bounds are used against fp32 SDF values
+                    R = std::nextafter((float)(Rd * (1.0 + 1e-6) + 1e-7), 3e38f);
+                    U = std::nextafter((float)(Ud + std::fabs(Ud) * 1e-6 + 1e-7), 3e38f);
+                }
+                const float t[3] = {(float)-C[0], (float)-C[1], (float)-C[2]};  // "translation" of the cluster centre
+                const float tt = std::fmin((float)(C[0] * C[0] + C[1] * C[1] + C[2] * C[2]), 3.0e30f);
+                auto at = [&](int k) -> float& { return blk[(k >> 2) * 512 + (jr >> 3) * 32 + (jr & 7) * 4 + (k & 3)]; };
                 for (int k = 0; k < 3; ++k) {
-                    const float hi = rna(t[k]);
-                    at(k) = hi;
-                    at(4 + k) = rna(t[k] - hi);
+                    const float h = rna(t[k]);
+                    at(k) = h;
+                    at(4 + k) = rna(t[k] - h);
                 }
                 const float h = rna(tt);
                 at(3) = h;
                 at(7) = rna(tt - h);
+                bounds[(size_t)j] = make_float2(R, U);
+                blockRmax[(size_t)(j >> 7)] = std::fmax(blockRmax[(size_t)(j >> 7)], R);
             }
             if ((rc = upload(c, tiles.data(), tiles.size(), &ds.tc_tiles))) return rc;
-            CU(c, cudaStreamSynchronize(c->stream));  // `tiles` goes out of scope
+            if ((rc = upload(c, bounds.data(), bounds.size(), &ds.cl_bound))) return rc;
+            if ((rc = upload(c, blockRmax.data(), blockRmax.size(), &ds.cl_block_rmax))) return rc;
+            if ((rc = upload(c, clRec.data(), clRec.size(), &ds.cl_rec))) return rc;
+            if ((rc = upload(c, perm.data(), perm.size(), &ds.cl_perm))) return rc;
+            CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
             ds.n_tc_blocks = nBlocks;
+            ds.n_clusters = nCl;
         }
         if ((rc = upload(c, one.data(), one.size(), &ds.rec1))) return rc;
         if ((rc = upload(c, chunkRmax.data(), chunkRmax.size(), &ds.chunk_rmax))) return rc;

@@ -28,6 +28,8 @@
 // Instantiated twice over the FIELD model (rm_numeric.cuh): NumJS (fp64, bit-exact) and NumFast (fp32).
 // Control arithmetic is double / non-fused in both.
 #pragma once
+#include <type_traits>
+
 #include "rm_numeric.cuh"
 #include "rm_types.h"
 
@@ -556,7 +558,8 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float (&q)[NQ][3], War
 // candidates are still resolved with the plain fp32 SDF and the winner polished in fp64.
 // ------------------------------------------------------------------------------------------
 constexpr int kTcGroups = 4;            // warpgroups of the CTA = TMEM accumulator buffers (4 x 128 columns = all of TMEM)
-constexpr int kTcStages = 16;           // B-tile ring (4 KB each)
+constexpr int kTcStages = 8;            // B-tile ring (4 KB each)
+constexpr unsigned kTcItemCap = 10240;  // work items of one pass (40 KB of the dynamic shared memory)
 constexpr int kTcBlock = 128;           // spheres per MMA (N) = query rows per batch (M)
 constexpr uint32_t kTcTileBytes = 4096;  // B tile: 128 rows x 8 tf32
 constexpr uint32_t kTcATileBytes = 8192;  // A tile: 128 rows x 16 tf32
@@ -656,17 +659,32 @@ struct TcCtx {
     unsigned g;          // blocks processed by this CTA so far (uniform across the CTA)
 };
 
-// One cooperative pass: up to 128 requests against every sphere.  Called convergently by all 512 threads of the CTA.
-// Thread `row` = threadIdx.x & 127 owns TMEM lane / query `row`; `grp` = threadIdx.x >> 7 selects (block parity, column
-// half), see below.  Partial results go to partBest / partCode [grp * 128 + row].  The single-thread jobs (MMA issue,
-// B-tile refill) rotate over the warps of a group.
+// One cooperative pass: the exact nearest-surface distance over EVERY sphere for up to 128 requests.  Called convergently
+// by all 512 threads of the CTA.
+//
+// 1. Cluster screen on the tensor cores (see rm_api.cu): S_j = |p - C_j|^2 for 128 queries x all clusters of 128 spheres.
+//    Thread `row` = threadIdx.x & 127 owns TMEM lane / query `row`; the four 4-warp groups `grp` = threadIdx.x >> 7 split the
+//    128-cluster blocks ((g0 + b) % 4 == grp, accumulator buffer `grp`).  From its accumulators a thread keeps
+//      ub = min_j (sqrt(S_j) + u_j)           — some sphere is at most this far,
+//      the clusters with sqrt(S_j) - R_j <= ub — the only ones that can hold the nearest sphere.
+// 2. ub is combined over the four groups; the surviving (query, cluster) pairs become work items in shared memory.
+// 3. The 16 warps drain the items: a warp loads the cluster's 128 spheres (sorted chunk-SoA copy, coalesced), evaluates the plain
+//    fp32 SDF at the item's query, and folds (distance, index) into the query's 64-bit key with one shared-memory atomicMin.
+// The result (distance, scene primitive index) of query `row` goes to partBest / partCode [row].
 //
 // Operand packing (K = 16 in two MMAs that read the SAME 8-wide B tile):
-//   B row (8 tf32)   : t_hi.x t_hi.y t_hi.z |t|^2_hi   t_lo.x t_lo.y t_lo.z |t|^2_lo
+//   B row (8 tf32)   : t_hi.x t_hi.y t_hi.z |t|^2_hi   t_lo.x t_lo.y t_lo.z |t|^2_lo          (t = -C_j)
 //   A row, MMA 1     : 2p_hi.x 2p_hi.y 2p_hi.z 1        2p_hi.x 2p_hi.y 2p_hi.z 1      -> 2 p_hi.(t_hi + t_lo) + |t|^2
 //   A row, MMA 2     : 2p_lo.x 2p_lo.y 2p_lo.z 0        2p_lo.x 2p_lo.y 2p_lo.z 0      -> 2 p_lo.(t_hi + t_lo)
+RM_DEV uint32_t float_flip(float f) {  // order-preserving map float -> uint32
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+RM_DEV float float_unflip(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
 static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef, const float4* shReq, unsigned head, unsigned nBatch, int qcap,
-                                            float* partBest, int* partCode) {
+                                            float* partBest, int* partCode, unsigned long long* shKey, unsigned* shItemCount) {
     const TcCtx tc = tcRef;  // registers: the asm memory clobbers below would otherwise force reloads from local memory
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wq = warp & 3;
     const int row = tid & 127, grp = tid >> 7;
@@ -703,23 +721,24 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + kTcLBO), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(one) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + 2u * kTcLBO), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(0.f) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + 3u * kTcLBO), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(0.f) : "memory");
+        shKey[row] = ((unsigned long long)float_flip(3.0e38f) << 32) | 0xFFFFFFFFull;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
     __syncthreads();
 
-    const int nB = P.scene.n_tc_blocks;
-    const unsigned g0 = tc.g;
+    const int nB = P.scene.n_tc_blocks, nCl = P.scene.n_clusters;
     const char* tiles = reinterpret_cast<const char*>(P.scene.tc_tiles);
+    const float2* __restrict__ bound = P.scene.cl_bound;
+    unsigned gBase = tc.g;  // global block counter at the start of the current sweep (fixes all mbarrier parities)
     auto tma = [&](int b) {  // B tile b -> its ring stage
-        const unsigned sidx = (g0 + (unsigned)b) % kTcStages;
+        const unsigned sidx = (gBase + (unsigned)b) % kTcStages;
         mbar_expect_tx(tc.barFull + 8u * sidx, kTcTileBytes);
         bulk_g2s(tc.sB + sidx * kTcTileBytes, tiles + (size_t)b * kTcTileBytes, kTcTileBytes, tc.barFull + 8u * sidx);
     };
     auto mma = [&](int b) {  // S[128 x 128] of block b -> the accumulator buffer of its group
-        const unsigned g = g0 + (unsigned)b, sidx = g % kTcStages;
+        const unsigned g = gBase + (unsigned)b, sidx = g % kTcStages;
         // (the accumulator buffer is free: the caller is the last of the group's warps to have drained block g - 4)
         mbar_wait(tc.barFull + 8u * sidx, (g / kTcStages) & 1u);
-        RM_TC_MARK(1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tc.tmem + (g % kTcGroups) * (uint32_t)kTcBlock;
         const uint64_t db = umma_desc(tc.sB + sidx * kTcTileBytes);
@@ -727,131 +746,196 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
         umma_tf32(d, umma_desc(tc.sA + 2u * kTcLBO), db, 1u);
         umma_commit(tc.barTmemFull + 8u * (g % kTcGroups));
     };
-    if (tid == 0) {
-        for (int b = 0; b < kTcStages && b < nB; ++b) tma(b);
-        for (int b = 0; b < kTcGroups && b < nB; ++b) mma(b);
-    }
-    __syncwarp();
 
-    // ---- per-thread screen state (this thread's blocks).  Granule = 64 spheres (two chunks).
     const float qq = fmaf(q[0], q[0], fmaf(q[1], q[1], q[2] * q[2]));
     // error bound of the split-TF32 value: measured ~1e-7 of (|p| + |t|)^2 (tools/tc_test.cu); 2e-6 budgeted
     const float E = 2.0e-6f * (qq + P.scene.tt_max + 2.f * NumFast::sqrt_(qq * P.scene.tt_max)) + 1e-30f;
-    const float rMin = P.scene.r_min;
-    float sRun = 3.0e38f, rootS = 1.0e19f;
-    unsigned short candPair[kCandCap];
-    float candS[kCandCap];
-    int nCand = 0;
-    bool overflow = false;
-    const float2* __restrict__ pairRmax = reinterpret_cast<const float2*>(P.scene.chunk_rmax);
-    auto passes = [&](float m, float rmaxP) {  // can a sphere of a granule with min squared centre distance m still win?
-        const float t = rootS + (rmaxP - rMin);
-        return m - E <= t * t * 1.00001f;
-    };
-    auto screen = [&](float mraw, int pair, float rmaxP) {
-        const float m = mraw + qq;  // min squared centre distance of the granule, +-E
-        if (m < sRun) {
-            sRun = m;
-            rootS = NumFast::sqrt_(fmaxf(m + E, 0.f));
-        }
-        if (passes(m, rmaxP)) {
-            if (nCand == kCandCap) {  // compact against the current bound before giving up
-                int w = 0;
-                for (int e = 0; e < nCand; ++e) {
-                    const float2 r2 = __ldg(pairRmax + candPair[e]);
-                    if (passes(candS[e], fmaxf(r2.x, r2.y))) {
-                        candPair[w] = candPair[e];
-                        candS[w] = candS[e];
-                        ++w;
-                    }
-                }
-                nCand = w;
-            }
-            if (nCand < kCandCap) {
-                candPair[nCand] = (unsigned short)pair;
-                candS[nCand] = m;
-                ++nCand;
-            } else {
-                overflow = true;
-            }
-        }
-    };
-
-    // Four 4-warp groups: group `grp` drains the blocks with (g0 + b) % 4 == grp out of accumulator buffer `grp`
-    // (all 128 columns per thread), so four blocks are in flight per CTA at any time.
-    const int b0 = (int)(((unsigned)grp - g0) % (unsigned)kTcGroups);
-    float4 rmNext = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b0 < nB) rmNext = __ldg(reinterpret_cast<const float4*>(P.scene.chunk_rmax) + b0);
     const uint32_t taddr = tc.tmem + (uint32_t)grp * (uint32_t)kTcBlock + ((uint32_t)(wq * 32) << 16);
     const uint32_t barTFullG = tc.barTmemFull + 8u * (unsigned)grp, drainG = tc.drainCnt + 4u * (unsigned)grp;
-    RM_TC_MARK(3);
-    for (int b = b0; b < nB; b += kTcGroups) {
-        const unsigned u = (g0 + (unsigned)b) / kTcGroups;
-        const float4 rm4 = rmNext;
-        if (b + kTcGroups < nB) rmNext = __ldg(reinterpret_cast<const float4*>(P.scene.chunk_rmax) + b + kTcGroups);
-        mbar_wait(barTFullG, u & 1u);
-        RM_TC_MARK(0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t v0[32], v1[32];
-        tmem_ld32(taddr, v0);
-        tmem_ld32(taddr + 32u, v1);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float mA = fminf(min32(v0), min32(v1));
-        tmem_ld32(taddr + 64u, v0);
-        tmem_ld32(taddr + 96u, v1);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float mB = fminf(min32(v0), min32(v1));
-        // the accumulator buffer is free as soon as its values are in registers
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    uint32_t* items;  // work-item list (row << 16 | cluster): the dynamic shared memory behind the A tile and the B ring
+    {
+        extern __shared__ __align__(128) float4 shDynTc[];
+        items = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(shDynTc) + kTcATileBytes + kTcStages * kTcTileBytes);
+    }
+    constexpr unsigned kItemCap = kTcItemCap;
+
+    // One sweep of the tensor cores over all cluster blocks; `consume(b, h, v0, v1)` gets 64 accumulators of block b at a time.
+    auto sweep = [&](auto&& consume) {
+        if (tid == 0) {
+            for (int b = 0; b < kTcStages && b < nB; ++b) tma(b);
+            for (int b = 0; b < kTcGroups && b < nB; ++b) mma(b);
+        }
         __syncwarp();
-        if (lane == 0) {
-            // whichever of the group's four warps drains the buffer LAST re-arms it: no warp ever waits for a straggler
-            unsigned old;
-            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(drainG) : "memory");
-            RM_TC_MARK(3);
-            if (old == 3u) {
-                asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(drainG), "r"(0u) : "memory");
-                if (b + kTcGroups < nB) mma(b + kTcGroups);    // next block of this buffer
-                if (b + kTcStages < nB) tma(b + kTcStages);  // MMA b has completed: its B stage is free
-                RM_TC_MARK(2);
-#ifdef RM_PHASE_TIMING
-                if (tid == 0) atomicAdd(&P.stats->n_rearm, 1ull);
-#endif
+        const int b0 = (int)(((unsigned)grp - gBase) % (unsigned)kTcGroups);  // this group's first block: (gBase + b0) % 4 == grp
+        for (int b = b0; b < nB; b += kTcGroups) {
+            const unsigned u = (gBase + (unsigned)b) / kTcGroups;
+            mbar_wait(barTFullG, u & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + 64u * (unsigned)h, v0);
+                tmem_ld32(taddr + 64u * (unsigned)h + 32u, v1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (h == 1) {
+                    // the accumulator buffer is free as soon as its values are in registers; whichever of the group's four
+                    // warps drains it LAST re-arms it: no warp ever waits for a straggler
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        unsigned old;
+                        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(drainG) : "memory");
+                        if (old == 3u) {
+                            asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(drainG), "r"(0u) : "memory");
+                            if (b + kTcGroups < nB) mma(b + kTcGroups);    // next block of this buffer
+                            if (b + kTcStages < nB) tma(b + kTcStages);  // MMA b has completed: its B stage is free
+                        }
+                    }
+                    __syncwarp();
+                }
+                consume(b, h, v0, v1);
             }
         }
-        __syncwarp();
-        if (valid) {
-            screen(mA, 2 * b, fmaxf(rm4.x, rm4.y));
-            screen(mB, 2 * b + 1, fmaxf(rm4.z, rm4.w));
+        __syncthreads();  // every MMA of the sweep has completed and been drained; the B ring is idle
+        gBase += (unsigned)nB;
+    };
+    // Work items: one warp per (query, cluster) pair, 4 spheres per lane, coalesced loads from the sorted chunk-SoA copy;
+    // (distance, index) folded into the query's key with one shared-memory atomicMin.  Two items in flight per warp.
+    auto drain_items = [&](unsigned nItems) {
+        const float* __restrict__ cr = reinterpret_cast<const float*>(P.scene.cl_rec);
+        auto eval = [&](uint32_t item, float& bestD, unsigned& bestI, unsigned& irow) {
+            irow = item >> 16;
+            const unsigned cl = item & 0xFFFFu;
+            const float4 qv = shReq[(head + irow) % (unsigned)qcap];
+            bestD = 3.0e38f;
+            bestI = 0xFFFFFFFFu;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float* ch = cr + (size_t)(cl * 4u + (unsigned)c) * 160u + (unsigned)lane;
+                const float lx = qv.x + __ldg(ch), ly = qv.y + __ldg(ch + 32), lz = qv.z + __ldg(ch + 64);
+                const float d = NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - __ldg(ch + 96);
+                if (d < bestD) {
+                    bestD = d;
+                    bestI = (cl * 4u + (unsigned)c) * 32u + (unsigned)lane;
+                }
+            }
+        };
+        auto fold = [&](float bestD, unsigned bestI, unsigned irow) {
+            const uint32_t key = float_flip(bestD);
+            const uint32_t kmin = __reduce_min_sync(kFull, key);
+            const uint32_t imin = __reduce_min_sync(kFull, key == kmin ? bestI : 0xFFFFFFFFu);
+            if (lane == 0) atomicMin(&shKey[irow], ((unsigned long long)kmin << 32) | (unsigned long long)imin);
+        };
+        const unsigned nWarps = blockDim.x >> 5;
+        for (unsigned it = (unsigned)warp; it < nItems; it += 2u * nWarps) {
+            float d0, d1 = 3.0e38f;
+            unsigned i0, i1 = 0xFFFFFFFFu, r0, r1 = 0u;
+            const bool two = it + nWarps < nItems;
+            eval(items[it], d0, i0, r0);
+            if (two) eval(items[it + nWarps], d1, i1, r1);
+            fold(d0, i0, r0);
+            if (two) fold(d1, i1, r1);
         }
-        RM_TC_MARK(3);
+        __syncthreads();
+    };
+
+    // ---- 1. first sweep: the nearest cluster centre of every query (pure minimum: FMNMX3), then that cluster's exact SDFs
+    float sMin = 3.0e38f;
+    int jMin = 0;
+    RM_TC_MARK(3);
+    sweep([&](int b, int h, const uint32_t(&v0)[32], const uint32_t(&v1)[32]) {
+        const float m = fminf(min32(v0), min32(v1));
+        if (m < sMin) {  // rare after the first blocks: locate the column
+            sMin = m;
+            int k = 0;
+#pragma unroll
+            for (int i = 31; i >= 0; --i) {
+                if (__uint_as_float(v1[i]) == m) k = 32 + i;
+                if (__uint_as_float(v0[i]) == m) k = i;
+            }
+            jMin = b * kTcBlock + 64 * h + k;
+        }
+    });
+    RM_TC_MARK(0);
+    partBest[grp * 128 + row] = sMin;
+    partCode[grp * 128 + row] = jMin;
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int g2 = 1; g2 < kTcGroups; ++g2)
+            if (partBest[g2 * 128 + row] < sMin) {
+                sMin = partBest[g2 * 128 + row];
+                jMin = partCode[g2 * 128 + row];
+            }
+        if (valid) items[row] = ((unsigned)row << 16) | (unsigned)min(jMin, nCl - 1);
     }
-    __syncthreads();  // all groups are through: every MMA of the pass has completed and been drained
-    tcRef.g = g0 + (unsigned)nB;
+    if (tid == 0) *shItemCount = 0u;
+    __syncthreads();
+    drain_items(nBatch);
+    // ub: the fp32 SDF of an actual sphere — nothing farther than this can be the nearest
+    float ub = float_unflip((uint32_t)(shKey[row] >> 32));
+    ub = ub + fabsf(ub) * 1.0e-6f + 1.0e-7f;
+    __syncthreads();  // every thread has read the keys / the first item round before the list is rebuilt
+    RM_TC_MARK(1);
+
+    // ---- 2. second sweep: clusters with sqrt(S_j) - R_j <= ub, i.e. S_j <= (ub + R_j)^2, become work items
+    const float qqLo = qq - E;
+    sweep([&](int b, int h, const uint32_t(&v0)[32], const uint32_t(&v1)[32]) {
+        if (!valid) return;
+        // one threshold for the whole block (its largest R), on the raw accumulator; the rare passers get their own R_j
+        const float tb = fmaxf(ub + __ldg(P.scene.cl_block_rmax + b), 0.f);
+        const float thr = tb * tb * 1.00001f - qqLo;
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) any |= (__uint_as_float(v0[i]) <= thr) | (__uint_as_float(v1[i]) <= thr);
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const float sv = __uint_as_float(i < 32 ? v0[i & 31] : v1[i & 31]);
+                if (sv <= thr) {
+                    const int j = b * kTcBlock + 64 * h + i;
+                    const float t = fmaxf(ub + __ldg(bound + j).x, 0.f);
+                    if (j < nCl && sv + qqLo <= t * t * 1.00001f) {
+                        const unsigned slot = atomicAdd(shItemCount, 1u);
+                        if (slot < kItemCap) items[slot] = ((unsigned)row << 16) | (unsigned)j;
+                    }
+                }
+            }
+        }
+    });
+    RM_TC_MARK(0);
+    const unsigned nItems = min(*(volatile unsigned*)shItemCount, kItemCap);
+    const bool listOverflow = *(volatile unsigned*)shItemCount > kItemCap;
+    drain_items(nItems);
+    RM_TC_MARK(2);
+    tcRef.g = gBase;
 #ifdef RM_PHASE_TIMING
     if (tid == 0) {
         atomicAdd(&P.stats->n_pass, 1ull);
         atomicAdd(&P.stats->n_req, (unsigned long long)nBatch);
+        atomicAdd(&P.stats->n_rearm, (unsigned long long)nItems);
         for (int i = 0; i < 4; ++i) atomicAdd(&P.stats->t_tc[i], (unsigned long long)tcT[i]);
     }
 #endif
-
-    // ---- resolve: plain fp32 SDFs of the few candidate granules (or of every block of this group when the list overflowed)
+    // results: partial 0 carries the answer, the other three are neutral
     float best = 10.f;
     int code = -1;
-    if (valid) {
-        if (overflow) {
-            for (int c = 0; c < P.scene.n_chunks; ++c)
-                if (((((unsigned)c >> 2) + g0) % (unsigned)kTcGroups) == (unsigned)grp) chunk_exact_gmem(P.scene.rec, c, q, best, code);
-        } else {
-            for (int e = 0; e < nCand; ++e) {
-                const float2 r2 = __ldg(pairRmax + candPair[e]);
-                if (passes(candS[e], fmaxf(r2.x, r2.y))) {
-                    const int c = 2 * (int)candPair[e];
-                    chunk_exact_gmem(P.scene.rec, c, q, best, code);
-                    if (c + 1 < P.scene.n_chunks) chunk_exact_gmem(P.scene.rec, c + 1, q, best, code);
-                }
+    if (grp == 0 && valid) {
+        const unsigned long long k = shKey[row];
+        uint32_t idx = (uint32_t)(k & 0xFFFFFFFFull);
+        float d = float_unflip((uint32_t)(k >> 32));
+        if (listOverflow) {  // pathological scene (item list full): every sphere, per lane
+            int c2 = -1;
+            float b2 = 3.0e38f;
+            for (int c = 0; c < nCl * 4; ++c) chunk_exact_gmem(P.scene.cl_rec, c, q, b2, c2);
+            if (c2 >= 0) {
+                d = b2;
+                idx = (uint32_t)c2;
             }
+        }
+        if (idx != 0xFFFFFFFFu && d < 10.f) {
+            best = d;
+            code = __ldg(P.scene.cl_perm + idx);
         }
     }
     partBest[grp * 128 + row] = best;
@@ -1502,6 +1586,8 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     __shared__ unsigned shTail, shHead, shGo, shStuck, shFinished;
     __shared__ __align__(8) unsigned long long shTcBar[kTcStages + kTcGroups];
     __shared__ unsigned shTcDrain[kTcGroups];
+    __shared__ unsigned long long shTcKey[kTcBlock];  // per request: (flipped fp32 distance << 32 | sorted sphere index), atomicMin
+    __shared__ unsigned shTcItems;
     __shared__ uint32_t shTmemBase;
     const int warpId = threadIdx.x >> 5;
     WarpStage ws;
@@ -1551,7 +1637,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     if constexpr (kTC) {
         if (useTC) {  // CTA-uniform
             // the dynamic shared memory (per-warp stages of the FFMA search) is re-used as A tile + B-tile ring
-            static_assert((size_t)kWarpsPerCta * 2 * kStageBytes >= (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes, "TC tiles do not fit");
+            static_assert((size_t)kWarpsPerCta * 2 * kStageBytes >= (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes + 4u * kTcItemCap, "TC tiles + item list do not fit");
             tc.sA = smem_u32(shStageDyn);
             tc.sB = tc.sA + kTcATileBytes;
             tc.barFull = smem_u32(&shTcBar[0]);
@@ -1619,7 +1705,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                     if constexpr (kTC) {
                         if (useTC) {
                             RM_T0();
-                            tc_pass(P, tc, shReq, head, nBatch, kQueueCap, shPartBest, shPartCode);
+                            tc_pass(P, tc, shReq, head, nBatch, kQueueCap, shPartBest, shPartCode, shTcKey, &shTcItems);
                             RM_T1(tSearch);
                             tcDone = true;
                         }

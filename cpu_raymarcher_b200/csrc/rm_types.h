@@ -60,10 +60,16 @@ struct DevScene {
     int32_t n_chunks;        // PK_TSPHERE: number of 32-primitive chunks
     float r_min, r_max;      // PK_TSPHERE: radius range (screening bound of the squared-distance search)
     float tt_max;            // PK_TSPHERE: largest |translation|^2 (error bound of the screening arithmetic)
-    // PK_TSPHERE tensor-core search: per 128 spheres one 4 KB shared-memory image [2 K-chunks][16 row groups][8 rows][4 tf32] of
-    // rows (t_hi, |t|^2_hi | t_lo, |t|^2_lo) — the K-major, no-swizzle B operand of tcgen05.mma.kind::tf32 (null = FFMA search)
+    // PK_TSPHERE cluster screen on the tensor cores (rm_api.cu / tc_pass): spheres in a balanced kd order, clusters of 128.
+    // tc_tiles: per 128 clusters a 4 KB shared-memory image [2 K-chunks][16 row groups][8 rows][4 tf32] of rows
+    // (-C_hi, |C|^2_hi | -C_lo, |C|^2_lo) — the K-major, no-swizzle B operand of tcgen05.mma.kind::tf32.  cl_bound: (R_j, u_j)
+    // per cluster.  cl_rec: sorted chunk-SoA copy of the spheres (chunk = cluster); cl_perm: sorted -> scene index.
     const float* tc_tiles;
-    int32_t n_tc_blocks;
+    const float2* cl_bound;
+    const float* cl_block_rmax;  // largest R_j of each 128-cluster block
+    const float4* cl_rec;
+    const int32_t* cl_perm;
+    int32_t n_tc_blocks, n_clusters;
     // acceleration structure
     const rm_bvh_node* bvh;
     const rm_octree_node* oct;
