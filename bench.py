@@ -239,7 +239,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    t_dev_ms, kern_ms, flops, evals, launches = 0.0, 0.0, 0.0, 0, 0
+    t_dev_ms, kern_ms, flops, xflops, evals, launches = 0.0, 0.0, 0.0, 0.0, 0, 0
     wall0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
@@ -247,6 +247,7 @@ def main():
         t_dev_ms += st["frame_ms"]        # max over ranks of the device time of the step (kernel + fused gather)
         kern_ms += st["kernel_ms_max"]
         flops += st["algorithmic_flops"]
+        xflops += st["executed_flops"]
         evals += st["sum_sdf_full"]
         launches += st["n_launches"]
         last = st
@@ -274,7 +275,14 @@ def main():
         "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tflops if peak_tflops else None, "traffic": None,
                      "peak_source": "measured live: rm_probe_fp32_peak (independent FFMA chains, all SMs, burst)",
-                     "flops_per_eval": "executed variant: translation-only sphere 11 | general sphere 26 / box 38 / torus 29",
+                     "flops_per_eval": "reference-equivalent: every SDF call the reference counts x translation-only sphere 7 (screened "
+                                       "search, >= 512 spheres) / 11 | general sphere 26 / box 38 / torus 29",
+                     "executed_tflops": xflops / (kern_ms * 1e-3) / 1e12 / world,
+                     "note": ("achieved = reference-equivalent SDF work / kernel time. With translation-only spheres behind a BVH "
+                              "the all-primitives fallback is answered exactly by a tensor-core cluster screen, so far fewer "
+                              "FLOPs are executed than the reference's brute force implies (executed_tflops); the kernel is then "
+                              "bound by the divergent ray/BVH control path, not by the FP32 pipe") if last.get("tc_passes") else None,
+                     "tc": {"passes": last.get("tc_passes", 0), "requests": last.get("tc_requests", 0), "items": last.get("tc_items", 0)},
                      "kernel_ms_per_step": kern_ms / args.steps},
     }
 

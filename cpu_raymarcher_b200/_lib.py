@@ -72,7 +72,8 @@ class Stats(C.Structure):
                 ("min_sdf", C.c_uint32), ("max_iters", C.c_uint32), ("min_iters", C.c_uint32),
                 ("sum_sdf_full", C.c_uint64), ("sum_iters_full", C.c_uint64), ("evals_by_type", C.c_uint64 * 3),
                 ("n_hit", C.c_uint64), ("operator_flops", C.c_double), ("algorithmic_flops", C.c_double), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("tc_passes", C.c_uint64), ("tc_requests", C.c_uint64), ("tc_items", C.c_uint64),
+                ("executed_flops", C.c_double)]
 
 
 # every symbol include/rm.h declares

@@ -253,6 +253,16 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
         L.algorithmic_flops = ts ? tsFlops * (double)s.evals_sphere
                                  : 26.0 * (double)s.evals_sphere + 38.0 * (double)s.evals_box + 29.0 * (double)s.evals_torus + L.operator_flops;
     }
+    L.tc_passes = s.tc_passes;
+    L.tc_requests = s.tc_requests;
+    L.tc_items = s.tc_items;
+    L.executed_flops = L.algorithmic_flops;
+    if (s.tc_passes) {
+        // leaf evaluations (11 FLOP) + two tf32 sweeps of 128 x 128 x 16 MACs per cluster block + 128 spheres per work item
+        const double leafEvals = (double)s.evals_sphere - (double)s.tc_requests * (double)c->scene.n_prims;
+        L.executed_flops = 11.0 * leafEvals + (double)s.tc_passes * (double)c->scene.n_tc_blocks * 2.0 * (2.0 * 128 * 128 * 16) +
+                           (double)s.tc_items * 128.0 * 11.0;
+    }
     L.kernel_ms = ms;
     L.n_launches = launches;
     L.device = c->device;

@@ -909,6 +909,11 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
     drain_items(nItems);
     RM_TC_MARK(2);
     tcRef.g = gBase;
+    if (tid == 0) {
+        atomicAdd(&P.stats->tc_passes, 1ull);
+        atomicAdd(&P.stats->tc_requests, (unsigned long long)nBatch);
+        atomicAdd(&P.stats->tc_items, (unsigned long long)(nBatch + nItems));
+    }
 #ifdef RM_PHASE_TIMING
     if (tid == 0) {
         atomicAdd(&P.stats->n_pass, 1ull);

@@ -99,6 +99,7 @@ struct DevStats {
     unsigned long long evals_sphere, evals_box, evals_torus;
     unsigned long long n_hit;
     unsigned long long op_flops;  // operator-tree scenes: FLOPs of the operator instructions executed
+    unsigned long long tc_passes, tc_requests, tc_items;  // cluster screen: cooperative passes, requests served, (query, cluster) work items
     unsigned int max_sdf, min_sdf, max_iters, min_iters;
     unsigned int queue;  // atomic tile counter of the persistent-CTA work queue
     unsigned long long t_total, t_search, t_barrier, t_stuck;  // RM_PHASE_TIMING builds: warp-cycles by phase

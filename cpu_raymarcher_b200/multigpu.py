@@ -57,7 +57,8 @@ def reduce_stats(stats_list):
     """Combine per-rank diagnostics the way main.ts:527-543 would over the whole frame."""
     out = dict(stats_list[0])
     for s in stats_list[1:]:
-        for k in ("n_pixels", "sum_sdf", "sum_iters", "sum_sdf_full", "sum_iters_full", "n_hit", "algorithmic_flops", "n_launches"):
+        for k in ("n_pixels", "sum_sdf", "sum_iters", "sum_sdf_full", "sum_iters_full", "n_hit", "algorithmic_flops", "executed_flops", "tc_passes", "tc_requests",
+                  "tc_items", "n_launches"):
             out[k] += s[k]
         for k in ("max_sdf", "max_iters"):
             out[k] = max(out[k], s[k])
@@ -206,7 +207,8 @@ class FrameSharder:
         dev = torch.device("cuda", self.local_rank)
         sums = torch.tensor([st["n_pixels"], st["sum_sdf"], st["sum_iters"], st["sum_sdf_full"], st["sum_iters_full"], st["n_hit"],
                              st["n_launches"]] + list(st["evals_by_type"]), dtype=torch.int64, device=dev)
-        fsum = torch.tensor([st["algorithmic_flops"]], dtype=torch.float64, device=dev)
+        fsum = torch.tensor([st["algorithmic_flops"], st["executed_flops"], float(st["tc_passes"]), float(st["tc_requests"]),
+                             float(st["tc_items"])], dtype=torch.float64, device=dev)
         maxs = torch.tensor([st["max_sdf"], st["max_iters"], int(st["kernel_ms"] * 1e6)], dtype=torch.int64, device=dev)
         mins = torch.tensor([st["min_sdf"], st["min_iters"]], dtype=torch.int64, device=dev)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
@@ -215,7 +217,8 @@ class FrameSharder:
         dist.all_reduce(mins, op=dist.ReduceOp.MIN)  # also orders every rank's peer stores before rank 0 reads the frame
         s, mx, mn = sums.tolist(), maxs.tolist(), mins.tolist()
         st.update(n_pixels=s[0], sum_sdf=s[1], sum_iters=s[2], sum_sdf_full=s[3], sum_iters_full=s[4], n_hit=s[5], n_launches=s[6],
-                  evals_by_type=s[7:10], algorithmic_flops=float(fsum.item()), max_sdf=mx[0], max_iters=mx[1], min_sdf=mn[0],
+                  evals_by_type=s[7:10], algorithmic_flops=float(fsum[0].item()), executed_flops=float(fsum[1].item()),
+                  tc_passes=int(fsum[2].item()), tc_requests=int(fsum[3].item()), tc_items=int(fsum[4].item()), max_sdf=mx[0], max_iters=mx[1], min_sdf=mn[0],
                   min_iters=mn[1])
         st["kernel_ms_max"] = mx[2] / 1e6
         st["frame_ms"] = st["kernel_ms_max"]  # the gather is fused into the kernel: the slowest rank's kernel is the frame

@@ -177,12 +177,19 @@ typedef struct rm_stats_t {
     uint64_t evals_by_type[3]; /* un-wrapped primitive evaluations split sphere/box/torus */
     uint64_t n_hit;            /* pixels with depth < MAX_DIST */
     double operator_flops;     /* operator-tree scenes: FLOPs of the operator nodes executed (transforms, twist, smooth min...) */
-    double algorithmic_flops;  /* sum over evals of the executed variant's FLOP count: general affine sphere 26 / box 38 /
-                                  torus 29; translation-only sphere fast path 11 */
+    double algorithmic_flops;  /* reference-equivalent work: every SDF call the reference counts x its FLOP count — general affine
+                                  sphere 26 / box 38 / torus 29, translation-only sphere 11, 7 in the screened
+                                  search of large scenes.  Equals the executed FLOPs except where executed_flops says otherwise. */
     double kernel_ms;          /* CUDA-event time of the render kernel(s) */
     double wall_ms;            /* host wall time of the whole call */
     int32_t n_launches;        /* kernels launched by the call */
     int32_t device;
+    /* Translation-only spheres behind a BVH (config 4): the all-primitives fallback (scene.ts:173) is answered exactly by a
+     * cluster screen on the tensor cores instead of N evaluations per request. */
+    uint64_t tc_passes;        /* cooperative passes (<= 128 requests each)                                     */
+    uint64_t tc_requests;      /* fallback requests served                                                      */
+    uint64_t tc_items;         /* (request, 128-sphere cluster) pairs evaluated sphere by sphere                 */
+    double executed_flops;     /* FLOPs actually executed for SDF work: leaf evaluations + tf32 MMAs + work items */
 } rm_stats_t;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
         dist.all_reduce(frame[k], op=dist.ReduceOp.SUM)
     st = po.stats(f.sdfEval, f.iters)
     local = dict(n_pixels=len(rows) * W, sum_sdf=int(st["total_sdf"]), sum_iters=int(st["total_iters"]), sum_sdf_full=int(f.sdf_full.sum()),
-                 sum_iters_full=int(f.iters_full.sum()), n_hit=int((f.depth_f64 < 10).sum()), algorithmic_flops=0.0, n_launches=1,
+                 sum_iters_full=int(f.iters_full.sum()), n_hit=int((f.depth_f64 < 10).sum()), algorithmic_flops=0.0, executed_flops=0.0, tc_passes=0, tc_requests=0, tc_items=0, n_launches=1,
                  max_sdf=int(st["max_sdf"]), min_sdf=int(st["min_sdf"]), max_iters=int(f.iters.max()), min_iters=int(f.iters.min()),
                  evals_by_type=[int(f.sdf_full.sum()), 0, 0], kernel_ms=1.0 + rank)
     gathered = [None] * world
