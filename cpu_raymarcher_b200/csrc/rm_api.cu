@@ -539,7 +539,9 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
         // The kernel computes |p - C_j|^2 for 128 queries x all clusters on the tensor cores (split-TF32 B tiles, pre-tiled as
         // shared-memory images) and evaluates only the clusters whose lower
         // bound does not exceed the best upper bound (work items spread over the CTA's warps).  The minimum over ALL spheres is unchanged.
-        if (n >= 256 && s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) && !std::getenv("RM_DISABLE_TC")) {
+        // (work items pack the cluster index in 16 bits: scenes beyond 65 535 clusters = 8.3 M spheres keep the FFMA search)
+        if (n >= 256 && (n + 127) / 128 <= 65535 && s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) &&
+            !std::getenv("RM_DISABLE_TC")) {
             auto rna = [](float x) {  // cvt.rna.tf32.f32
                 uint32_t u;
                 std::memcpy(&u, &x, 4);

@@ -321,6 +321,34 @@ def test_fast_path_tolerance_matrix(fast_worker, oracle, preset, accel, alg):
     assert dz >= 0.99, f"depth agreement among hit pixels {dz}"
 
 
+@pytest.mark.parametrize("n", [256, 257, 300, 1000, 4097, 12800])
+def test_fast_path_cluster_screen_sizes(fast_worker, oracle, n):
+    """Translation-only spheres behind a BVH: the all-primitives fallback runs as the tensor-core cluster screen
+    (>= 256 spheres).  Sizes around the 128-sphere cluster / 128-cluster block boundaries, rotated camera."""
+    W, H = 96, 54
+    syn = (n, 0x5EED0001)
+    ref = _oracle_scene(oracle, 1, "BVH", 0.35, 1.1, synthetic=syn).render(W, H, "sphere-tracer")
+    f = fast_worker.on_message(make_job(W, H, 1, "BVH", "sphere-tracer", 0.35, 1.1, synthetic=syn), shader="phong", extras=True)
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"n={n}: pixel agreement {px} (depth-only among hits {dz})"
+    assert np.array_equal(f.sdfEval, ref.sdfEval) or px >= PIXEL_AGREEMENT  # counters follow the same control flow
+    st = fast_worker.stats()
+    if (ref.sdf_full >= n).any():  # at least one full-scene fallback happened: it went through the screen
+        assert st["tc_passes"] > 0 and st["tc_requests"] > 0 and st["tc_items"] >= st["tc_requests"]
+        if n >= 12800:  # (tiny scenes pay a whole 128 x 128 MMA block for a couple of clusters)
+            assert st["executed_flops"] < st["algorithmic_flops"]
+
+
+@pytest.mark.parametrize("alg", ["fixed-step", "adaptive-step-v3"])
+def test_fast_path_cluster_screen_other_algorithms(fast_worker, oracle, alg):
+    W, H = 80, 45
+    syn = (3000, 0x5EED0001)
+    ref = _oracle_scene(oracle, 1, "BVH", -0.2, 2.0, synthetic=syn).render(W, H, alg)
+    f = fast_worker.on_message(make_job(W, H, 1, "BVH", alg, -0.2, 2.0, synthetic=syn), shader="phong", extras=True)
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"pixel agreement {px} (depth-only among hits {dz})"
+
+
 @pytest.mark.parametrize("accel", ["BVH", "Octree"])
 def test_fast_path_synthetic_spheres(fast_worker, oracle, accel):
     W, H = 128, 72
