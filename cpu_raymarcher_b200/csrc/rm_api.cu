@@ -41,6 +41,7 @@ struct rm_ctx {
     std::string err;
     // scene
     bool has_scene = false;
+    bool exact_only = false;  // operator trees / mandelbulb: always the exact (fp64) kernels
     DevScene scene{};
     std::vector<void*> scene_allocs;
     TreeProgram tree;            // operator-tree scenes: compiled programs (host copy, for the per-frame animation offsets)
@@ -80,6 +81,7 @@ void free_scene(rm_ctx* c) {
     for (void* p : c->scene_allocs) cudaFree(p);
     c->scene_allocs.clear();
     c->has_scene = false;
+    c->exact_only = false;
     c->tree = TreeProgram();
     c->d_anim = nullptr;
     c->anim_valid = false;
@@ -161,7 +163,8 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.shader = rq->shader;
     P.shader2 = rq->shader_analytics;
     P.length_sqrt = (c->flags & RM_F_LENGTH_SQRT) ? 1 : 0;
-    const bool tree = c->scene.n_instrs > 0;
+    const bool tree = c->exact_only;
+    P.scene.time = rq->time;
     // Operator trees always run the exact (fp64, unfused) kernels: B200 has full-rate-class fp64 and these scenes
     // are a handful of primitives, so there is no reduced-precision variant to disagree with the reference.  A
     // context created without RM_F_VALIDATE_FP64 only swaps V8's compensated hypot for a plain sqrt.
@@ -380,7 +383,7 @@ int rm_build_octree(int32_t n, const uint8_t* type, const float* w2l, const doub
 static int check_scene_arrays(const rm_scene* s) {
     if (!s || s->n_prims < 0 || (s->n_prims > 0 && (!s->type || !s->world_to_local || !s->params))) return RM_ERR_ARG;
     for (int32_t i = 0; i < s->n_prims; ++i)
-        if (s->type[i] > RM_PRIM_TORUS) return RM_ERR_UNSUPPORTED_PRIMITIVE;
+        if (s->type[i] > RM_PRIM_MANDELBULB) return RM_ERR_UNSUPPORTED_PRIMITIVE;
     std::string err;
     return validate_tree(*s, err);
 }
@@ -433,22 +436,30 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     // Primitives: sphere / box / torus; scene objects: those, or operator trees over them.
     // Anything else (mandelbulb, unknown kinds) is rejected loudly.
     const bool tree = s->n_objects > 0;
+    bool hasBulb = false;
+    for (int32_t i = 0; i < n; ++i) hasBulb = hasBulb || s->type[i] == RM_PRIM_MANDELBULB;
+    const bool exactOnly = tree || hasBulb;  // these scenes run the exact (fp64) kernels in every context
     {
         std::string terr;
         int trc = validate_tree(*s, terr);
         if (trc) return fail(c, trc, "%s", terr.c_str());
     }
     const int32_t nObj = tree ? s->n_objects : n;  // Scene.objectSDFs.length
-    bool allTS = n > 0 && !tree;
+    bool allTS = n > 0 && !exactOnly;
     uint32_t hist[3] = {0, 0, 0};
     for (int32_t i = 0; i < n; ++i) {
-        if (s->type[i] > RM_PRIM_TORUS)
-            return fail(c, RM_ERR_UNSUPPORTED_PRIMITIVE, "primitive %d has type %d: only sphere/box/torus are supported (no CPU fallback)", i, (int)s->type[i]);
-        hist[s->type[i]]++;
+        if (s->type[i] > RM_PRIM_MANDELBULB)
+            return fail(c, RM_ERR_UNSUPPORTED_PRIMITIVE, "primitive %d has type %d: only sphere/box/torus/mandelbulb are supported (no CPU fallback)", i, (int)s->type[i]);
+        if (s->type[i] == RM_PRIM_MANDELBULB) {
+            const double* q = s->params + 4 * (size_t)i;
+            if (!(q[1] >= 0.0 && q[1] <= 100000.0)) return fail(c, RM_ERR_ARG, "primitive %d: mandelbulb iteration count %g out of range", i, q[1]);
+        } else {
+            hist[s->type[i]]++;
+        }
         const float* m = s->world_to_local + 16 * (size_t)i;
         for (int k = 0; k < 16; ++k)
             if (!std::isfinite(m[k])) return fail(c, RM_ERR_ARG, "primitive %d: non-finite transform", i);
-        if (!(c->flags & RM_F_VALIDATE_FP64) && !tree && !is_affine(m))
+        if (!(c->flags & RM_F_VALIDATE_FP64) && !exactOnly && !is_affine(m))
             return fail(c, RM_ERR_UNSUPPORTED_PRIMITIVE, "primitive %d: projective world->local is only supported by the validation build", i);
         allTS = allTS && is_translation_sphere(s->type[i], m);
     }
@@ -496,7 +507,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
 
     // fast-path packed records (plain primitive lists only)
     std::vector<float4> rec;
-    if (tree) {
+    if (exactOnly) {
     } else if (allTS) {
         const int32_t nChunks = (n + 31) / 32;
         rec.resize((size_t)nChunks * 40);  // 40 float4 = 160 floats = tx[32] ty[32] tz[32] r[32] tt[32]
@@ -716,7 +727,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             }
         }
         ds.n_nodes = nn;
-        if (s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) && !tree) {
+        if (s->accel_kind == RM_ACCEL_BVH && !(c->flags & RM_F_VALIDATE_FP64) && !exactOnly) {
             // fast path: locate leaf boxes through a uniform grid instead of descending the tree
             LeafGrid grid;
             build_leaf_grid(bvh, grid);
@@ -738,6 +749,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     }
     CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
     c->scene = ds;
+    c->exact_only = exactOnly;
     c->has_scene = true;
     return RM_OK;
 }

@@ -100,7 +100,8 @@ void compute_prim_geometry(int32_t n, const uint8_t* type, const float* w2l, con
         else if (type[i] == RM_PRIM_BOX) {
             double hx = (double)f32(q[0]), hy = (double)f32(q[1]), hz = (double)f32(q[2]);
             localRadius = lengthSqrt ? std::sqrt(hx * hx + hy * hy + hz * hz) : hypot3(hx, hy, hz);
-        } else localRadius = q[0] + q[1];
+        } else if (type[i] == RM_PRIM_MANDELBULB) localRadius = 2.5;  // mandelbulb.ts:80-83
+        else localRadius = q[0] + q[1];
         // BoundingBox.fromPrimitive (boundingBox.ts:133-154)
         const float* s = ok ? inv : m;
         double scaleX = hypot3(s[0], s[1], s[2]);
@@ -412,7 +413,8 @@ void leaf_geom(const rm_scene& s, int32_t i, bool lengthSqrt, NodeGeom& g) {
     else if (s.type[i] == RM_PRIM_BOX) {
         double hx = (double)f32(q[0]), hy = (double)f32(q[1]), hz = (double)f32(q[2]);
         g.radius = lengthSqrt ? std::sqrt(hx * hx + hy * hy + hz * hz) : hypot3(hx, hy, hz);
-    } else g.radius = q[0] + q[1];
+    } else if (s.type[i] == RM_PRIM_MANDELBULB) g.radius = 2.5;  // mandelbulb.ts:80-83
+    else g.radius = q[0] + q[1];
 }
 
 void node_geom(const rm_scene& s, int32_t ni, bool lengthSqrt, NodeGeom& g) {
@@ -556,7 +558,7 @@ struct Compiler {
         switch (nd.kind) {
             case RM_NODE_PRIMITIVE:
                 emit(I_PRIM, nd.prim);
-                hist[s.type[nd.prim]]++;
+                if (s.type[nd.prim] <= RM_PRIM_TORUS) hist[s.type[nd.prim]]++;
                 return;
             case RM_NODE_ROUND:
                 pushed = prologue(nd, true);

@@ -90,6 +90,30 @@ RM_DEV double leaf_sdf_exact(const DevScene& sc, int j, double x, double y, doub
         double outsideDist = length_sqrt ? sqrt(o0 * o0 + o1 * o1 + o2 * o2) : v8_hypot3(o0, o1, o2);
         double insideDist = jsmin(jsmax(q0, jsmax(q1, q2)), 0.0);
         return outsideDist + insideDist;
+    } else if (type == RM_PRIM_MANDELBULB) {  // mandelbulb.ts:38-78 (Math.* = CUDA's double-precision libm)
+        const double px = lx, py = lz, pz = ly;  // p.xyz = p.xzy
+        double zx = px, zy = py, zz = pz;
+        double dr = 1.0, r = 0.0;
+        const double power = prm[0], dphi = (prm[2] != 0.0) ? sc.time * prm[3] : 0.0;
+        const int iterations = (int)prm[1];
+        for (int i = 0; i < iterations; ++i) {
+            r = length_sqrt ? sqrt(zx * zx + zy * zy + zz * zz) : v8_hypot3(zx, zy, zz);
+            if (r > 2.0) break;
+            double theta = atan2(zy, zx);
+            double phi = asin(zz / r);
+            if (prm[2] != 0.0) phi += dphi;
+            dr = pow(r, power - 1.0) * dr * power + 1.0;
+            r = pow(r, power);  // the loop variable now holds r^power: that is what the return reads after the last pass
+            theta = theta * power;
+            phi = phi * power;
+            double st, ct, sp, cp;
+            sincos(theta, &st, &ct);
+            sincos(phi, &sp, &cp);
+            zx = (double)f32r(r * ct * cp + px);
+            zy = (double)f32r(r * st * cp + py);
+            zz = (double)f32r(r * sp + pz);
+        }
+        return 0.5 * log(r) * r / dr;
     } else {  // torus.ts:14-25
         double qx = sqrt(lx * lx + lz * lz) - prm[0];
         double qy = ly;

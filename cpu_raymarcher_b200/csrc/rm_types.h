@@ -75,6 +75,7 @@ struct DevScene {
     const rm_octree_node* oct;
     const int32_t* leaf_prims;
     uint32_t type_hist[3];  // number of sphere / box / torus primitives in the scene
+    double time;            // Job.time of the current render (AnimatedTranslate offsets are precomputed; the Mandelbulb reads it)
     // operator trees (n_instrs > 0): n_prims counts scene OBJECTS; type / w2l / params hold the trees' leaves
     int32_t n_instrs;
     const DevInstr* instrs;

@@ -1,7 +1,6 @@
-"""Scene presets — host-side mirror of src/util/sceneManager.ts: sphere / box / torus primitives, the six SDF
-operators of src/util/primitive_operations/ (Round, Twist, SmoothUnion, SmoothSubtraction, Repetition,
-AnimatedTranslate) and presets 0-12, 14-18.  Preset 13 (Mandelbulb) is outside the path
-and raises UnsupportedPreset — there is no CPU fallback to route it to."""
+"""Scene presets — host-side mirror of src/util/sceneManager.ts: sphere / box / torus / mandelbulb primitives, the
+six SDF operators of src/util/primitive_operations/ (Round, Twist, SmoothUnion, SmoothSubtraction, Repetition,
+AnimatedTranslate) and all 19 presets."""
 from __future__ import annotations
 
 import math
@@ -11,15 +10,16 @@ import numpy as np
 
 from . import glmatrix as gm
 
-SPHERE, BOX, TORUS = 0, 1, 2
+SPHERE, BOX, TORUS, MANDELBULB = 0, 1, 2, 3
 
 PRESET_NAMES = [
     "Sphere", "Random Spheres", "Grid of Spheres", "Dense Sphere Grid", "Atom", "Torus", "Rounded Box", "Cube",
     "Sphere and Cube", "Pyramid of Boxes", "Smooth Union", "Smooth Subtraction", "Smooth Union [A]", "Mandelbulb [A]",
     "Twisted Torus", "Infinite Spheres", "Screw", "Chicken", "67",
 ]
-SUPPORTED_PRESETS = (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18)
+SUPPORTED_PRESETS = tuple(range(19))
 OPERATOR_PRESETS = (6, 10, 11, 12, 14, 15, 16, 17, 18)
+NODE_PRESETS = OPERATOR_PRESETS + (13,)  # built from Node objects (operators, mandelbulb)
 
 # numpy view of rm_op_node (include/rm.h)
 OP_NODE_DTYPE = np.dtype([("kind", np.int32), ("child", np.int32, 2), ("prim", np.int32), ("p", np.float64, 4),
@@ -110,6 +110,13 @@ def create_torus(x, y, z, radius, rotation=None) -> Node:  # sceneManager.ts:47-
     return Node("primitive", get_transform(x, y, z, rotation), type=TORUS, params=(float(radius), float(radius) / 4, 0.0, 0.0))
 
 
+def create_mandelbulb(x, y, z, power=8.0, iterations=9, enable_animation=True, animation_speed=0.05, rotation=None) -> Node:
+    """sceneManager.ts:51-71: getTransform, then mat4.scale(transform, transform, [0.5, 0.5, 0.5])."""
+    transform = gm.mat4_scale(get_transform(x, y, z, rotation), (0.5, 0.5, 0.5))
+    return Node("primitive", transform, type=MANDELBULB,
+                params=(float(power), float(iterations), 1.0 if enable_animation else 0.0, float(animation_speed)))
+
+
 def create_smooth_union(prim1: Node, prim2: Node, k: float) -> Node:  # smoothUnion.ts:9-15: super(mat4.create())
     return Node("smooth-union", gm.mat4_create(), (prim1, prim2), p=(float(k), 0.0, 0.0, 0.0))
 
@@ -190,6 +197,8 @@ def _operator_preset(index: int):
     if index == 12:
         return [create_smooth_union(create_animated_translate(create_sphere(0, 0, 0, 1), (1, 0, 0), 3.0, 0.005),
                                     create_sphere(0, 0, 0, 1), 0.2)]
+    if index == 13:
+        return [create_mandelbulb(0, 0, 0, 8, 80, True, -0.0001)]
     if index == 14:
         return [create_twist(create_torus(0, 0, 0, 1.3, (-math.pi / 2, 0, 0)), 3)]
     if index == 15:
@@ -213,7 +222,7 @@ def _operator_preset(index: int):
 
 def get_preset(index: int) -> PrimitiveList:
     """SceneManager.getPreset(index).objects (sceneManager.ts:102-356,359-361)."""
-    if index in OPERATOR_PRESETS:
+    if index in NODE_PRESETS:
         return flatten(_operator_preset(index))
     pl = PrimitiveList()
     if index == 0:
@@ -248,9 +257,6 @@ def get_preset(index: int) -> PrimitiveList:
         add_box(pl, 0, 0.5, 0, (0.9, 0.25, 0.9))
         add_box(pl, 0, 0, 0, (0.6, 0.25, 0.6))
         add_box(pl, 0, -0.5, 0, (0.3, 0.25, 0.3))
-    elif 0 <= index < len(PRESET_NAMES):
-        raise UnsupportedPreset(f"preset {index} ({PRESET_NAMES[index]!r}) is the Mandelbulb fractal, which is outside the "
-                                "B200 hot path (sphere/box/torus primitives and the six SDF operators)")
     else:
         raise IndexError(index)
     return pl

@@ -33,7 +33,7 @@ typedef struct rm_ctx rm_ctx; /* opaque: one CUDA device, its stream, device-res
 typedef enum rm_status {
     RM_OK = 0,
     RM_ERR_ARG = -1,                   /* null pointer, bad size, bad enum */
-    RM_ERR_UNSUPPORTED_PRIMITIVE = -2, /* mandelbulb or unknown primitive / operator kinds (outside the path) */
+    RM_ERR_UNSUPPORTED_PRIMITIVE = -2, /* unknown primitive / operator kinds (no CPU fallback to route them to) */
     RM_ERR_CUDA = -3,                  /* no device, launch or copy failure (message in rm_last_error) */
     RM_ERR_STATE = -4,                 /* e.g. rm_render before rm_upload_scene */
     RM_ERR_NOMEM = -5
@@ -43,8 +43,8 @@ typedef enum rm_status {
 #define RM_F_VALIDATE_FP64 1u /* fp64, non-fused, JS-number-exact validation kernels (bit-exact counters/hit mask) */
 #define RM_F_LENGTH_SQRT 2u   /* validation only: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot (gl-matrix caveat) */
 
-/* src/util/primitives/{sphere,box,torus}.ts */
-typedef enum rm_prim_type { RM_PRIM_SPHERE = 0, RM_PRIM_BOX = 1, RM_PRIM_TORUS = 2 } rm_prim_type;
+/* src/util/primitives/{sphere,box,torus,mandelbulb}.ts */
+typedef enum rm_prim_type { RM_PRIM_SPHERE = 0, RM_PRIM_BOX = 1, RM_PRIM_TORUS = 2, RM_PRIM_MANDELBULB = 3 } rm_prim_type;
 /* SDF operators (the classes under src/util/primitive_operations/).  A scene object is either a primitive or a tree of these
  * over primitives; trees are passed as a flat node array (any order, children referenced by index). */
 typedef enum rm_node_kind {
@@ -113,7 +113,8 @@ typedef struct rm_scene {
     int32_t n_prims;
     const uint8_t* type;         /* [n_prims] rm_prim_type */
     const float* world_to_local; /* [16*n_prims] column-major mat4, exactly Primitive.transform (primitive.ts:4,10) */
-    const double* params;        /* [4*n_prims] sphere: r | box: hx,hy,hz (f32-valued) | torus: R, r */
+    const double* params;        /* [4*n_prims] sphere: r | box: hx,hy,hz (f32-valued) | torus: R, r |
+                                    mandelbulb: power, iterations, enableAnimation (0/1), animationSpeed (mandelbulb.ts:11-15) */
     int32_t accel_kind;          /* rm_accel_kind */
     /* Optional host-built structure (e.g. walked out of the reference's own BVH/Octree objects).
      * If accel_kind != NONE and nodes == NULL the library builds it natively with a builder that is
@@ -137,7 +138,7 @@ typedef struct rm_scene {
 typedef struct rm_request {
     int32_t width, height;  /* full frame size */
     int32_t y_start, y_end; /* rows of this band; outputs are tile-local ((y-y_start)*width + x) */
-    double time;            /* Job.time -> Scene.updateTime (raymarcher.ts:59): drives AnimatedTranslate */
+    double time;            /* Job.time -> Scene.updateTime (raymarcher.ts:59): drives AnimatedTranslate and the Mandelbulb */
     float rot3[9];          /* column-major mat3 */
     float origin[3];
     int32_t algorithm;       /* rm_algorithm */
@@ -174,7 +175,7 @@ typedef struct rm_stats_t {
     uint32_t max_sdf, min_sdf, max_iters, min_iters;
     /* un-wrapped totals (throughput accounting: SDF evals/s) */
     uint64_t sum_sdf_full, sum_iters_full;
-    uint64_t evals_by_type[3]; /* un-wrapped primitive evaluations split sphere/box/torus */
+    uint64_t evals_by_type[3]; /* un-wrapped primitive evaluations split sphere/box/torus (mandelbulb evaluations: the rest) */
     uint64_t n_hit;            /* pixels with depth < MAX_DIST */
     double operator_flops;     /* operator-tree scenes: FLOPs of the operator nodes executed (transforms, twist, smooth min...) */
     double algorithmic_flops;  /* reference-equivalent work: every SDF call the reference counts x its FLOP count — general affine

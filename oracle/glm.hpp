@@ -103,6 +103,7 @@ inline void v3_transform_mat4(vec3& out, const vec3& a, const mat4& m) {
     out.e[2] = js::f32(r2);
 }
 
+inline void m4_scale(mat4& out, const mat4& a, const double v[3]);
 inline mat4 m4_create() {
     mat4 m{};
     m.e[0] = m.e[5] = m.e[10] = m.e[15] = 1.f;
@@ -243,6 +244,15 @@ inline void m4_from_rts(mat4& out, const double q[4], const double v[3], const d
     out.e[13] = js::f32(v[1]);
     out.e[14] = js::f32(v[2]);
     out.e[15] = 1;
+}
+
+// mat4.scale(out, a, v): columns 0..2 scaled, column 3 copied (gl-matrix 3.4.4)
+inline void m4_scale(mat4& out, const mat4& a, const double v[3]) {
+    mat4 r;
+    for (int c = 0; c < 3; ++c)
+        for (int k = 0; k < 4; ++k) r.e[4 * c + k] = js::f32(a[4 * c + k] * v[c]);
+    for (int k = 12; k < 16; ++k) r.e[k] = a.e[k];
+    out = r;
 }
 
 }  // namespace glm

@@ -95,6 +95,13 @@ inline double round(double x) {
 // float32 store that follows every use in the reference with probability ~2^-29.)
 inline double sin(double x) { return std::sin(x); }
 inline double cos(double x) { return std::cos(x); }
+// Math.atan2 / asin / pow / log (mandelbulb.ts): V8 uses its fdlibm port (ieee754::atan2 ...), < 1 ulp; the oracle calls
+// this container's libm.  The Mandelbulb's iteration stores z in a Float32Array every pass, which absorbs last-bit
+// differences with probability 1 - 2^-29 each; parity for that primitive is therefore stated as a pixel-agreement bar.
+inline double atan2(double y, double x) { return std::atan2(y, x); }
+inline double asin(double x) { return std::asin(x); }
+inline double pow(double x, double y) { return std::pow(x, y); }
+inline double log(double x) { return std::log(x); }
 
 // float32 store
 inline float f32(double x) { return (float)x; }

@@ -18,11 +18,16 @@ struct orc_scene {
 
 static Primitive prim_from_flat(int type, const float* m, const double* prm) {
     Primitive p;
-    p.type = type;
+    p.type = type == 3 ? (int)MANDELBULB : type;  // rm_prim_type 3 = mandelbulb: power, iterations, enableAnimation, animationSpeed
     for (int i = 0; i < 16; ++i) p.transform.e[i] = m[i];
     if (type == SPHERE) p.radius = prm[0];
     else if (type == BOX) p.halfSize = glm::v3_from(prm[0], prm[1], prm[2]);
-    else {
+    else if (type == 3) {
+        p.power = prm[0];
+        p.iterations = (int)prm[1];
+        p.enableAnimation = prm[2] != 0.0;
+        p.animationSpeed = prm[3];
+    } else {
         p.majorRadius = prm[0];
         p.minorRadius = prm[1];
     }
@@ -55,11 +60,16 @@ int orc_scene_n_prims(orc_scene* s) { return (int)s->scene.objects.size(); }
 void orc_scene_get_prims(orc_scene* s, uint8_t* type, float* w2l, double* params) {
     for (size_t i = 0; i < s->scene.objects.size(); ++i) {
         const Primitive& p = s->scene.objects[i];
-        type[i] = (uint8_t)p.type;
+        type[i] = (uint8_t)(p.type == MANDELBULB ? 3 : p.type);
         std::memcpy(w2l + 16 * i, p.transform.e, 16 * sizeof(float));
         double* q = params + 4 * i;
         q[0] = q[1] = q[2] = q[3] = 0;
-        if (p.type == SPHERE) q[0] = p.radius;
+        if (p.type == MANDELBULB) {
+            q[0] = p.power;
+            q[1] = p.iterations;
+            q[2] = p.enableAnimation ? 1.0 : 0.0;
+            q[3] = p.animationSpeed;
+        } else if (p.type == SPHERE) q[0] = p.radius;
         else if (p.type == BOX) {
             q[0] = p.halfSize[0];
             q[1] = p.halfSize[1];
@@ -112,7 +122,7 @@ void orc_scene_set_tree(orc_scene* s, const uint8_t* type, const float* w2l, con
 }
 static void tree_count(const Primitive& p, int& nNodes, int& nPrims) {
     nNodes++;
-    if (p.type <= TORUS) nPrims++;
+    if (p.type <= TORUS || p.type == MANDELBULB) nPrims++;
     if (p.a) tree_count(*p.a, nNodes, nPrims);
     if (p.b) tree_count(*p.b, nNodes, nPrims);
 }
@@ -121,10 +131,15 @@ void orc_scene_tree_counts(orc_scene* s, int* nNodes, int* nPrims) {
     for (auto& p : s->scene.objects) tree_count(p, *nNodes, *nPrims);
 }
 static void flat_prim(const Primitive& p, uint8_t* type, float* w2l, double* q) {
-    *type = (uint8_t)p.type;
+    *type = (uint8_t)(p.type == MANDELBULB ? 3 : p.type);
     std::memcpy(w2l, p.transform.e, 16 * sizeof(float));
     q[0] = q[1] = q[2] = q[3] = 0;
-    if (p.type == SPHERE) q[0] = p.radius;
+    if (p.type == MANDELBULB) {
+        q[0] = p.power;
+        q[1] = p.iterations;
+        q[2] = p.enableAnimation ? 1.0 : 0.0;
+        q[3] = p.animationSpeed;
+    } else if (p.type == SPHERE) q[0] = p.radius;
     else if (p.type == BOX) {
         q[0] = p.halfSize[0];
         q[1] = p.halfSize[1];
@@ -140,7 +155,7 @@ static int tree_flat(const Primitive& p, orc_op_node* nodes, uint8_t* type, floa
     std::memset(&nd, 0, sizeof(nd));
     nd.child[0] = nd.child[1] = nd.prim = -1;
     std::memcpy(nd.transform, p.transform.e, sizeof(nd.transform));
-    if (p.type <= TORUS) {
+    if (p.type <= TORUS || p.type == MANDELBULB) {
         nd.kind = 0;
         nd.prim = nextPrim++;
         flat_prim(p, type + nd.prim, w2l + 16 * nd.prim, params + 4 * nd.prim);

@@ -36,7 +36,8 @@ enum PrimType {
     SMOOTH_UNION = 5,        // smoothUnion.ts
     SMOOTH_SUBTRACTION = 6,  // smoothSubstraction.ts
     REPETITION = 7,          // repetition.ts
-    ANIMATED_TRANSLATE = 8   // animatedTranslate.ts
+    ANIMATED_TRANSLATE = 8,  // animatedTranslate.ts
+    MANDELBULB = 9           // primitives/mandelbulb.ts (a leaf; rm_prim_type 3 in the flat arrays)
 };
 
 // primitive.ts:3-44 + sphere.ts / box.ts / torus.ts + the six operator classes.  One tagged struct instead
@@ -53,7 +54,11 @@ struct Primitive {
     double smoothness = 0;                    // smoothUnion.ts:7 / smoothSubstraction.ts:7
     vec3 spacing = glm::v3_create();          // repetition.ts:6 (the caller's vec3, f32)
     vec3 direction = glm::v3_create();        // animatedTranslate.ts:9 (normalised, f32)
-    double amplitude = 0, speed = 0, time = 0;  // animatedTranslate.ts:10-12
+    double amplitude = 0, speed = 0, time = 0;  // animatedTranslate.ts:10-12 (time also: mandelbulb.ts:16)
+    double power = 8.0;                         // mandelbulb.ts:12-15
+    int iterations = 9;
+    bool enableAnimation = true;
+    double animationSpeed = -0.2;
 
     // primitive.ts:20-30 and the operator overrides
     vec3 getWorldPosition() const {
@@ -81,6 +86,7 @@ struct Primitive {
             case TWIST: return a->getLocalBoundingRadius();                       // twist.ts:38-41
             case SMOOTH_SUBTRACTION: return a->getLocalBoundingRadius();          // smoothSubstraction.ts:36-39
             case REPETITION: return js::kInf;                                     // repetition.ts:31-34
+            case MANDELBULB: return 2.5;                                          // mandelbulb.ts:80-83
             case ANIMATED_TRANSLATE: return a->getLocalBoundingRadius() + amplitude;  // animatedTranslate.ts:50-53
             default: {                                                            // smoothUnion.ts:37-48
                 double r1 = a->getLocalBoundingRadius(), r2 = b->getLocalBoundingRadius();
@@ -115,6 +121,26 @@ struct Primitive {
                 double qx = std::sqrt(x * x + z * z) - majorRadius;
                 double qy = y;
                 return std::sqrt(qx * qx + qy * qy) - minorRadius;
+            }
+            case MANDELBULB: {  // mandelbulb.ts:38-78
+                vec3 p = glm::v3_from(l[0], l[2], l[1]);  // p.xyz = p.xzy
+                vec3 z = p;
+                double dr = 1.0, r = 0.0;
+                for (int i = 0; i < iterations; ++i) {
+                    r = glm::v3_length(z);
+                    if (r > 2.0) break;
+                    double theta = js::atan2(z[1], z[0]);
+                    double phi = js::asin(z[2] / r);
+                    if (enableAnimation) phi += time * animationSpeed;
+                    dr = js::pow(r, power - 1.0) * dr * power + 1.0;
+                    r = js::pow(r, power);  // NB: the loop variable r now holds r^power (it is what the return uses after the last pass)
+                    theta = theta * power;
+                    phi = phi * power;
+                    z.e[0] = js::f32(r * js::cos(theta) * js::cos(phi) + p[0]);
+                    z.e[1] = js::f32(r * js::sin(theta) * js::cos(phi) + p[1]);
+                    z.e[2] = js::f32(r * js::sin(phi) + p[2]);
+                }
+                return 0.5 * js::log(r) * r / dr;
             }
             case ROUND:  // round.ts:15-24
                 return a->sdf(backToWorld(l)) - radius;
@@ -167,7 +193,7 @@ struct Primitive {
     // primitive.ts:42-44 and the overrides (animatedTranslate.ts:30-32 does NOT forward to its child)
     void setTime(double t) {
         switch (type) {
-            case ANIMATED_TRANSLATE: time = t; break;
+            case ANIMATED_TRANSLATE: case MANDELBULB: time = t; break;  // animatedTranslate.ts:30-32, mandelbulb.ts:33-35
             case ROUND: case TWIST: case REPETITION: a->setTime(t); break;
             case SMOOTH_UNION: case SMOOTH_SUBTRACTION: a->setTime(t); b->setTime(t); break;
             default: break;
@@ -635,7 +661,22 @@ inline Primitive createAnimatedTranslate(const Primitive& prim, const vec3& dire
     return p;
 }
 
-// presets 0-12, 14-18 (sceneManager.ts:102-356).  Returns false for preset 13 (Mandelbulb: SURVEY.md §8f row 4).
+// sceneManager.ts:51-71
+inline Primitive createMandelbulb(double x, double y, double z, double power, int iterations, bool enableAnimation, double animationSpeed,
+                                  const vec3* rot = nullptr) {
+    Primitive p;
+    p.type = MANDELBULB;
+    p.transform = getTransform(x, y, z, rot);
+    const double half[3] = {0.5, 0.5, 0.5};
+    glm::m4_scale(p.transform, p.transform, half);
+    p.power = power;
+    p.iterations = iterations;
+    p.enableAnimation = enableAnimation;
+    p.animationSpeed = animationSpeed;
+    return p;
+}
+
+// all 19 presets (sceneManager.ts:102-356)
 inline bool makePreset(int idx, std::vector<Primitive>& out) {
     out.clear();
     switch (idx) {
@@ -703,6 +744,7 @@ inline bool makePreset(int idx, std::vector<Primitive>& out) {
             out.push_back(createSmoothUnion(createAnimatedTranslate(createSphere(0, 0, 0, 1), glm::v3_from(1, 0, 0), 3.0, 0.005),
                                             createSphere(0, 0, 0, 1), 0.2));
             break;
+        case 13: out.push_back(createMandelbulb(0, 0, 0, 8, 80, true, -0.0001)); break;  // :247-253 Mandelbulb [A]
         case 14: {  // :254-262 Twisted Torus
             vec3 rot = glm::v3_from(-M_PI / 2, 0, 0);
             out.push_back(createTwist(createTorus(0, 0, 0, 1.3, &rot), 3));

@@ -146,3 +146,60 @@ def test_operator_full_size_properties(fast_worker, val_worker):
     bot = val_worker.on_message(make_job(W, H, 17, "BVH", "sphere-tracer", 0.15, 0.5, 500, H))
     assert np.array_equal(np.concatenate([top.sdfEval, bot.sdfEval]), b.sdfEval)
     assert np.array_equal(np.concatenate([top.normal, bot.normal]), b.normal)
+
+
+# ------------------------------------------------------------------------------------------ Mandelbulb
+def _agree(f, ref):
+    same = (f.depth == ref.depth) & (f.sdfEval == ref.sdfEval) & (f.iters == ref.iters)
+    same &= (f.normal.reshape(-1, 3) == ref.normal.reshape(-1, 3)).all(1)
+    return float(same.mean())
+
+
+@pytest.mark.parametrize("accel", ["None", "Octree", "BVH"])
+@pytest.mark.parametrize("time", [0.0, 5000.0])
+def test_mandelbulb_preset_agreement(val_worker, oracle, accel, time):
+    """Preset 13.  atan2 / asin / pow / log / sin / cos are libm calls on both sides (CUDA vs glibc, each <= 1-2 ulp) inside a
+    chaotic iteration, so the bar is the north star's pixel agreement (>= 99.9 % of pixels identical in every plane), not
+    bit-exactness; in practice the frames below differ in at most a handful of pixels."""
+    W, H = 128, 72
+    ref = _oracle(oracle, 13, accel, 0.3, 0.6, time=time).render(W, H, "sphere-tracer")
+    f = val_worker.on_message(make_job(W, H, 13, accel, "sphere-tracer", 0.3, 0.6, time=time), extras=True)
+    assert (ref.depth_f64 < 10).sum() > 500, "the fractal should be visible"
+    assert np.array_equal(f.depth_f64 < 10, ref.depth_f64 < 10) or _agree(f, ref) >= PIXEL_AGREEMENT
+    assert _agree(f, ref) >= PIXEL_AGREEMENT
+
+
+@pytest.mark.parametrize("alg", ALGS)
+def test_mandelbulb_all_algorithms(val_worker, oracle, alg):
+    W, H = 96, 54
+    ref = _oracle(oracle, 13, "None").render(W, H, alg)
+    f = val_worker.on_message(make_job(W, H, 13, "None", alg), extras=True)
+    assert _agree(f, ref) >= PIXEL_AGREEMENT
+
+
+def test_mandelbulb_default_build_and_animation(fast_worker, oracle):
+    W, H = 128, 72
+    ref = _oracle(oracle, 13, "BVH", 0.1, 0.4).render(W, H, "sphere-tracer")
+    f = fast_worker.on_message(make_job(W, H, 13, "BVH", "sphere-tracer", 0.1, 0.4), shader="phong", extras=True)
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"pixel agreement {px} (depth-only among hits {dz})"
+    a = fast_worker.on_message(make_job(64, 36, 13, "None", time=0.0))
+    b = fast_worker.on_message(make_job(64, 36, 13, "None", time=20000.0))  # phi += time * -0.0001 per inner iteration
+    assert not np.array_equal(a.depth, b.depth)
+
+
+def test_mandelbulb_inside_an_operator_tree(oracle):
+    """A Mandelbulb leaf under Round + SmoothUnion: the leaf evaluator is shared with the tree interpreter."""
+    W, H = 96, 54
+    objs = [sm.create_smooth_union(sm.create_round(sm.create_mandelbulb(0.4, 0, 0, 8, 12, True, -0.0001), 0.02),
+                                   sm.create_sphere(-1.0, 0.2, 0.0, 0.4), 0.1)]
+    pl = sm.flatten(objs)
+    t, m, q = pl.arrays()
+    ref = oracle.OracleScene().set_tree(t, m, q, pl.op_nodes, pl.object_root).build_accel("Octree").set_camera(0.0, 0.3).set_time(123.0).render(W, H)
+    ctx = rb.Context(0, validate_fp64=True)
+    ctx.upload_scene(t, m, q, "Octree", op_nodes=pl.op_nodes, object_root=pl.object_root)
+    cam = Camera()
+    cam.set_angles(0.0, 0.3)
+    f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), time=123.0), extras=True)
+    assert _agree(f, ref) >= PIXEL_AGREEMENT
+    ctx.close()

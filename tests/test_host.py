@@ -75,10 +75,12 @@ def test_presets_match_oracle_bitwise(oracle, idx):
     assert np.array_equal(bits(q), bits(oq))
 
 
-def test_mandelbulb_preset_is_rejected():
-    with pytest.raises(sm.UnsupportedPreset):
-        sm.get_preset(13)
-    assert 13 not in sm.SUPPORTED_PRESETS and len(sm.SUPPORTED_PRESETS) == 18
+def test_every_reference_preset_is_supported():
+    assert sm.SUPPORTED_PRESETS == tuple(range(19)) == tuple(range(sm.get_preset_count()))
+    t, m, q = sm.get_preset(13).arrays()  # Mandelbulb [A]: a leaf primitive with a scaled transform (sceneManager.ts:62-63)
+    assert list(t) == [sm.MANDELBULB] and list(q[0]) == [8.0, 80.0, 1.0, -0.0001] and m[0][0] == 0.5
+    with pytest.raises(IndexError):
+        sm.get_preset(19)
 
 
 def test_synthetic_scene_matches_oracle_bitwise(oracle):
