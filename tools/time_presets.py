@@ -1,5 +1,8 @@
 """Kernel time of every reference preset (all 19) at a given resolution: python tools/time_presets.py [W H] (needs a GPU)."""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import cpu_raymarcher_b200 as rb
 from cpu_raymarcher_b200 import scene_manager as sm

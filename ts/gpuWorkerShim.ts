@@ -13,6 +13,7 @@ import { Camera } from '../../reference/src/util/camera';
 import { Sphere } from '../../reference/src/util/primitives/sphere';
 import { Box } from '../../reference/src/util/primitives/box';
 import { Torus } from '../../reference/src/util/primitives/torus';
+import { Mandelbulb } from '../../reference/src/util/primitives/mandelbulb';
 import { Primitive } from '../../reference/src/util/primitives/primitive';
 import { Round } from '../../reference/src/util/primitive_operations/round';
 import { Twist } from '../../reference/src/util/primitive_operations/twist';
@@ -42,12 +43,13 @@ function flattenObjects(index: number, objects: Primitive[]) {
     const me = nodes.length;
     const rec = { kind: 0, child: [-1, -1], prim: -1, p: [0, 0, 0, 0], dir: [0, 0, 0, 0], transform: o.transform as Float32Array };
     nodes.push(rec);
-    if (o instanceof Sphere || o instanceof Box || o instanceof Torus) {
+    if (o instanceof Sphere || o instanceof Box || o instanceof Torus || o instanceof Mandelbulb) {
       rec.prim = type.length;
       w2l.push(...(o.transform as Float32Array));                    // Primitive.transform (primitive.ts:4,10)
       if (o instanceof Sphere) { type.push(0); params.push(o.radius, 0, 0, 0); }
       else if (o instanceof Box) { type.push(1); params.push(o.halfSize[0], o.halfSize[1], o.halfSize[2], 0); }
-      else { type.push(2); params.push(o.majorRadius, o.minorRadius, 0, 0); }
+      else if (o instanceof Torus) { type.push(2); params.push(o.majorRadius, o.minorRadius, 0, 0); }
+      else { type.push(3); params.push(o.power, o.iterations, o.enableAnimation ? 1 : 0, o.animationSpeed); }
     } else if (o instanceof Round) { rec.kind = 1; rec.p[0] = o.radius; rec.child[0] = visit(o.primitive); }
     else if (o instanceof Twist) { rec.kind = 2; rec.p[0] = o.twistAmount; rec.child[0] = visit(o.primitive); }
     else if (o instanceof SmoothUnion) { rec.kind = 3; rec.p[0] = o.smoothness; rec.child = [visit(o.prim1), visit(o.prim2)]; }
@@ -60,7 +62,7 @@ function flattenObjects(index: number, objects: Primitive[]) {
     return me;
   };
   const roots = objects.map(visit);
-  const flat = objects.every(o => o instanceof Sphere || o instanceof Box || o instanceof Torus);
+  const flat = objects.every(o => o instanceof Sphere || o instanceof Box || o instanceof Torus || o instanceof Mandelbulb);
   const buf = new ArrayBuffer(NODE_BYTES * nodes.length), dv = new DataView(buf);
   nodes.forEach((n, i) => {
     const o = NODE_BYTES * i;
