@@ -179,7 +179,8 @@ def _golden_cases():
 def test_validation_matches_committed_golden(val_worker, case):
     g = np.load(os.path.join(GOLDEN, case["name"] + ".npz"))
     job = make_job(case["W"], case["H"], case["preset"], case["accel"], case["alg"], case["pitch"], case["yaw"],
-                   synthetic=tuple(case["synthetic"]) if case.get("synthetic") else None, step=case["step"], over=case["over"])
+                   synthetic=tuple(case["synthetic"]) if case.get("synthetic") else None, step=case["step"], over=case["over"],
+                   time=case.get("time", 0.0))
     f = val_worker.on_message(job, shader="phong", shader_analytics="sdf-heatmap", extras=True)
     for k in ("depth", "normal", "sdfEval", "iters"):
         assert np.array_equal(getattr(f, k), g[k]), k

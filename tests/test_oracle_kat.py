@@ -145,7 +145,7 @@ def test_oracle_matches_committed_golden(oracle, case):
         s.load_synthetic(*case["synthetic"])
     else:
         s.load_preset(case["preset"])
-    s.build_accel(case["accel"]).set_camera(case["pitch"], case["yaw"])
+    s.build_accel(case["accel"]).set_camera(case["pitch"], case["yaw"]).set_time(case.get("time", 0.0))
     f = s.render(case["W"], case["H"], case["alg"], step_size=case["step"], overshoot=case["over"])
     for k in ("depth", "normal", "sdfEval", "iters"):
         assert np.array_equal(getattr(f, k), g[k]), k

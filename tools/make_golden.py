@@ -15,9 +15,9 @@ os.makedirs(OUT, exist_ok=True)
 cases = []
 
 
-def add(name, preset, accel, alg, W=48, H=32, pitch=0.0, yaw=0.0, step=0.1, over=1.2, synthetic=None):
+def add(name, preset, accel, alg, W=48, H=32, pitch=0.0, yaw=0.0, step=0.1, over=1.2, synthetic=None, time=0.0):
     cases.append(dict(name=name, preset=preset, accel=accel, alg=alg, W=W, H=H, pitch=pitch, yaw=yaw, step=step, over=over,
-                      synthetic=synthetic))
+                      synthetic=synthetic, time=time))
 
 
 add("cfg1_sphere_none_st", 0, "None", "sphere-tracer", 64, 64)
@@ -32,6 +32,16 @@ add("boxes_octree_v3", 9, "Octree", "adaptive-step-v3", yaw=2.0, pitch=-0.4, ove
 add("atom_bvh_fixed_small_step", 4, "BVH", "fixed-step", step=0.03)
 add("random_octree_adaptive", 1, "Octree", "adaptive-step", yaw=4.0)
 add("spherecube_bvh_v3", 8, "BVH", "adaptive-step-v3", yaw=0.7)
+# SDF operator presets (src/util/primitive_operations): one per operator scene, all three structures and several algorithms
+add("op_roundedbox_none_st", 6, "None", "sphere-tracer", yaw=0.4, pitch=0.2)
+add("op_smoothunion_bvh_v2", 10, "BVH", "adaptive-step-v2", yaw=1.1)
+add("op_smoothsub_octree_st", 11, "Octree", "sphere-tracer", yaw=0.6, pitch=0.3)
+add("op_animated_bvh_st_t314", 12, "BVH", "sphere-tracer", time=314.0)
+add("op_twistedtorus_none_fixed", 14, "None", "fixed-step", yaw=0.3)
+add("op_infinitespheres_bvh_st", 15, "BVH", "sphere-tracer", yaw=0.2, pitch=0.1)
+add("op_screw_octree_v3", 16, "Octree", "adaptive-step-v3", yaw=2.2)
+add("op_chicken_bvh_st", 17, "BVH", "sphere-tracer", yaw=0.8, pitch=0.2)
+add("op_67_none_adaptive", 18, "None", "adaptive-step", yaw=0.1)
 
 for c in cases:
     s = po.OracleScene()
@@ -39,7 +49,7 @@ for c in cases:
         s.load_synthetic(*c["synthetic"])
     else:
         s.load_preset(c["preset"])
-    s.build_accel(c["accel"]).set_camera(c["pitch"], c["yaw"])
+    s.build_accel(c["accel"]).set_camera(c["pitch"], c["yaw"]).set_time(c["time"])
     f = s.render(c["W"], c["H"], c["alg"], step_size=c["step"], overshoot=c["over"])
     np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), depth=f.depth, normal=f.normal, sdfEval=f.sdfEval, iters=f.iters,
                         depth_f64=f.depth_f64, sdf_full=f.sdf_full,
