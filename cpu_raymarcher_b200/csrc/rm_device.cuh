@@ -47,6 +47,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RM_MIN_BLOCKS_OTHER
 #define RM_MIN_BLOCKS_OTHER 8
 #endif
+#ifndef RM_TC_WARPS
+#define RM_TC_WARPS 16  // warps per CTA of the translation-only-sphere BVH kernel (one CTA per SM; the first 16 run the tensor-core sweeps)
+#endif
 
 enum Phase : int {
     PH_IDLE = 0,
@@ -712,7 +715,8 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
     const TcCtx tc = tcRef;  // registers: the asm memory clobbers below would otherwise force reloads from local memory
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wq = warp & 3;
     const int row = tid & 127, grp = tid >> 7;
-    const bool valid = (unsigned)row < nBatch;
+    const bool sweeper = tid < 4 * kTcBlock;  // the first 16 warps: four 4-warp groups; any further warps only drain work items
+    const bool valid = sweeper && (unsigned)row < nBatch;
 #ifdef RM_PHASE_TIMING
     long long tcT[4] = {0, 0, 0, 0}, tcMark = clock64();
 #define RM_TC_MARK(i)                     \
@@ -790,7 +794,7 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
             for (int b = 0; b < kTcGroups && b < nB; ++b) mma(b);
         }
         __syncwarp();
-        const int b0 = (int)(((unsigned)grp - gBase) % (unsigned)kTcGroups);  // this group's first block: (gBase + b0) % 4 == grp
+        const int b0 = sweeper ? (int)(((unsigned)grp - gBase) % (unsigned)kTcGroups) : nB;  // this group's first block: (gBase + b0) % 4 == grp
         for (int b = b0; b < nB; b += kTcGroups) {
             const unsigned u = (gBase + (unsigned)b) / kTcGroups;
             mbar_wait(barTFullG, u & 1u);
@@ -881,8 +885,10 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
         }
     });
     RM_TC_MARK(0);
-    partBest[grp * 128 + row] = sMin;
-    partCode[grp * 128 + row] = jMin;
+    if (sweeper) {
+        partBest[grp * 128 + row] = sMin;
+        partCode[grp * 128 + row] = jMin;
+    }
     __syncthreads();
     if (grp == 0) {
 #pragma unroll
@@ -897,7 +903,7 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
     __syncthreads();
     drain_items(nBatch);
     // ub: the fp32 SDF of an actual sphere — nothing farther than this can be the nearest
-    float ub = float_unflip((uint32_t)(shKey[row] >> 32));
+    float ub = float_unflip((uint32_t)(shKey[row] >> 32));  // (row = tid & 127: defined for every thread)
     ub = ub + fabsf(ub) * 1.0e-6f + 1.0e-7f;
     __syncthreads();  // every thread has read the keys / the first item round before the list is rebuilt
     RM_TC_MARK(1);
@@ -967,8 +973,10 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
             code = __ldg(P.scene.cl_perm + idx);
         }
     }
-    partBest[grp * 128 + row] = best;
-    partCode[grp * 128 + row] = code;
+    if (sweeper) {
+        partBest[grp * 128 + row] = best;
+        partCode[grp * 128 + row] = code;
+    }
 }
 
 template <int PK>
@@ -1569,17 +1577,17 @@ RM_DEV unsigned long long warp_sum_u64(unsigned long long v) {
 
 template <class NP, int ACCEL, int PK>
 struct CtaShape {
-    static constexpr int kWarps = (!NP::kExact && ACCEL == RM_ACCEL_BVH) ? (PK == PK_TSPHERE ? 16 : 8) : 4;
+    static constexpr int kWarps = (!NP::kExact && ACCEL == RM_ACCEL_BVH) ? (PK == PK_TSPHERE ? RM_TC_WARPS : 8) : 4;
 };
 template <class NP, int ACCEL, int PK>
 __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
-                                  (ACCEL == RM_ACCEL_BVH) ? (RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL, PK>::kWarps : RM_MIN_BLOCKS_OTHER)
+                                  (ACCEL == RM_ACCEL_BVH) ? ((RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL, PK>::kWarps > 0 ? (RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL, PK>::kWarps : 1) : RM_MIN_BLOCKS_OTHER)
     render_kernel(const __grid_constant__ RenderParams P) {
     constexpr int kWarpsPerCta = CtaShape<NP, ACCEL, PK>::kWarps;
     constexpr int kQueueCap = kWarpsPerCta * 32;  // each thread has at most one request outstanding
     constexpr unsigned kBatch = (kWarpsPerCta >= 8) ? 64u : 32u;  // requests served per cooperative pass (FFMA search)
     // translation-only spheres behind a BVH: the pass runs on the tensor cores, 128 requests at a time (tc_pass)
-    constexpr bool kTC = !NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE && kWarpsPerCta == 16;
+    constexpr bool kTC = !NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE && kWarpsPerCta >= 16;
     constexpr unsigned kBatchMax = kTC ? (unsigned)kTcBlock : kBatch;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
