@@ -47,6 +47,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RM_MIN_BLOCKS_OTHER
 #define RM_MIN_BLOCKS_OTHER 8
 #endif
+#ifndef RM_TC_BATCH
+#define RM_TC_BATCH 128  // requests that trigger a tensor-core pass (<= 128)
+#endif
 #ifndef RM_TC_WARPS
 #define RM_TC_WARPS 16  // warps per CTA of the translation-only-sphere BVH kernel (one CTA per SM; the first 16 run the tensor-core sweeps)
 #endif
@@ -1669,7 +1672,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     // the shared queue pays off when one all-primitives pass is much more expensive than a march step
     const bool useQueue = !NP::kExact && (ACCEL == RM_ACCEL_BVH) && P.scene.n_prims >= 256;
     const bool useTC = kTC && useQueue && P.scene.tc_tiles != nullptr;
-    const unsigned batchCap = useTC ? kBatchMax : kBatch;
+    const unsigned batchCap = useTC ? min(kBatchMax, (unsigned)RM_TC_BATCH) : kBatch;
     TcCtx tc;
     if constexpr (kTC) {
         if (useTC) {  // CTA-uniform
