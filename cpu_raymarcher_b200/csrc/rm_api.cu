@@ -731,16 +731,19 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             // fast path: locate leaf boxes through a uniform grid instead of descending the tree
             LeafGrid grid;
             build_leaf_grid(bvh, grid);
-            static_assert(sizeof(LeafRef) == sizeof(uint3), "LeafRef layout");
             for (int k = 0; k < 3; ++k) {
                 ds.grid_dims[k] = grid.dims[k];
                 ds.grid_origin[k] = grid.origin[k];
                 ds.grid_inv[k] = grid.inv_cell[k];
                 ds.grid_cell[k] = grid.cell[k];
             }
-            if ((rc = upload(c, (const uint3*)grid.leaves.data(), grid.leaves.size(), &ds.grid_leaves))) return rc;
+            std::vector<uint4> entries(grid.cell_leaf.size());
+            for (size_t e = 0; e < entries.size(); ++e) {
+                const LeafRef& lr = grid.leaves[(size_t)grid.cell_leaf[e]];
+                entries[e] = make_uint4((uint32_t)lr.node, lr.lo, lr.hi, 0u);
+            }
             if ((rc = upload(c, grid.cell_start.data(), grid.cell_start.size(), &ds.grid_cell_start))) return rc;
-            if ((rc = upload(c, grid.cell_leaf.data(), grid.cell_leaf.size(), &ds.grid_cell_leaf))) return rc;
+            if ((rc = upload(c, entries.data(), entries.size(), &ds.grid_entries))) return rc;
             CU(c, cudaStreamSynchronize(c->stream));  // `grid` goes out of scope
         }
         if ((rc = upload(c, bvh.data(), bvh.size(), &ds.bvh))) return rc;

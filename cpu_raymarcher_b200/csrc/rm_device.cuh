@@ -1371,7 +1371,7 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
     const uint32_t e0 = sc.grid_cell_start[c], e1 = sc.grid_cell_start[c + 1];
     const bool hasPrev = lz.prev[0] >= 0;
     for (uint32_t e = e0; e < e1; ++e) {
-        const uint3 lr = sc.grid_leaves[sc.grid_cell_leaf[e]];
+        const uint4 lr = __ldg(sc.grid_entries + e);
         if (hasPrev && cell_in_range(lr.y, lr.z, lz.prev[0], lz.prev[1], lz.prev[2])) continue;  // seen in an earlier cell
         const rm_bvh_node* nd = sc.bvh + lr.x;
         double tE, tX;
@@ -2032,7 +2032,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                         const size_t c = ((size_t)gz * P.scene.grid_dims[1] + gy) * P.scene.grid_dims[0] + gx;
                         const uint32_t e0 = P.scene.grid_cell_start[c], e1 = P.scene.grid_cell_start[c + 1];
                         for (uint32_t e = e0; e < e1; ++e) {
-                            const rm_bvh_node* nd = nodes + P.scene.grid_leaves[P.scene.grid_cell_leaf[e]].x;
+                            const rm_bvh_node* nd = nodes + __ldg(P.scene.grid_entries + e).x;
                             if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
                             const int pc = nd->prim_count;
                             leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);

@@ -86,9 +86,9 @@ struct DevScene {
     const uint32_t* obj_flops;   // per object: FLOPs of its operator instructions per call
     uint32_t all_op_flops;       // sum of obj_flops (one pass over every object)
     // uniform grid over the BVH leaf boxes (fast path; see rm_host.h LeafGrid)
-    const uint3* grid_leaves;         // per leaf ordinal: x = node index, y = packed lo cell, z = packed hi cell
     const uint32_t* grid_cell_start;  // [nx*ny*nz + 1]
-    const int32_t* grid_cell_leaf;    // leaf ordinals, ascending within a cell
+    const uint4* grid_entries;        // per cell entry (ascending leaf ordinal within a cell): x = BVH node index of the leaf,
+                                      // y / z = packed lo / hi cell of the leaf's range — self-contained, one load per entry
     int32_t grid_dims[3];
     float grid_origin[3], grid_inv[3], grid_cell[3];
 };
