@@ -471,6 +471,21 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float (&q)[NQ][3], War
         bulk_g2s(ws.bufAddr[sgi], rec + (size_t)c * 4 * kChunkF4, bytes, ws.bar[sgi]);
     };
     const bool resident = ws.resident && first == 0 && stride == 1;
+    if (resident) {
+        // tiny scenes (<= 4 chunks, staged once per kernel): every sphere's SDF straight from shared memory, no pipeline,
+        // no screen — the per-query set-up of the streamed search would cost more than the handful of evaluations
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            best[k] = 10.f;
+            code[k] = -1;
+        }
+        for (int c = 0; c < nChunks; ++c) {
+            const uint32_t ch = ws.bufAddr[0] + (unsigned)kChunkBytes * (unsigned)c;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) chunk_exact_smem(ch, c * 32, min(32, P.scene.n_prims - c * 32), q[k], best[k], code[k]);
+        }
+        return;
+    }
     float a2[NQ][3], qq[NQ], E[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
