@@ -340,6 +340,17 @@ def test_fast_path_cluster_screen_sizes(fast_worker, oracle, n):
             assert st["executed_flops"] < st["algorithmic_flops"]
 
 
+@pytest.mark.parametrize("W,H,y0,y1", [(1, 1, 0, 1), (8, 4, 0, 4), (9, 5, 0, 5), (33, 17, 3, 11), (640, 3, 1, 2)])
+def test_fast_path_cluster_screen_tiny_frames_and_bands(fast_worker, oracle, W, H, y0, y1):
+    """Frames with fewer pixels than one CTA has lanes (idle warps must still join and leave the cooperative passes)."""
+    syn = (1500, 0x5EED0001)
+    ref = _oracle_scene(oracle, 1, "BVH", 0.1, 0.2, synthetic=syn).render(W, H, "sphere-tracer", y_start=y0, y_end=y1)
+    f = fast_worker.on_message(make_job(W, H, 1, "BVH", "sphere-tracer", 0.1, 0.2, y0, y1, synthetic=syn), extras=True)
+    assert f.depth.size == W * (y1 - y0)
+    assert np.array_equal(f.sdfEval, ref.sdfEval) and np.array_equal(f.iters, ref.iters)
+    assert np.array_equal(f.depth, ref.depth)
+
+
 @pytest.mark.parametrize("alg", ["fixed-step", "adaptive-step-v3"])
 def test_fast_path_cluster_screen_other_algorithms(fast_worker, oracle, alg):
     W, H = 80, 45
