@@ -737,13 +737,14 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
                 ds.grid_inv[k] = grid.inv_cell[k];
                 ds.grid_cell[k] = grid.cell[k];
             }
-            std::vector<uint4> entries(grid.cell_leaf.size());
-            for (size_t e = 0; e < entries.size(); ++e) {
-                const LeafRef& lr = grid.leaves[(size_t)grid.cell_leaf[e]];
-                entries[e] = make_uint4((uint32_t)lr.node, lr.lo, lr.hi, 0u);
-            }
+            std::vector<uint32_t> cellNode(grid.cell_leaf.size());
+            for (size_t e = 0; e < cellNode.size(); ++e) cellNode[e] = (uint32_t)grid.leaves[(size_t)grid.cell_leaf[e]].node;
             if ((rc = upload(c, grid.cell_start.data(), grid.cell_start.size(), &ds.grid_cell_start))) return rc;
-            if ((rc = upload(c, entries.data(), entries.size(), &ds.grid_entries))) return rc;
+            if ((rc = upload(c, cellNode.data(), cellNode.size(), &ds.grid_cell_node))) return rc;
+            if (grid.dir_ok) {
+                if ((rc = upload(c, reinterpret_cast<const uint4*>(grid.cell_dir.data()), grid.cell_dir.size(), &ds.grid_cell_dir))) return rc;
+                if ((rc = upload(c, grid.dir_node.data(), grid.dir_node.size(), &ds.grid_dir_node))) return rc;
+            }
             CU(c, cudaStreamSynchronize(c->stream));  // `grid` goes out of scope
         }
         if ((rc = upload(c, bvh.data(), bvh.size(), &ds.bvh))) return rc;

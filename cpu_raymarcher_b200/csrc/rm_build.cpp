@@ -266,6 +266,41 @@ void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
             for (int y = lo[1]; y <= hi[1]; ++y)
                 for (int x = lo[0]; x <= hi[0]; ++x) g.cell_leaf[fill[((size_t)z * g.dims[1] + y) * g.dims[0] + x]++] = (int32_t)li;
     }
+    // ---- direction lists
+    static_assert(sizeof(LeafGrid::CellDir) == 16, "CellDir is one 16-byte load");
+    auto for_face = [&](const LeafRef& lr, int k, auto&& fn) {
+        int lo[3] = {(int)(lr.lo & 255), (int)((lr.lo >> 8) & 255), (int)((lr.lo >> 16) & 255)};
+        int hi[3] = {(int)(lr.hi & 255), (int)((lr.hi >> 8) & 255), (int)((lr.hi >> 16) & 255)};
+        const int a = k >> 1;
+        if (k & 1) lo[a] = hi[a];  // step in -a: the range starts at its hi face
+        else hi[a] = lo[a];        // step in +a: at its lo face
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) fn(((size_t)z * g.dims[1] + y) * g.dims[0] + x);
+    };
+    std::vector<uint32_t> dcount(nCells * 6, 0u);
+    for (size_t li = 0; li < g.leaves.size(); ++li)
+        for (int k = 0; k < 6; ++k) for_face(g.leaves[li], k, [&](size_t c) { dcount[c * 6 + k]++; });
+    g.cell_dir.resize(nCells);
+    std::vector<uint32_t> dfill(nCells * 6, 0u);
+    uint64_t total = 0;
+    for (size_t c = 0; c < nCells; ++c) {
+        g.cell_dir[c].base = (uint32_t)total;
+        for (int k = 0; k < 6; ++k) {
+            if (dcount[c * 6 + k] > 65535u) g.dir_ok = false;
+            g.cell_dir[c].cnt[k] = (uint16_t)std::min(dcount[c * 6 + k], 65535u);
+            dfill[c * 6 + k] = (uint32_t)total;
+            total += dcount[c * 6 + k];
+        }
+    }
+    if (total > 0xFFFFFFFFull) g.dir_ok = false;
+    if (g.dir_ok) {
+        g.dir_node.assign((size_t)total, 0u);
+        for (size_t li = 0; li < g.leaves.size(); ++li)  // ascending leaf ordinal within every list
+            for (int k = 0; k < 6; ++k) for_face(g.leaves[li], k, [&](size_t c) { g.dir_node[dfill[c * 6 + k]++] = (uint32_t)g.leaves[li].node; });
+    } else {
+        g.cell_dir.clear();
+    }
 }
 
 // --------------------------------------------------------------------------------------- octree

@@ -1383,16 +1383,34 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
     const double invD[3] = {lz.invD[0], lz.invD[1], lz.invD[2]};
     const int cx = lz.cell[0], cy = lz.cell[1], cz = lz.cell[2];
     const size_t c = ((size_t)cz * sc.grid_dims[1] + cy) * sc.grid_dims[0] + cx;
-    const uint32_t e0 = sc.grid_cell_start[c], e1 = sc.grid_cell_start[c + 1];
-    const bool hasPrev = lz.prev[0] >= 0;
+    // First cell of the walk: every leaf of the cell.  Later cells: only the leaves whose cell range starts here along the
+    // step that brought us in (direction list lz.prev[0] = 2 * axis + (step < 0)) — the others were met in the previous cell.
+    const int code = lz.prev[0];
+    const uint32_t* __restrict__ list;
+    uint32_t e0, e1;
+    if (code < 0) {
+        list = sc.grid_cell_node;
+        e0 = __ldg(sc.grid_cell_start + c);
+        e1 = __ldg(sc.grid_cell_start + c + 1);
+    } else {
+        const uint4 cd = __ldg(sc.grid_cell_dir + c);
+        const unsigned cnt[6] = {cd.y & 0xFFFFu, cd.y >> 16, cd.z & 0xFFFFu, cd.z >> 16, cd.w & 0xFFFFu, cd.w >> 16};
+        list = sc.grid_dir_node;
+        e0 = cd.x;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) e0 += (k < code) ? cnt[k] : 0u;
+        unsigned len = cnt[0];
+#pragma unroll
+        for (int k = 1; k < 6; ++k) len = (k == code) ? cnt[k] : len;
+        e1 = e0 + len;
+    }
     for (uint32_t e = e0; e < e1; ++e) {
-        const uint4 lr = __ldg(sc.grid_entries + e);
-        if (hasPrev && cell_in_range(lr.y, lr.z, lz.prev[0], lz.prev[1], lz.prev[2])) continue;  // seen in an earlier cell
-        const rm_bvh_node* nd = sc.bvh + lr.x;
+        const uint32_t node = __ldg(list + e);
+        const rm_bvh_node* nd = sc.bvh + node;
         double tE, tX;
         if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tE, tX)) continue;
         if (tX < 0.0 || tE > 10.0) continue;
-        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)lr.x);
+        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)node);
     }
     int ax = 0;
     if (lz.tNext[1] < lz.tNext[ax]) ax = 1;
@@ -1403,9 +1421,7 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
         lz.done = true;
         return;
     }
-    lz.prev[0] = cx;
-    lz.prev[1] = cy;
-    lz.prev[2] = cz;
+    lz.prev[0] = 2 * ax + (lz.step[ax] < 0 ? 1 : 0);
     const int nc = lz.cell[ax] + lz.step[ax];
     if (nc < 0 || nc >= sc.grid_dims[ax]) {
         lz.done = true;
@@ -1943,7 +1959,12 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 r.nIv = 0;
                 r.lazy = kLazy;
                 if constexpr (kLazy) {
-                    if (!lazy_init(P.scene, o, r.d, lz)) r.lazy = true;  // missed the root box: lz.done, empty list
+                    if (P.scene.grid_cell_dir == nullptr) {  // no direction lists (counts beyond 16 bits): the literal list
+                        r.lazy = false;
+                        r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
+                    } else if (!lazy_init(P.scene, o, r.d, lz)) {
+                        r.lazy = true;  // missed the root box: lz.done, empty list
+                    }
                 } else {
                     r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
                 }
@@ -2047,7 +2068,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                         const size_t c = ((size_t)gz * P.scene.grid_dims[1] + gy) * P.scene.grid_dims[0] + gx;
                         const uint32_t e0 = P.scene.grid_cell_start[c], e1 = P.scene.grid_cell_start[c + 1];
                         for (uint32_t e = e0; e < e1; ++e) {
-                            const rm_bvh_node* nd = nodes + __ldg(P.scene.grid_entries + e).x;
+                            const rm_bvh_node* nd = nodes + __ldg(P.scene.grid_cell_node + e);
                             if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
                             const int pc = nd->prim_count;
                             leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);

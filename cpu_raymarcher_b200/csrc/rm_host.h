@@ -63,6 +63,16 @@ struct LeafGrid {
     std::vector<LeafRef> leaves;        // in pre-order (left-first) leaf order
     std::vector<uint32_t> cell_start;   // [nx*ny*nz + 1]
     std::vector<int32_t> cell_leaf;     // leaf ordinals, ascending within a cell
+    // Direction lists of the DDA walk: entering cell c by a step along axis a in direction s, the only leaves not seen in the
+    // previous cell are those whose cell range STARTS at c along that step (lo[a] == c[a] for s > 0, hi[a] == c[a] for s < 0).
+    // Per cell: base offset + six counts (k = 2 * axis + (s < 0)); the lists hold BVH node indices, ascending leaf ordinal.
+    struct CellDir {
+        uint32_t base;
+        uint16_t cnt[6];
+    };
+    std::vector<CellDir> cell_dir;      // [nx*ny*nz]
+    std::vector<uint32_t> dir_node;
+    bool dir_ok = true;                 // false: some count does not fit 16 bits (the walk then falls back to the tree)
 };
 void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& grid);
 

@@ -87,8 +87,10 @@ struct DevScene {
     uint32_t all_op_flops;       // sum of obj_flops (one pass over every object)
     // uniform grid over the BVH leaf boxes (fast path; see rm_host.h LeafGrid)
     const uint32_t* grid_cell_start;  // [nx*ny*nz + 1]
-    const uint4* grid_entries;        // per cell entry (ascending leaf ordinal within a cell): x = BVH node index of the leaf,
-                                      // y / z = packed lo / hi cell of the leaf's range — self-contained, one load per entry
+    const uint32_t* grid_cell_node;   // per cell entry (ascending leaf ordinal within a cell): BVH node index of the leaf
+    // direction lists of the DDA walk (rm_host.h LeafGrid::CellDir): x = base, y / z / w = six 16-bit counts; null = unavailable
+    const uint4* grid_cell_dir;
+    const uint32_t* grid_dir_node;
     int32_t grid_dims[3];
     float grid_origin[3], grid_inv[3], grid_cell[3];
 };
