@@ -741,6 +741,29 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
             for (size_t e = 0; e < cellNode.size(); ++e) cellNode[e] = (uint32_t)grid.leaves[(size_t)grid.cell_leaf[e]].node;
             if ((rc = upload(c, grid.cell_start.data(), grid.cell_start.size(), &ds.grid_cell_start))) return rc;
             if ((rc = upload(c, cellNode.data(), cellNode.size(), &ds.grid_cell_node))) return rc;
+            if (allTS) {  // leaf records of the point query
+                std::vector<LeafRecTS> lrec(bvh.size());
+                std::memset(lrec.data(), 0, lrec.size() * sizeof(LeafRecTS));
+                for (size_t ni = 0; ni < bvh.size(); ++ni) {
+                    const rm_bvh_node& nd = bvh[ni];
+                    if (nd.left >= 0 || nd.right >= 0 || nd.prim_count <= 0) continue;
+                    LeafRecTS& lr = lrec[ni];
+                    for (int k = 0; k < 3; ++k) {
+                        lr.bmin[k] = nd.bmin[k];
+                        lr.bmax[k] = nd.bmax[k];
+                    }
+                    lr.prim_first = nd.prim_first;
+                    lr.count = nd.prim_count <= 2 ? nd.prim_count : -nd.prim_count;
+                    for (int k = 0; k < nd.prim_count && k < 2; ++k) {
+                        const int32_t j = leaf[(size_t)nd.prim_first + (size_t)k];
+                        const float* m = s->world_to_local + 16 * (size_t)j;
+                        lr.s[k] = make_float4(m[12], m[13], m[14], (float)s->params[4 * (size_t)j]);
+                        lr.r[k] = s->params[4 * (size_t)j];
+                    }
+                }
+                if ((rc = upload(c, lrec.data(), lrec.size(), &ds.grid_leafrec))) return rc;
+                CU(c, cudaStreamSynchronize(c->stream));  // `lrec` goes out of scope
+            }
             if (grid.dir_ok) {
                 if ((rc = upload(c, reinterpret_cast<const uint4*>(grid.cell_dir.data()), grid.cell_dir.size(), &ds.grid_cell_dir))) return rc;
                 if ((rc = upload(c, grid.dir_node.data(), grid.dir_node.size(), &ds.grid_dir_node))) return rc;

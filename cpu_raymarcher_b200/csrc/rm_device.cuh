@@ -2037,6 +2037,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         double dd = 10.0;      // the query result handed to the control logic
         float distF = 10.f;    // fast model: running fp32 min over the candidate primitives
         int argmin = -1;       // fast model: its primitive
+        int argRec = -1;       // fast model, leaf records: 2 * node + slot of the winner when it is held inline
         unsigned cnt = 0;
         bool needAll = false, polish = false;
         if (waiting && !r.pending) {
@@ -2068,11 +2069,42 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                         const size_t c = ((size_t)gz * P.scene.grid_dims[1] + gy) * P.scene.grid_dims[0] + gx;
                         const uint32_t e0 = P.scene.grid_cell_start[c], e1 = P.scene.grid_cell_start[c + 1];
                         for (uint32_t e = e0; e < e1; ++e) {
-                            const rm_bvh_node* nd = nodes + __ldg(P.scene.grid_cell_node + e);
-                            if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
-                            const int pc = nd->prim_count;
-                            leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);
-                            cnt += (unsigned)pc;
+                            const uint32_t node = __ldg(P.scene.grid_cell_node + e);
+                            if constexpr (PK == PK_TSPHERE) {
+                                // one 80-byte record per leaf: box + spheres inline
+                                const float4* lr = reinterpret_cast<const float4*>(P.scene.grid_leafrec + node);
+                                const float4 a = __ldg(lr), b = __ldg(lr + 1);
+                                if (!(r.q[0] >= a.x && r.q[0] <= b.x && r.q[1] >= a.y && r.q[1] <= b.y && r.q[2] >= a.z && r.q[2] <= b.z)) continue;
+                                const int pc = __float_as_int(a.w);
+                                if (pc > 0) {
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        if (k < pc) {
+                                            const float4 sp = __ldg(lr + 2 + k);
+                                            const float lx = r.q[0] + sp.x, ly = r.q[1] + sp.y, lz2 = r.q[2] + sp.z;
+                                            const float d = NumFast::sqrt_(fmaf(lx, lx, fmaf(ly, ly, lz2 * lz2))) - sp.w;
+                                            if (d < distF) {
+                                                distF = d;
+                                                argRec = (int)(2u * node) + k;
+                                                argmin = -1;
+                                            }
+                                        }
+                                    }
+                                    r.nSphere += (unsigned)pc;
+                                    cnt += (unsigned)pc;
+                                } else {  // a leaf with more than two primitives (depth limit of the builder): the generic path
+                                    const int before = argmin;
+                                    leaf_prims<NP, PK>(P, P.scene.leaf_prims + __float_as_int(b.w), -pc, r.q, dd, distF, argmin, r);
+                                    if (argmin != before) argRec = -1;
+                                    cnt += (unsigned)(-pc);
+                                }
+                            } else {
+                                const rm_bvh_node* nd = nodes + node;
+                                if (!box_contains(nd->bmin, nd->bmax, r.q)) continue;
+                                const int pc = nd->prim_count;
+                                leaf_prims<NP, PK>(P, P.scene.leaf_prims + nd->prim_first, pc, r.q, dd, distF, argmin, r);
+                                cnt += (unsigned)pc;
+                            }
                         }
                     }
                 } else {
@@ -2100,8 +2132,14 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
         if constexpr (!NP::kExact) {
             // fast model: one fp64 evaluation of the nearest candidate found by the fp32 search
-            if (polish && argmin >= 0)
+            if (polish && argmin >= 0) {
                 dd = jsmin(prim_sdf_polish<PK>(P.scene, argmin, r.q), 10.0);
+            } else if (polish && argRec >= 0) {  // winner held inline in a leaf record: same arithmetic as prim_sdf_polish
+                const LeafRecTS* lr = P.scene.grid_leafrec + (argRec >> 1);
+                const float4 sp = __ldg(&lr->s[argRec & 1]);
+                const double lx = (double)__fadd_rn(r.q[0], sp.x), ly = (double)__fadd_rn(r.q[1], sp.y), lz2 = (double)__fadd_rn(r.q[2], sp.z);
+                dd = jsmin(sqrt(lx * lx + ly * ly + lz2 * lz2) - __ldg(&lr->r[argRec & 1]), 10.0);
+            }
         }
         // ---- (d2) the dense all-primitives pass ----
         if (!useQueue) {

@@ -40,6 +40,19 @@ struct DevInstr {
 constexpr int kMaxPointStack = 3 * RM_MAX_TREE_DEPTH + 2;
 constexpr int kMaxDistStack = RM_MAX_TREE_DEPTH + 2;
 
+// Fast path, translation-only spheres behind a BVH: everything the point query needs about a leaf in one 80-byte record
+// indexed by BVH node index (box, up to two spheres inline with their fp64 radii) — three dependent loads per query
+// (cell -> entry -> record) instead of six (cell -> entry -> node -> leaf list -> sphere -> radius).
+struct LeafRecTS {
+    float bmin[3];
+    int32_t count;       // 1 or 2: spheres inline; 0: not a leaf; < 0: -count primitives, take the generic path through the node
+    float bmax[3];
+    int32_t prim_first;
+    float4 s[2];         // (tx, ty, tz, r)
+    double r[2];         // radii as the reference holds them (JS numbers)
+};
+static_assert(sizeof(LeafRecTS) == 80, "LeafRecTS layout");
+
 // Device-resident scene (all pointers are device pointers).
 struct DevScene {
     int32_t n_prims;
@@ -87,6 +100,7 @@ struct DevScene {
     uint32_t all_op_flops;       // sum of obj_flops (one pass over every object)
     // uniform grid over the BVH leaf boxes (fast path; see rm_host.h LeafGrid)
     const uint32_t* grid_cell_start;  // [nx*ny*nz + 1]
+    const LeafRecTS* grid_leafrec;    // PK_TSPHERE: per BVH node (see LeafRecTS); null otherwise
     const uint32_t* grid_cell_node;   // per cell entry (ascending leaf ordinal within a cell): BVH node index of the leaf
     // direction lists of the DDA walk (rm_host.h LeafGrid::CellDir): x = base, y / z / w = six 16-bit counts; null = unavailable
     const uint4* grid_cell_dir;
