@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -213,13 +214,15 @@ void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
     for (size_t i = 0; i < nodes.size(); ++i)
         if (nodes[i].left < 0 && nodes[i].right < 0 && nodes[i].prim_count > 0) leafNodes.push_back((int32_t)i);
     const rm_bvh_node& root = nodes[0];
-    // resolution: about 2.5 * cbrt(#leaves) cells along the longest axis, at most 128 (ranges pack into bytes)
+    // resolution: about 1.75 * cbrt(#leaves) cells along the longest axis, at most 128 (ranges pack into bytes)
     double ext[3], maxExt = 0;
     for (int k = 0; k < 3; ++k) {
         ext[k] = (double)root.bmax[k] - (double)root.bmin[k];
         if (ext[k] > maxExt) maxExt = ext[k];
     }
-    int target = (int)std::lround(2.5 * std::cbrt((double)std::max<size_t>(leafNodes.size(), 1)));
+    double factor = 1.75;  // measured flat optimum 1.25 .. 2.5 on config 4 (10k and 100k spheres)
+    if (const char* e = std::getenv("RM_GRID_FACTOR")) factor = std::atof(e);  // tuning knob (tools/, profiles/README.md)
+    int target = (int)std::lround(factor * std::cbrt((double)std::max<size_t>(leafNodes.size(), 1)));
     target = std::min(128, std::max(1, target));
     for (int k = 0; k < 3; ++k) {
         g.origin[k] = root.bmin[k];
