@@ -351,6 +351,53 @@ def test_fast_path_cluster_screen_tiny_frames_and_bands(fast_worker, oracle, W, 
     assert np.array_equal(f.depth, ref.depth)
 
 
+def test_fast_path_host_supplied_bvh_with_fat_leaves():
+    """rm_scene.nodes: a host-built structure whose leaves hold more than two primitives (what the reference's builder only
+    produces at its depth limit).  The fast point query then leaves its inline leaf records for the generic leaf loop; the
+    validation build walks the same nodes literally.  Both must agree."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import _lib
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    t, m, q = sm.synthetic_spheres(400).arrays()
+    nodes, nn, leaf = rb.build_bvh(t, m, q)
+    src = np.frombuffer(nodes, dtype=np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("l", "<i4"), ("r", "<i4"), ("pf", "<i4"), ("pc", "<i4")]), count=nn)
+    # collapse the tree to depth 2: root -> two fat leaves (the subtrees of the root's children)
+    def leaves_under(i):
+        if src["l"][i] < 0 and src["r"][i] < 0:
+            return list(leaf[src["pf"][i]: src["pf"][i] + src["pc"][i]])
+        out = []
+        for ch in (src["l"][i], src["r"][i]):
+            if ch >= 0:
+                out += leaves_under(ch)
+        return out
+    L, R = int(src["l"][0]), int(src["r"][0])
+    pl, pr = leaves_under(L), leaves_under(R)
+    fat = (_lib.BvhNode * 3)()
+    for dst, si, first, cnt, kids in ((0, 0, 0, 0, (1, 2)), (1, L, 0, len(pl), (-1, -1)), (2, R, len(pl), len(pr), (-1, -1))):
+        fat[dst].bmin[:] = [float(v) for v in src["bmin"][si]]
+        fat[dst].bmax[:] = [float(v) for v in src["bmax"][si]]
+        fat[dst].left, fat[dst].right = kids
+        fat[dst].prim_first, fat[dst].prim_count = first, cnt
+    fat_leaf = np.array(pl + pr, np.int32)
+    assert len(pl) > 2 and len(pr) > 2
+    W, H = 96, 54
+    cam = Camera()
+    cam.set_angles(0.2, 0.7)
+    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position())
+    frames = []
+    for val in (True, False):
+        ctx = rb.Context(0, validate_fp64=val)
+        ctx.upload_scene(t, m, q, "BVH", nodes=fat, n_nodes=3, leaf=fat_leaf)
+        frames.append(ctx.render(rq, extras=True))
+        ctx.close()
+    a, b = frames
+    assert np.array_equal(a.sdfEval, b.sdfEval) and np.array_equal(a.iters, b.iters)
+    same = (a.depth == b.depth) & (np.abs(a.normal.reshape(-1, 3).astype(int) - b.normal.reshape(-1, 3).astype(int)).max(1) <= RGB_TOL)
+    assert same.mean() >= PIXEL_AGREEMENT
+    assert int(a.sdf_u32.max()) >= min(len(pl), len(pr))  # the fat leaves were really evaluated
+
+
 @pytest.mark.parametrize("alg", ["fixed-step", "adaptive-step-v3"])
 def test_fast_path_cluster_screen_other_algorithms(fast_worker, oracle, alg):
     W, H = 80, 45
