@@ -590,17 +590,19 @@ struct Compiler {
         }
         return pushed;
     }
-    void node(int32_t ni) {
+    // `frozen`: below an AnimatedTranslate.  Scene.updateTime reaches a node only through the setTime overrides, and
+    // AnimatedTranslate's does not forward to its child — everything underneath keeps its construction-time time = 0.
+    void node(int32_t ni, bool frozen = false) {
         const rm_op_node& nd = s.op_nodes[ni];
         int pushed = 0;
         switch (nd.kind) {
             case RM_NODE_PRIMITIVE:
-                emit(I_PRIM, nd.prim);
+                emit(I_PRIM, nd.prim, frozen ? 0.0 : 1.0);  // c = time scale seen by the leaf (mandelbulb.ts:33-35)
                 if (s.type[nd.prim] <= RM_PRIM_TORUS) hist[s.type[nd.prim]]++;
                 return;
             case RM_NODE_ROUND:
                 pushed = prologue(nd, true);
-                node(nd.child[0]);
+                node(nd.child[0], frozen);
                 if (pushed) emit(I_POP, pushed);
                 emit(I_SUBC, 0, nd.p[0]);
                 flops += 1;
@@ -609,7 +611,7 @@ struct Compiler {
                 pushed = prologue(nd, true);
                 emit(I_TWIST, 0, nd.p[0]);
                 flops += 9;
-                node(nd.child[0]);
+                node(nd.child[0], frozen);
                 emit(I_POP, pushed + 1);
                 return;
             case RM_NODE_REPETITION: {
@@ -617,7 +619,7 @@ struct Compiler {
                 const float sp[3] = {f32(nd.p[0]), f32(nd.p[1]), f32(nd.p[2])};
                 emit(I_REPEAT, 0, 0.0, sp);
                 flops += 12;
-                node(nd.child[0]);
+                node(nd.child[0], frozen);
                 emit(I_POP, pushed + 1);
                 return;
             }
@@ -627,17 +629,18 @@ struct Compiler {
                 std::memcpy(a.dir, nd.dir, sizeof(a.dir));
                 a.amplitude = nd.p[0];
                 a.speed = nd.p[1];
+                a.frozen = frozen;
                 out.anims.push_back(a);
                 emit(I_SUBV, (int32_t)out.anims.size() - 1);
                 flops += 3;
-                node(nd.child[0]);
+                node(nd.child[0], true);
                 emit(I_POP, pushed + 1);
                 return;
             }
             default:
                 pushed = prologue(nd, true);
-                node(nd.child[0]);
-                node(nd.child[1]);
+                node(nd.child[0], frozen);
+                node(nd.child[1], frozen);
                 if (pushed) emit(I_POP, pushed);
                 emit(nd.kind == RM_NODE_SMOOTH_UNION ? I_SUNION : I_SSUB, 0, nd.p[0]);
                 flops += 10;
@@ -700,7 +703,7 @@ void eval_anim_offsets(const TreeProgram& prog, double time, std::vector<float>&
     out4.assign(prog.anims.size() * 4, 0.f);
     for (size_t i = 0; i < prog.anims.size(); ++i) {
         const AnimSlot& a = prog.anims[i];
-        const double offset = std::sin(time * a.speed) * a.amplitude;  // Math.sin (animatedTranslate.ts:36)
+        const double offset = std::sin((a.frozen ? 0.0 : time) * a.speed) * a.amplitude;  // Math.sin (animatedTranslate.ts:36)
         for (int k = 0; k < 3; ++k) out4[4 * i + k] = f32((double)a.dir[k] * offset);  // vec3.scale -> f32
     }
 }

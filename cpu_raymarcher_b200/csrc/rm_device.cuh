@@ -72,7 +72,7 @@ enum Phase : int {
 // ------------------------------------------------------------------------------------------
 
 // Exact model: Primitive.sdf (primitive.ts:33-39) = f32(transformMat4(p, M)) then localSdf, for leaf primitive j.
-RM_DEV double leaf_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt) {
+RM_DEV double leaf_sdf_exact(const DevScene& sc, int j, double x, double y, double z, int length_sqrt, double time_scale = 1.0) {
     const float* m = sc.w2l + 16 * (size_t)j;
     double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7];
     double m8 = m[8], m9 = m[9], m10 = m[10], m11 = m[11], m12 = m[12], m13 = m[13], m14 = m[14], m15 = m[15];
@@ -100,7 +100,7 @@ RM_DEV double leaf_sdf_exact(const DevScene& sc, int j, double x, double y, doub
         const double px = lx, py = lz, pz = ly;  // p.xyz = p.xzy
         double zx = px, zy = py, zz = pz;
         double dr = 1.0, r = 0.0;
-        const double power = prm[0], dphi = (prm[2] != 0.0) ? sc.time * prm[3] : 0.0;
+        const double power = prm[0], dphi = (prm[2] != 0.0) ? (sc.time * time_scale) * prm[3] : 0.0;
         const int iterations = (int)prm[1];
         for (int i = 0; i < iterations; ++i) {
             r = length_sqrt ? sqrt(zx * zx + zy * zy + zz * zz) : v8_hypot3(zx, zy, zz);
@@ -150,7 +150,7 @@ static __device__ __noinline__ double object_sdf_exact(const DevScene& sc, int j
         const DevInstr in = sc.instrs[pc];
         const double X = px[sp], Y = py[sp], Z = pz[sp];
         switch (in.op) {
-            case I_PRIM: ds[dp++] = leaf_sdf_exact(sc, in.a, X, Y, Z, length_sqrt); break;
+            case I_PRIM: ds[dp++] = leaf_sdf_exact(sc, in.a, X, Y, Z, length_sqrt, in.c); break;  // c: 0 below an AnimatedTranslate
             case I_XFORM: {  // vec3.transformMat4 into a Float32Array
                 const float* m = sc.mats + 16 * (size_t)in.a;
                 double w = (double)m[3] * X + (double)m[7] * Y + (double)m[11] * Z + (double)m[15];

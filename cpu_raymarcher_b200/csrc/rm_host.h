@@ -30,6 +30,7 @@ int validate_tree(const rm_scene& s, std::string& err);
 struct AnimSlot {
     float dir[3];
     double amplitude, speed;
+    bool frozen;  // sits under another AnimatedTranslate, whose setTime does not forward (animatedTranslate.ts:30-32): time stays 0
 };
 struct TreeProgram {
     std::vector<DevInstr> instrs;

@@ -148,6 +148,70 @@ def test_operator_full_size_properties(fast_worker, val_worker):
     assert np.array_equal(np.concatenate([top.normal, bot.normal]), b.normal)
 
 
+# ------------------------------------------------------------------------------------------ random operator trees
+def _random_tree(rng, depth, has_twist):
+    """A random operator tree over rotated / translated leaves (uses every operator kind)."""
+    def leaf():
+        pos = rng.uniform(-1.2, 1.2, 3)
+        rot = tuple(rng.uniform(-1.0, 1.0, 3)) if rng.random() < 0.5 else None
+        k = rng.integers(0, 3)
+        if k == 0:
+            return sm.create_sphere(*pos, rng.uniform(0.2, 0.6), rot)
+        if k == 1:
+            return sm.create_box(*pos, tuple(rng.uniform(0.1, 0.5, 3)), rot)
+        return sm.create_torus(*pos, rng.uniform(0.3, 0.7), rot)
+    if depth == 0:
+        return leaf()
+    k = rng.integers(0, 7)
+    if k == 0:
+        return sm.create_round(_random_tree(rng, depth - 1, has_twist), rng.uniform(0.01, 0.2))
+    if k == 1:
+        has_twist.append(True)
+        return sm.create_twist(_random_tree(rng, depth - 1, has_twist), rng.uniform(0.5, 4.0))
+    if k == 2:
+        return sm.create_smooth_union(_random_tree(rng, depth - 1, has_twist), _random_tree(rng, depth - 1, has_twist), rng.uniform(0.0005, 0.3))
+    if k == 3:
+        return sm.create_smooth_subtract(_random_tree(rng, depth - 1, has_twist), _random_tree(rng, depth - 1, has_twist), rng.uniform(0.01, 0.3))
+    if k == 4:
+        return sm.create_repetition(_random_tree(rng, depth - 1, has_twist), tuple(rng.uniform(1.5, 3.0, 3)))
+    if k == 5:
+        return sm.create_animated_translate(_random_tree(rng, depth - 1, has_twist), tuple(rng.uniform(-1, 1, 3)), rng.uniform(0.2, 1.5), rng.uniform(0.001, 0.02))
+    return leaf()
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_validation_random_operator_trees(oracle, seed):
+    """Fuzz: random trees (depth <= 3, every operator kind, rotated leaves), random accel / algorithm / camera / time.
+    Bit-exact against the oracle; trees containing a Twist (libm sin / cos on both sides) must at least meet the
+    north-star agreement bar — in practice they are bit-exact too."""
+    rng = np.random.default_rng(1000 + seed)
+    has_twist = []
+    objs = [_random_tree(rng, int(rng.integers(1, 4)), has_twist) for _ in range(int(rng.integers(1, 4)))]
+    accel = ["None", "Octree", "BVH"][seed % 3]
+    alg = ALGS[seed % len(ALGS)]
+    pitch, yaw, time = float(rng.uniform(-0.8, 0.8)), float(rng.uniform(0, 6.28)), float(rng.uniform(0, 500))
+    W, H = 72, 40
+    pl = sm.flatten(objs)
+    t, m, q = pl.arrays()
+    osc = oracle.OracleScene()
+    if pl.op_nodes is None:
+        osc.set_prims(t, m, q)
+    else:
+        osc.set_tree(t, m, q, pl.op_nodes, pl.object_root)
+    ref = osc.build_accel(accel).set_camera(pitch, yaw).set_time(time).render(W, H, alg)
+    ctx = rb.Context(0, validate_fp64=True)
+    ctx.upload_scene(t, m, q, accel, op_nodes=pl.op_nodes, object_root=pl.object_root)
+    cam = Camera()
+    cam.set_angles(pitch, yaw)
+    f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), algorithm=alg, time=time), extras=True)
+    ctx.close()
+    if has_twist:
+        same = (f.depth == ref.depth) & (f.sdfEval == ref.sdfEval) & (f.iters == ref.iters)
+        assert same.mean() >= PIXEL_AGREEMENT
+    else:
+        assert_bit_exact(f, ref, oracle, W, H)
+
+
 # ------------------------------------------------------------------------------------------ Mandelbulb (SURVEY.md §8f row 4)
 def _agree(f, ref):
     same = (f.depth == ref.depth) & (f.sdfEval == ref.sdfEval) & (f.iters == ref.iters)
@@ -186,6 +250,27 @@ def test_mandelbulb_default_build_and_animation(fast_worker, oracle):
     a = fast_worker.on_message(make_job(64, 36, 13, "None", time=0.0))
     b = fast_worker.on_message(make_job(64, 36, 13, "None", time=20000.0))  # phi += time * -0.0001 per inner iteration
     assert not np.array_equal(a.depth, b.depth)
+
+
+def test_time_does_not_reach_below_an_animated_translate(oracle):
+    """AnimatedTranslate.setTime keeps the time for itself (animatedTranslate.ts:30-32): an AnimatedTranslate or a Mandelbulb
+    underneath stays at time 0 whatever Job.time says.  (Found by the random-tree test.)"""
+    W, H = 80, 45
+    inner = sm.create_animated_translate(sm.create_sphere(0.2, 0.1, 0.0, 0.5), (0, 1, 0), 1.5, 0.01)
+    objs = [sm.create_animated_translate(inner, (1, 0, 0), 1.0, 0.004),
+            sm.create_animated_translate(sm.create_mandelbulb(-1.5, 0, 0, 8, 10, True, -0.01), (0, 0, 1), 0.5, 0.003)]
+    pl = sm.flatten(objs)
+    t, m, q = pl.arrays()
+    for time in (0.0, 321.0):
+        ref = oracle.OracleScene().set_tree(t, m, q, pl.op_nodes, pl.object_root).build_accel("None").set_camera(0.1, 0.2).set_time(time).render(W, H)
+        ctx = rb.Context(0, validate_fp64=True)
+        ctx.upload_scene(t, m, q, "None", op_nodes=pl.op_nodes, object_root=pl.object_root)
+        cam = Camera()
+        cam.set_angles(0.1, 0.2)
+        f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), time=time), extras=True)
+        ctx.close()
+        assert _agree(f, ref) >= PIXEL_AGREEMENT, time
+        assert (ref.depth_f64 < 10).sum() > 100
 
 
 def test_mandelbulb_inside_an_operator_tree(oracle):
