@@ -490,3 +490,67 @@ def test_multi_gpu_fused_gather_matches_single_gpu():
                         "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
+
+
+# ------------------------------------------------------------------------------------------ random primitive lists
+def _random_scene(rng, n):
+    from cpu_raymarcher_b200 import scene_manager as sm
+    pl = sm.PrimitiveList()
+    for _ in range(n):
+        pos = rng.uniform(-2.0, 2.0, 3)
+        rot = tuple(rng.uniform(-3.0, 3.0, 3)) if rng.random() < 0.6 else None
+        k = rng.integers(0, 3)
+        if k == 0:
+            sm.add_sphere(pl, *pos, rng.uniform(0.05, 0.5), rot)
+        elif k == 1:
+            sm.add_box(pl, *pos, tuple(rng.uniform(0.05, 0.4, 3)), rot)
+        else:
+            sm.add_torus(pl, *pos, rng.uniform(0.1, 0.5), rot)
+    return pl.arrays()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_validation_random_primitive_lists(oracle, seed):
+    """Fuzz: random mixes of rotated spheres / boxes / tori, every structure and algorithm, random camera and step sizes."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200.camera import Camera
+    rng = np.random.default_rng(7000 + seed)
+    t, m, q = _random_scene(rng, int(rng.integers(1, 80)))
+    accel = ["None", "Octree", "BVH"][seed % 3]
+    alg = ALGS[(seed // 3) % len(ALGS)]
+    pitch, yaw = float(rng.uniform(-1.2, 1.2)), float(rng.uniform(0, 6.28))
+    step, over = float(rng.uniform(0.02, 0.3)), float(rng.uniform(1.0, 2.0))
+    W, H = 72, 40
+    ref = oracle.OracleScene().set_prims(t, m, q).build_accel(accel).set_camera(pitch, yaw).render(W, H, alg, step_size=step, overshoot=over)
+    ctx = rb.Context(0, validate_fp64=True)
+    ctx.upload_scene(t, m, q, accel)
+    cam = Camera()
+    cam.set_angles(pitch, yaw)
+    f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), algorithm=alg, step_size=step, overshoot=over),
+                   extras=True)
+    ctx.close()
+    assert_bit_exact(f, ref, oracle, W, H)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fast_path_random_primitive_lists(oracle, seed):
+    """Same generator through the fp32 fast path; sizes 300-700 behind a BVH go through the CTA-cooperative all-primitives
+    pass of the GENERAL record layout (8-warp CTAs, FFMA search)."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200.camera import Camera
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(300, 700)) if seed % 2 == 0 else int(rng.integers(1, 120))
+    t, m, q = _random_scene(rng, n)
+    accel = ["BVH", "Octree", "None"][seed % 3] if seed % 2 else "BVH"
+    alg = ALGS[seed % len(ALGS)]
+    pitch, yaw = float(rng.uniform(-1.0, 1.0)), float(rng.uniform(0, 6.28))
+    W, H = 96, 54
+    ref = oracle.OracleScene().set_prims(t, m, q).build_accel(accel).set_camera(pitch, yaw).render(W, H, alg)
+    ctx = rb.Context(0)
+    ctx.upload_scene(t, m, q, accel)
+    cam = Camera()
+    cam.set_angles(pitch, yaw)
+    f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), algorithm=alg, shader="phong"), extras=True)
+    ctx.close()
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"n={n} {accel} {alg}: pixel agreement {px} (depth-only among hits {dz})"
