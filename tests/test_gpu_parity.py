@@ -554,3 +554,46 @@ def test_fast_path_random_primitive_lists(oracle, seed):
     ctx.close()
     px, dz = fast_agreement(f, ref, oracle, W, H)
     assert px >= PIXEL_AGREEMENT, f"n={n} {accel} {alg}: pixel agreement {px} (depth-only among hits {dz})"
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fast_path_cluster_screen_adversarial_sphere_sets(oracle, seed):
+    """Translation-only sphere sets that stress the bounds of the cluster screen: tight clumps, nested and coincident
+    spheres, radii spanning three orders of magnitude, far outliers, a camera inside the cloud."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    rng = np.random.default_rng(4000 + seed)
+    n = int(rng.integers(256, 2500))
+    kind = seed % 4
+    if kind == 0:    # a few tight clumps
+        centres = rng.normal(0, 0.05, (n, 3)) + rng.uniform(-1.5, 1.5, (8, 3))[rng.integers(0, 8, n)]
+        radii = rng.uniform(0.005, 0.05, n)
+    elif kind == 1:  # nested + coincident spheres, radii over three orders of magnitude
+        centres = rng.uniform(-1.0, 1.0, (n, 3))
+        centres[: n // 4] = centres[n // 4: 2 * (n // 4)]
+        radii = 10 ** rng.uniform(-3, -0.3, n)
+    elif kind == 2:  # a thin sheet plus far outliers
+        centres = np.stack([rng.uniform(-2, 2, n), rng.normal(0, 0.01, n), rng.uniform(-2, 2, n)], 1)
+        centres[:5] = rng.uniform(6, 9, (5, 3))
+        radii = rng.uniform(0.01, 0.08, n)
+    else:            # uniform cloud, big radii variance
+        centres = rng.uniform(-2.5, 2.5, (n, 3))
+        radii = np.where(rng.random(n) < 0.02, rng.uniform(0.3, 0.8, n), rng.uniform(0.01, 0.04, n))
+    w2l = sm.get_transform_batch(centres)
+    t = np.zeros(n, np.uint8)
+    q = np.zeros((n, 4))
+    q[:, 0] = radii
+    pitch, yaw = float(rng.uniform(-0.6, 0.6)), float(rng.uniform(0, 6.28))
+    W, H = 80, 45
+    ref = oracle.OracleScene().set_prims(t, w2l, q).build_accel("BVH").set_camera(pitch, yaw).render(W, H, "sphere-tracer")
+    ctx = rb.Context(0)
+    ctx.upload_scene(t, w2l, q, "BVH")
+    cam = Camera()
+    cam.set_angles(pitch, yaw)
+    f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="phong"), extras=True)
+    st = ctx.stats()
+    ctx.close()
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"kind {kind} n={n}: pixel agreement {px} (depth-only among hits {dz}); tc passes {st['tc_passes']}"
+    assert np.array_equal(f.sdfEval, ref.sdfEval) or px >= PIXEL_AGREEMENT
