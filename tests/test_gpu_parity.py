@@ -322,7 +322,7 @@ def test_fast_path_tolerance_matrix(fast_worker, oracle, preset, accel, alg):
     assert dz >= 0.99, f"depth agreement among hit pixels {dz}"
 
 
-@pytest.mark.parametrize("n", [256, 257, 300, 1000, 4097, 12800])
+@pytest.mark.parametrize("n", [256, 257, 300, 1000, 4097, 12800, 16384, 16385, 33000, 70000])
 def test_fast_path_cluster_screen_sizes(fast_worker, oracle, n):
     """Translation-only spheres behind a BVH: the all-primitives fallback runs as the tensor-core cluster screen
     (>= 256 spheres).  Sizes around the 128-sphere cluster / 128-cluster block boundaries, rotated camera."""
