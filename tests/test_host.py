@@ -210,3 +210,28 @@ def test_plane_layout_is_aligned_and_disjoint():
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
         assert a1 <= b0
     assert all(lay[k] % 256 == 0 for k in sizes) and lay["total"] >= spans[-1][1]
+
+
+def test_napi_addon_compiles_against_the_c_abi(tmp_path):
+    """addon/rm_napi.cc (the Node binding of INTEGRATION.md) must stay well-formed against include/rm.h; Node.js itself is
+    not available here, so it is compiled against the restated N-API prototypes of addon/napi_min.h."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    out = tmp_path / "rm_napi.o"
+    subprocess.check_call([cxx, "-std=c++17", "-fPIC", "-Wall", "-c", os.path.join(ROOT, "addon", "rm_napi.cc"), "-o", str(out)])
+    assert out.stat().st_size > 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/rm.h is the drop-in boundary: it must compile as C (no C++-isms, no torch / CUDA types)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "rm.h"\nint main(void) { rm_scene s; rm_op_node n; (void)s; (void)n; return sizeof(rm_stats_t) > 0 ? 0 : 1; }\n')
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
