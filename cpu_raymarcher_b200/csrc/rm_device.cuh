@@ -14,14 +14,17 @@
 // Design (B200-first, not a translation):
 //   * persistent CTAs; each warp pulls 8x4-pixel tiles from an atomic work queue;
 //   * every lane owns one ray and runs it as an explicit state machine
-//     (STEP -> scene-distance query -> consume -> ... -> 4 normal queries -> finalize); lanes whose
-//     ray terminated are found with __ballot_sync and refilled with fresh pixels immediately, so
-//     divergent ray lengths do not idle lanes; all scene-distance queries of a warp — march steps,
+//     (STEP -> scene-distance query -> consume -> ... -> 4 normal queries -> finalize); terminated
+//     rays are found with __ballot_sync and the warp takes its next tile once the current one has
+//     retired (measured best, RM_INIT_LANES); all scene-distance queries of a warp — march steps,
 //     normal taps, V3 bridging taps — funnel through ONE code site;
-//   * a query is first resolved through the acceleration structure (few primitives, lane-local);
+//   * a query is first resolved through the acceleration structure (few primitives, lane-local; the fast BVH
+//     kernels use a uniform grid over the leaf boxes + inline leaf records instead of the tree);
 //     queries that need every primitive (no acceleration structure, the BVH "empty candidate set"
-//     fallback of scene.ts:173, points outside the octree root) run the dense all-primitives loop
-//     in which every lane reads the same primitive record (one broadcast load per warp per primitive);
+//     fallback of scene.ts:173, points outside the octree root) run the all-primitives pass: records
+//     streamed through shared memory by TMA bulk copies, or — for translation-only spheres behind a
+//     BVH — the CTA-cooperative cluster screen on the tcgen05 tensor cores (tc_pass);
+//   * SDF operator trees and the Mandelbulb run as compiled per-object programs in the exact kernels;
 //   * per-pixel outputs are quantised exactly like the reference's typed arrays and the diagnostics
 //     are reduced in the epilogue (warp reduce, one atomic set per warp).
 //
