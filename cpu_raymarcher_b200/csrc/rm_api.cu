@@ -737,6 +737,8 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
                 ds.grid_inv[k] = grid.inv_cell[k];
                 ds.grid_cell[k] = grid.cell[k];
             }
+            ds.lazy_cap = RM_PEND_CAP;
+            if (const char* e = std::getenv("RM_LAZY_CAP")) ds.lazy_cap = std::max(1, std::min(RM_PEND_CAP, std::atoi(e)));  // test knob
             std::vector<uint32_t> cellNode(grid.cell_leaf.size());
             for (size_t e = 0; e < cellNode.size(); ++e) cellNode[e] = (uint32_t)grid.leaves[(size_t)grid.cell_leaf[e]].node;
             if ((rc = upload(c, grid.cell_start.data(), grid.cell_start.size(), &ds.grid_cell_start))) return rc;

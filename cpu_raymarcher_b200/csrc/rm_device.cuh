@@ -1296,7 +1296,7 @@ RM_DEV bool cell_in_range(uint32_t lo, uint32_t hi, int x, int y, int z) {
 // cell of its (convex) cell range, with the reference's exact slab test; accepted intervals wait in a small
 // buffer sorted by (tEnter, right-first DFS order) and are released once the walk has passed their tEnter,
 // so the consumer sees exactly the stably-sorted list of the reference — but only as far as the march needs.
-constexpr int kPendCap = 64;
+constexpr int kPendCap = RM_PEND_CAP;  // rm_types.h
 struct LazyIv {
     double tNext[3], tDelta[3], invD[3];  // invD = 1 / direction, computed once per ray
     double tEnd, safeT;
@@ -1307,7 +1307,11 @@ struct LazyIv {
     bool done, overflow;
 };
 
-RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node) {
+RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node, int cap) {
+    if (lz.count >= cap) {  // (cap < kPendCap only under the RM_LAZY_CAP test knob)
+        lz.overflow = true;
+        return;
+    }
     if (lz.head + lz.count >= kPendCap) {  // compact
         for (int i = 0; i < lz.count; ++i) {
             lz.pEnter[i] = lz.pEnter[lz.head + i];
@@ -1413,7 +1417,7 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
         double tE, tX;
         if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tE, tX)) continue;
         if (tX < 0.0 || tE > 10.0) continue;
-        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)node);
+        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)node, sc.lazy_cap);
     }
     int ax = 0;
     if (lz.tNext[1] < lz.tNext[ax]) ax = 1;
@@ -1437,6 +1441,9 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
 // next interval of the sorted list, or false when the list is exhausted
 RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz, double& enter, double& exit_) {
     for (;;) {
+        // Once an insertion has been dropped the buffer is no longer the complete sorted prefix: hand over to the literal
+        // list right away (everything popped so far was final, so the caller continues at the same cursor index).
+        if (lz.overflow) return false;
         if (lz.count > 0 && (lz.done || lz.pEnter[lz.head] < lz.safeT)) {
             enter = lz.pEnter[lz.head];
             exit_ = lz.pExit[lz.head];

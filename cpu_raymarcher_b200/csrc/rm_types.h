@@ -5,6 +5,10 @@
 
 #include "../../include/rm.h"
 
+#ifndef RM_PEND_CAP
+#define RM_PEND_CAP 64  // pending (sorted, not yet released) intervals of the lazy grid walk; overflow -> literal list
+#endif
+
 namespace rm {
 
 constexpr int kTileW = 8;   // image tile handed to a warp by the atomic work queue: 8 x 4 = 32 pixels
@@ -99,6 +103,8 @@ struct DevScene {
     const uint32_t* obj_flops;   // per object: FLOPs of its operator instructions per call
     uint32_t all_op_flops;       // sum of obj_flops (one pass over every object)
     // uniform grid over the BVH leaf boxes (fast path; see rm_host.h LeafGrid)
+    int32_t lazy_cap;                 // pending-interval capacity of the lazy walk (= its buffer size; smaller only under the
+                                      // RM_LAZY_CAP test knob, which forces the hand-over to the literal interval list)
     const uint32_t* grid_cell_start;  // [nx*ny*nz + 1]
     const LeafRecTS* grid_leafrec;    // PK_TSPHERE: per BVH node (see LeafRecTS); null otherwise
     const uint32_t* grid_cell_node;   // per cell entry (ascending leaf ordinal within a cell): BVH node index of the leaf

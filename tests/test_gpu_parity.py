@@ -597,3 +597,27 @@ def test_fast_path_cluster_screen_adversarial_sphere_sets(oracle, seed):
     px, dz = fast_agreement(f, ref, oracle, W, H)
     assert px >= PIXEL_AGREEMENT, f"kind {kind} n={n}: pixel agreement {px} (depth-only among hits {dz}); tc passes {st['tc_passes']}"
     assert np.array_equal(f.sdfEval, ref.sdfEval) or px >= PIXEL_AGREEMENT
+
+
+@pytest.mark.parametrize("cap", [1, 3, 8])
+def test_fast_path_lazy_walk_hand_over_to_literal_interval_list(oracle, cap, monkeypatch):
+    """The fast BVH kernels produce the reference's sorted interval list lazily through a bounded buffer; when it overflows the
+    ray hands over to the literal findRayIntersections list at the same cursor index.  RM_LAZY_CAP (read at upload) shrinks
+    the buffer so that the hand-over happens on nearly every ray.  (A stale-buffer bug in this path was found with it.)"""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    monkeypatch.setenv("RM_LAZY_CAP", str(cap))
+    W, H = 96, 54
+    for syn, preset in (((1500, 0x5EED0001), 1), (None, 3)):
+        t, m, q = (sm.synthetic_spheres(*syn) if syn else sm.get_preset(preset)).arrays()
+        ref = _oracle_scene(oracle, preset, "BVH", 0.2, 0.9, synthetic=syn).render(W, H, "sphere-tracer")
+        ctx = rb.Context(0)
+        ctx.upload_scene(t, m, q, "BVH")
+        cam = Camera()
+        cam.set_angles(0.2, 0.9)
+        f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="phong"), extras=True)
+        ctx.close()
+        assert np.array_equal(f.sdfEval, ref.sdfEval) and np.array_equal(f.iters, ref.iters), (cap, preset)
+        px, dz = fast_agreement(f, ref, oracle, W, H)
+        assert px >= PIXEL_AGREEMENT
