@@ -621,3 +621,83 @@ def test_fast_path_lazy_walk_hand_over_to_literal_interval_list(oracle, cap, mon
         assert np.array_equal(f.sdfEval, ref.sdfEval) and np.array_equal(f.iters, ref.iters), (cap, preset)
         px, dz = fast_agreement(f, ref, oracle, W, H)
         assert px >= PIXEL_AGREEMENT
+
+
+def test_fast_path_cluster_screen_more_blocks_than_ring_stages(fast_worker, oracle):
+    """150 000 spheres = 1172 clusters = 10 tensor-core blocks: more than the 8 B-tile stages, so the ring is refilled while
+    the sweeps run (config 4 itself has 7 blocks and never refills)."""
+    W, H = 48, 27
+    syn = (150000, 0x5EED0001)
+    ref = _oracle_scene(oracle, 1, "BVH", 0.3, 0.8, synthetic=syn).render(W, H, "sphere-tracer")
+    f = fast_worker.on_message(make_job(W, H, 1, "BVH", "sphere-tracer", 0.3, 0.8, synthetic=syn), shader="phong", extras=True)
+    px, dz = fast_agreement(f, ref, oracle, W, H)
+    assert px >= PIXEL_AGREEMENT, f"pixel agreement {px} (depth-only among hits {dz})"
+    assert np.array_equal(f.sdfEval, ref.sdfEval)
+    assert fast_worker.stats()["tc_passes"] > 0
+
+
+def test_fast_path_cluster_screen_item_list_overflow(monkeypatch):
+    """Two clumps of 60 000 spheres with a common centre each: every cluster of the nearer clump is within reach of every
+    query, so a 128-request pass wants ~60 000 work items — more than the shared-memory list holds; the pass then falls back
+    to evaluating every sphere for its requests.  Checked against the other all-primitives implementation of the library
+    (RM_DISABLE_TC=1: the FFMA screened search), which shares no code with the cluster screen."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    rng = np.random.default_rng(77)
+    n = 120000
+    centres = np.zeros((n, 3))
+    centres[: n // 2, 0] = -1.5
+    centres[n // 2:, 0] = 1.5
+    centres += rng.normal(0, 1e-4, (n, 3))
+    radii = rng.uniform(0.01, 0.3, n)
+    w2l = sm.get_transform_batch(centres)
+    t = np.zeros(n, np.uint8)
+    q = np.zeros((n, 4))
+    q[:, 0] = radii
+    W, H = 256, 144
+    cam = Camera()
+    cam.set_angles(0.1, 0.3)
+    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="phong")
+    frames, stats = [], []
+    for disable in ("", "1"):
+        if disable:
+            monkeypatch.setenv("RM_DISABLE_TC", "1")
+        ctx = rb.Context(0)
+        ctx.upload_scene(t, w2l, q, "BVH")
+        frames.append(ctx.render(rq, extras=True))
+        stats.append(ctx.stats())
+        ctx.close()
+    a, b = frames
+    assert stats[0]["tc_passes"] > 0 and stats[1]["tc_passes"] == 0
+    assert stats[0]["tc_items"] / stats[0]["tc_passes"] > 5000, (stats[0]["tc_passes"], stats[0]["tc_items"])  # average; full passes hit the 10 240 cap
+    assert np.array_equal(a.sdfEval, b.sdfEval) and np.array_equal(a.iters, b.iters)
+    assert np.array_equal(a.depth, b.depth) and np.array_equal(a.normal, b.normal) and np.array_equal(a.rgba, b.rgba)
+
+
+def test_full_size_cluster_screen_equals_ffma_search(monkeypatch):
+    """BASELINE config 4 at its full size (100 000 spheres, 3840 x 2160), where the oracle is far too slow: the tensor-core
+    cluster screen and the FFMA screened search (RM_DISABLE_TC=1) are independent implementations of the all-primitives
+    fallback — every plane of the frame and every diagnostic must be identical."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    t, m, q = sm.synthetic_spheres(100000).arrays()
+    W, H = 3840, 2160
+    cam = Camera()
+    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap")
+    frames, stats = [], []
+    for disable in ("", "1"):
+        if disable:
+            monkeypatch.setenv("RM_DISABLE_TC", "1")
+        ctx = rb.Context(0)
+        ctx.upload_scene(t, m, q, "BVH")
+        frames.append(ctx.render(rq))
+        stats.append(ctx.stats())
+        ctx.close()
+    a, b = frames
+    assert stats[0]["tc_passes"] > 0 and stats[1]["tc_passes"] == 0
+    for k in ("depth", "normal", "sdfEval", "iters", "rgba"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    for k in ("sum_sdf", "sum_iters", "max_sdf", "min_sdf", "sum_sdf_full", "n_hit"):
+        assert stats[0][k] == stats[1][k], k
