@@ -701,3 +701,27 @@ def test_full_size_cluster_screen_equals_ffma_search(monkeypatch):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     for k in ("sum_sdf", "sum_iters", "max_sdf", "min_sdf", "sum_sdf_full", "n_hit"):
         assert stats[0][k] == stats[1][k], k
+
+
+def test_full_size_lazy_grid_walk_equals_literal_interval_list(monkeypatch):
+    """Config 4 scene at 1920 x 1080: the lazily produced, grid-ordered interval list against the literal
+    BVH.findRayIntersections list (RM_LAZY_CAP=1 makes every ray hand over to it): identical frames."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    t, m, q = sm.synthetic_spheres(100000).arrays()
+    W, H = 1920, 1080
+    cam = Camera()
+    cam.set_angles(0.2, 1.0)
+    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="phong")
+    frames = []
+    for cap in ("", "1"):
+        if cap:
+            monkeypatch.setenv("RM_LAZY_CAP", cap)
+        ctx = rb.Context(0)
+        ctx.upload_scene(t, m, q, "BVH")
+        frames.append(ctx.render(rq))
+        ctx.close()
+    a, b = frames
+    for k in ("depth", "normal", "sdfEval", "iters", "rgba"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
