@@ -725,3 +725,23 @@ def test_full_size_lazy_grid_walk_equals_literal_interval_list(monkeypatch):
     a, b = frames
     for k in ("depth", "normal", "sdfEval", "iters", "rgba"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+@pytest.mark.parametrize("accel", ["None", "Octree", "BVH"])
+def test_empty_scene(oracle, accel):
+    """Scene.objectSDFs = []: getDistance returns MAX_DIST every time (scene.ts:145-146,183-189); both builds must march the
+    same way as the reference (no primitive arrays, empty acceleration structures)."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200.camera import Camera
+    t, m, q = np.zeros(0, np.uint8), np.zeros((0, 16), np.float32), np.zeros((0, 4))
+    W, H = 40, 24
+    cam = Camera()
+    for alg in ("sphere-tracer", "fixed-step", "adaptive-step-v3"):
+        ref = oracle.OracleScene().set_prims(t, m, q).build_accel(accel).set_camera(0.0, 0.0).render(W, H, alg)
+        for val in (True, False):
+            ctx = rb.Context(0, validate_fp64=val)
+            ctx.upload_scene(t, m, q, accel)
+            f = ctx.render(rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), algorithm=alg), extras=True)
+            ctx.close()
+            assert np.array_equal(f.sdfEval, ref.sdfEval) and np.array_equal(f.iters, ref.iters), (accel, alg, val)
+            assert np.array_equal(f.depth, ref.depth) and np.array_equal(f.normal, ref.normal), (accel, alg, val)
