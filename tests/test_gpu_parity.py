@@ -506,6 +506,9 @@ def _random_scene(rng, n):
             sm.add_box(pl, *pos, tuple(rng.uniform(0.05, 0.4, 3)), rot)
         else:
             sm.add_torus(pl, *pos, rng.uniform(0.1, 0.5), rot)
+        if rng.random() < 0.3:  # non-uniform scale folded into world->local, like createMandelbulb's mat4.scale (sceneManager.ts:62-63)
+            from cpu_raymarcher_b200 import glmatrix as gm
+            pl.world_to_local[-1] = gm.mat4_scale(pl.world_to_local[-1], tuple(rng.uniform(0.5, 2.0, 3)))
     return pl.arrays()
 
 
