@@ -1307,11 +1307,7 @@ struct LazyIv {
     bool done, overflow;
 };
 
-RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node, int cap) {
-    if (lz.count >= cap) {  // (cap < kPendCap only under the RM_LAZY_CAP test knob)
-        lz.overflow = true;
-        return;
-    }
+RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node) {
     if (lz.head + lz.count >= kPendCap) {  // compact
         for (int i = 0; i < lz.count; ++i) {
             lz.pEnter[i] = lz.pEnter[lz.head + i];
@@ -1320,7 +1316,10 @@ RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node, int ca
         }
         lz.head = 0;
         if (lz.count >= kPendCap) {
+            // The buffer can no longer be the complete sorted prefix: drop it and hand over to the literal list (everything
+            // popped so far was final, so the caller continues at the same cursor index).
             lz.overflow = true;
+            lz.count = 0;
             return;
         }
     }
@@ -1417,7 +1416,12 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
         double tE, tX;
         if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tE, tX)) continue;
         if (tX < 0.0 || tE > 10.0) continue;
-        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)node, sc.lazy_cap);
+        if (lz.overflow) break;
+        lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)node);
+    }
+    if (lz.count > sc.lazy_cap) {  // RM_LAZY_CAP test knob (normally the buffer size): force the hand-over
+        lz.overflow = true;
+        lz.count = 0;
     }
     int ax = 0;
     if (lz.tNext[1] < lz.tNext[ax]) ax = 1;
@@ -1441,9 +1445,6 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
 // next interval of the sorted list, or false when the list is exhausted
 RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz, double& enter, double& exit_) {
     for (;;) {
-        // Once an insertion has been dropped the buffer is no longer the complete sorted prefix: hand over to the literal
-        // list right away (everything popped so far was final, so the caller continues at the same cursor index).
-        if (lz.overflow) return false;
         if (lz.count > 0 && (lz.done || lz.pEnter[lz.head] < lz.safeT)) {
             enter = lz.pEnter[lz.head];
             exit_ = lz.pExit[lz.head];
