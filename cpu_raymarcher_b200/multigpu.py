@@ -225,13 +225,16 @@ class FrameSharder:
         return st
 
     def download_frame(self, shader=None) -> dict:
-        """Rank 0: copy the assembled full-frame planes to host arrays (the reference's frame buffers, main.ts:324-329)."""
+        """Rank 0: copy the assembled full-frame planes to host arrays (the reference's frame buffers, main.ts:324-329).
+        The arrays are views over page-locked memory that the next download_frame overwrites — copy what must be kept."""
         W, H = self.size
         n = W * H
-        out = {"depth": np.empty(n, np.uint8), "normal": np.empty(3 * n, np.uint8), "sdfEval": np.empty(n, np.uint16),
-               "iters": np.empty(n, np.uint16)}
+        # page-locked planes owned by the context (rm_host_alloc), reused from frame to frame: the D2H runs at PCIe speed
+        pa = self.ctx._pinned_array
+        out = {"depth": pa("mg_depth", n, np.uint8), "normal": pa("mg_normal", 3 * n, np.uint8), "sdfEval": pa("mg_sdf", n, np.uint16),
+               "iters": pa("mg_iters", n, np.uint16)}
         if shader is not None:
-            out["rgba"] = np.empty(4 * n, np.uint8)
+            out["rgba"] = pa("mg_rgba", 4 * n, np.uint8)
         for k, name in (("depth", "depth"), ("normal", "normal"), ("sdfEval", "sdf"), ("iters", "iters"), ("rgba", "rgba")):
             if k in out:
                 self.ctx.memcpy_d2h(out[k], self.frame_ptr + self.layout[name])
@@ -254,6 +257,8 @@ class FrameSharder:
             return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h}
         import torch.distributed as dist
         self.render_frame(job, shader)
+        if self.rank == 0:
+            self.download_frame(shader)  # warm-up allocates the page-locked planes
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
