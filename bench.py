@@ -313,6 +313,12 @@ def main():
                                "sample": f"{len(rows)} of {H} rows (evenly spaced) x {W} px, {r['seconds']:.1f} s; "
                                          "C++ restatement of the reference TS path (not V8)",
                                "sdf_evals_per_s": r["evals_s"], "accel_build_ms": t_accel}
+        if threads > 4:
+            # the reference never runs more than 4 workers (main.ts:318): the same sample at its real cap
+            sub = rows[np.linspace(0, len(rows) - 1, num=min(len(rows), max(4, len(rows) // (threads // 4))), dtype=np.int64)]
+            r4 = run_cpu(s, wl, np.unique(sub), 4)
+            out["cpu_baseline"]["value_at_4_workers"] = r4["mrays_s"]
+            out["cpu_baseline"]["sample_at_4_workers"] = f"{len(np.unique(sub))} rows, {r4['seconds']:.1f} s (the reference's worker cap, main.ts:318)"
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
