@@ -54,12 +54,27 @@ struct rm_ctx {
     rm_stats_t last{};
     // band staging for rm_render (device planes + pinned host mirror)
     DevBuf d_frame, h_frame;
+    // early download of finished row bands (rm_render into page-locked planes)
+    cudaStream_t copy_stream = nullptr;
+    unsigned int* h_band_flags = nullptr;  // page-locked, written by the kernel (kMaxBands words)
+    struct EarlyCopy {
+        bool on = false;
+        int n_bands = 0, band_rows = 0, band_h = 0, width = 0;
+        struct Plane { char* dst; const char* src; size_t bpp; } planes[9];
+        int n_planes = 0;
+    } early;
     // user allocations (rm_alloc / rm_host_alloc)
     std::vector<void*> user_allocs;
     std::vector<std::pair<char*, size_t>> host_allocs;
 };
 
 namespace {
+
+constexpr size_t kEarlyCopyMinBytes = 16u << 20;  // frames below this are downloaded in one piece after the kernel
+bool early_copy_enabled() {  // RM_EARLY_COPY=0: test / measurement knob, read per call
+    const char* e = std::getenv("RM_EARLY_COPY");
+    return !(e && e[0] == '0');
+}
 
 int fail(rm_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -210,6 +225,12 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.sdf_u32 = out->sdf_eval_u32;
     P.depth_f64 = out->depth_f64;
     P.stats = c->d_stats;
+    const bool early = c->early.on && P.n_tiles > 0;
+    if (early) {
+        P.band_flags = c->h_band_flags;
+        P.band_rows = c->early.band_rows;
+        for (int b = 0; b < kMaxBands; ++b) c->h_band_flags[b] = 0u;
+    }
 
     DevStats init{};
     init.min_sdf = 0xffffffffu;
@@ -225,6 +246,29 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     }
     CU(c, cudaEventRecord(c->ev1, stream));
     CU(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, stream));
+    if (early) {
+        // download each row band as soon as the kernel reports it finished; what is left goes out after the kernel
+        const rm_ctx::EarlyCopy& ec = c->early;
+        bool sent[kMaxBands] = {};
+        auto send = [&](int b) -> cudaError_t {
+            const size_t y0 = (size_t)b * ec.band_rows, y1 = std::min<size_t>(y0 + ec.band_rows, (size_t)ec.band_h);
+            for (int k = 0; k < ec.n_planes; ++k) {
+                const size_t off = y0 * ec.width * ec.planes[k].bpp, bytes = (y1 - y0) * ec.width * ec.planes[k].bpp;
+                cudaError_t e = cudaMemcpyAsync(ec.planes[k].dst + off, ec.planes[k].src + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e != cudaSuccess) return e;
+            }
+            sent[b] = true;
+            return cudaSuccess;
+        };
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) CU(c, q);
+            for (int b = 0; b < ec.n_bands; ++b)
+                if (!sent[b] && (q == cudaSuccess || *(volatile unsigned int*)&c->h_band_flags[b])) CU(c, send(b));
+            if (q == cudaSuccess) break;
+        }
+        CU(c, cudaStreamSynchronize(c->copy_stream));
+    }
     CU(c, cudaStreamSynchronize(stream));
     float ms = 0.f;
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -320,6 +364,8 @@ int rm_create(rm_ctx** out, int device, unsigned flags) {
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaMalloc((void**)&c->d_stats, sizeof(DevStats)));
     CUC(cudaMallocHost((void**)&c->h_stats, sizeof(DevStats)));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUC(cudaHostAlloc((void**)&c->h_band_flags, kMaxBands * sizeof(unsigned int), cudaHostAllocMapped));
 #undef CUC
     *out = c;
     return RM_OK;
@@ -336,6 +382,8 @@ void rm_destroy(rm_ctx* c) {
     if (c->h_frame.p) cudaFreeHost(c->h_frame.p);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->h_band_flags) cudaFreeHost(c->h_band_flags);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -826,8 +874,6 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     dev.depth_f32 = out->depth_f32 ? (float*)(d + oDf) : nullptr;
     dev.sdf_eval_u32 = out->sdf_eval_u32 ? (uint32_t*)(d + oSu) : nullptr;
     dev.depth_f64 = out->depth_f64 ? (double*)(d + oD64) : nullptr;
-    rc = render_device_locked(c, rq, &dev, c->stream);
-    if (rc) return rc;
     auto pinned = [&](const void* p, size_t bytes) {
         if (!p) return true;
         for (auto& h : c->host_allocs)
@@ -837,7 +883,36 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     const bool direct = pinned(out->depth, np) && pinned(out->normal, 3 * np) && pinned(out->sdf_eval, 2 * np) && pinned(out->iters, 2 * np) &&
                         pinned(wantRgba ? out->rgba : nullptr, 4 * np) && pinned(wantRgba2 ? out->rgba_analytics : nullptr, 4 * np) &&
                         pinned(out->depth_f32, 4 * np) && pinned(out->sdf_eval_u32, 4 * np) && pinned(out->depth_f64, 8 * np);
-    if (np > 0 && direct) {
+    // big frames into page-locked planes: the D2H of finished row bands overlaps the rest of the render
+    rm_ctx::EarlyCopy& ec = c->early;
+    ec = rm_ctx::EarlyCopy();
+    if (direct && rq->stripe_count <= 1 && total >= kEarlyCopyMinBytes && early_copy_enabled()) {
+        ec.n_bands = (int)std::min<size_t>(kMaxBands, total / (kEarlyCopyMinBytes / 2));
+        ec.band_rows = (bandH + ec.n_bands - 1) / ec.n_bands;
+        ec.n_bands = (bandH + ec.band_rows - 1) / ec.band_rows;
+        ec.band_h = bandH;
+        ec.width = rq->width;
+        auto add = [&](void* dst, size_t off, size_t bpp) {
+            if (dst) ec.planes[ec.n_planes++] = {(char*)dst, (const char*)d + off, bpp};
+        };
+        add(out->depth, oDepth, 1);
+        add(out->normal, oNormal, 3);
+        add(out->sdf_eval, oSdf, 2);
+        add(out->iters, oIters, 2);
+        add(wantRgba ? out->rgba : nullptr, oRgba, 4);
+        add(wantRgba2 ? out->rgba_analytics : nullptr, oRgba2, 4);
+        add(out->depth_f32, oDf, 4);
+        add(out->sdf_eval_u32, oSu, 4);
+        add(out->depth_f64, oD64, 8);
+        ec.on = ec.n_bands > 1;
+    }
+    rc = render_device_locked(c, rq, &dev, c->stream);
+    const bool copied = ec.on;
+    ec.on = false;
+    if (rc) return rc;
+    if (np > 0 && direct && copied) {
+        // every band already went out during the render
+    } else if (np > 0 && direct) {
         // caller's planes are page-locked memory of this context: DMA straight into them
         auto cp = [&](void* dst, size_t off, size_t bytes) { return dst ? cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
         CU(c, cp(out->depth, oDepth, np));

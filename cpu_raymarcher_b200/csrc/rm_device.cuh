@@ -1666,6 +1666,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     __shared__ float shPartBest[kWarpsPerCta * kBatch];  // partial search results of the batch in flight: [warp][request] (FFMA) or [half][row] (TC)
     __shared__ int shPartCode[kWarpsPerCta * kBatch];
     __shared__ unsigned shTail, shHead, shGo, shStuck, shFinished;
+    __shared__ unsigned shBandFin[kWarpsPerCta][kMaxBands];  // early download: pixels this warp finalised per row band, not yet published
     __shared__ __align__(8) unsigned long long shTcBar[kTcStages + kTcGroups];
     __shared__ unsigned shTcDrain[kTcGroups];
     __shared__ unsigned long long shTcKey[kTcBlock];  // per request: (flipped fp32 distance << 32 | sorted sphere index), atomicMin
@@ -1702,6 +1703,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
     }
     shReady[threadIdx.x] = 0u;
+    if (threadIdx.x < kWarpsPerCta * kMaxBands) (&shBandFin[0][0])[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         shTail = 0u;
         shHead = 0u;
@@ -1748,6 +1750,30 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     // warp-uniform work-queue cursor
     int tile = -1, tilePos = kTileW * kTileH;
     bool queueEmpty = false;
+
+    // Early download (rm_render into page-locked planes): publish this warp's finished-pixel counts per row band;
+    // the thread that completes a band raises its flag in host memory and the host starts that band's D2H while the
+    // kernel is still running.  Called warp-uniformly once per tile and at exit: one fence per tile, not per pixel.
+    auto publish_bands = [&]() {
+        if (!P.band_flags) return;
+        __syncwarp();  // orders every lane's pixel stores before lane b's fence below
+        if (lane < kMaxBands) {
+            const unsigned n = shBandFin[warpId][lane];
+            if (n) {
+                shBandFin[warpId][lane] = 0u;
+                const int rows = min(P.band_rows, (P.y_end - P.y_start) - lane * P.band_rows);
+                // release at gpu scope: the pixel stores are performed before the count becomes visible.  Not
+                // __threadfence() + atomicAdd: that fence also invalidates the SM's L1 (CCTL.IVALL), once per tile
+                unsigned prev;
+                asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(prev) : "l"(&P.stats->band_done[lane]), "r"(n) : "memory");
+                if (prev + n == (unsigned)rows * (unsigned)P.width) {
+                    __threadfence_system();
+                    *(volatile unsigned int*)&P.band_flags[lane] = 1u;
+                }
+            }
+        }
+        __syncwarp();
+    };
 
     // Warp scheduler.  Expensive, warp-serialising stages are deferred until enough lanes want them: BVH
     // ray set-up (a full tree traversal) runs when initLanes lanes are free or nothing else can progress;
@@ -1903,6 +1929,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
         while (idle && !queueEmpty) {
             if (tilePos >= kTileW * kTileH) {
+                publish_bands();
                 unsigned t = 0;
                 if (lane == 0) t = atomicAdd(&P.stats->queue, 1u);
                 t = __shfl_sync(kFull, t, 0);
@@ -2357,6 +2384,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             st.max_iters = max(st.max_iters, it16);
             st.min_iters = min(st.min_iters, it16);
             r.phase = PH_IDLE;
+            if (P.band_flags) atomicAdd(&shBandFin[warpId][r.py / P.band_rows], 1u);  // early download, flushed per tile
         }
 
         // ---- (g) cooperative mode: publish whether this warp can still make progress on its own ----
@@ -2397,6 +2425,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             if (warpId == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(512u) : "memory");
         }
     }
+    publish_bands();  // pixels finalised since the warp's last tile fetch
     // ---- epilogue: diagnostics (main.ts:527-548) — warp reduce, one atomic set per warp ----
     unsigned long long s0 = warp_sum_u64(st.sum_sdf), s1 = warp_sum_u64(st.sum_iters);
     unsigned long long s2 = warp_sum_u64(st.sum_sdf_full), s3 = warp_sum_u64(st.sum_iters_full);

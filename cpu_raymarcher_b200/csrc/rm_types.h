@@ -116,6 +116,8 @@ struct DevScene {
 };
 
 // Per-launch statistics accumulated by the render kernel's epilogue (one atomic set per warp).
+constexpr int kMaxBands = 16;  // row bands of one rm_render whose D2H is started while the kernel still runs
+
 struct DevStats {
     unsigned long long sum_sdf, sum_iters;            // on the u16-wrapped per-pixel values
     unsigned long long sum_sdf_full, sum_iters_full;  // un-wrapped
@@ -128,6 +130,7 @@ struct DevStats {
     unsigned long long t_total, t_search, t_barrier, t_stuck;  // RM_PHASE_TIMING builds: warp-cycles by phase
     unsigned long long n_pass, n_req, n_rearm, t_tc[4];        // RM_PHASE_TIMING builds: cooperative passes, requests served, buffer re-arms and
                                                                // tc_pass cycles by step as seen by thread 0
+    unsigned int band_done[kMaxBands];  // rm_render with page-locked planes: pixels finalised per row band (early D2H)
     unsigned int pad_;
 };
 
@@ -153,6 +156,10 @@ struct RenderParams {
     uint32_t* sdf_u32;
     double* depth_f64;
     DevStats* stats;
+    // early download (rm_render only; null otherwise): the thread that finalises the last pixel of a row band raises
+    // band_flags[band] in page-locked host memory, and the host starts that band's D2H while the kernel still runs
+    unsigned int* band_flags;
+    int32_t band_rows;
 };
 
 struct ShadeParams {

@@ -239,7 +239,9 @@ int rm_probe_fp32_peak(rm_ctx* ctx, double* tflops);
 
 /* Pinned (page-locked) host memory owned by the context.  Result planes that live in it are filled by direct
  * asynchronous D2H copies (no staging copy on the host); any other host pointer still works through a staging
- * buffer.  A Node addon would back its ArrayBuffers with this memory (napi_create_external_arraybuffer). */
+ * buffer.  For frames of 16 MB and more the copies of finished row bands are issued while the kernel is still
+ * rendering the rest of the frame (the kernel flags each completed band), so rm_render costs about the kernel
+ * time.  A Node addon would back its ArrayBuffers with this memory (napi_create_external_arraybuffer). */
 int rm_host_alloc(rm_ctx* ctx, size_t bytes, void** host_ptr);
 int rm_host_free(rm_ctx* ctx, void* host_ptr);
 

@@ -476,6 +476,33 @@ def test_pinned_result_planes_match_pageable(fast_worker):
     assert np.array_equal(c.normal, d.normal) and c.depth.size == 64 * 40
 
 
+@pytest.mark.parametrize("accel,W,H", [("BVH", 2560, 1437), ("None", 4096, 1031), ("Octree", 1920, 1080)])
+def test_early_band_download_matches_pageable(fast_worker, monkeypatch, accel, W, H):
+    """Big frames into page-locked planes: row bands are downloaded while the kernel still runs (the kernel flags each
+    finished band). Same bytes as the pageable path and as the same call with the early download switched off."""
+    job = make_job(W, H, 3, accel, "sphere-tracer")
+    kw = dict(shader="phong", shader_analytics="sdf-heatmap", extras=True)
+    a = fast_worker.on_message(job, **kw)
+    keys = ("depth", "normal", "sdfEval", "iters", "rgba", "rgba_analytics", "depth_f32", "sdf_u32", "depth_f64")
+    for rep in range(2):  # the second pass reuses the planes: stale bytes of the first must all be overwritten
+        b = fast_worker.on_message(job, pinned=True, **kw)
+        for k in keys:
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (k, rep)
+        b.depth[:] = 0
+        b.rgba[:] = 0
+        b.depth_f64[:] = 0
+    monkeypatch.setenv("RM_EARLY_COPY", "0")
+    c = fast_worker.on_message(job, pinned=True, **kw)
+    for k in keys:
+        assert np.array_equal(getattr(a, k), getattr(c, k)), k
+    # planes only (no shader, no extras): fewer planes, fewer bands
+    monkeypatch.delenv("RM_EARLY_COPY")
+    d = fast_worker.on_message(make_job(3840, 2160, 0, "None"), pinned=True)
+    e = fast_worker.on_message(make_job(3840, 2160, 0, "None"))
+    for k in ("depth", "normal", "sdfEval", "iters"):
+        assert np.array_equal(getattr(d, k), getattr(e, k)), k
+
+
 def test_multi_gpu_fused_gather_matches_single_gpu():
     """N >= 2 GPUs only: torchrun, one process per GPU, CUDA-IPC fused gather + NCCL stats all-reduce."""
     import subprocess
