@@ -79,7 +79,7 @@ class Stats(C.Structure):
 # every symbol include/rm.h declares
 EXPORTS = ["rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_upload_scene",
            "rm_build_bvh", "rm_build_octree", "rm_build_bvh_scene", "rm_build_octree_scene", "rm_render", "rm_render_device", "rm_stats", "rm_shade", "rm_alloc",
-           "rm_free", "rm_host_alloc", "rm_host_free", "rm_probe_fp32_peak", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
+           "rm_free", "rm_host_alloc", "rm_host_free", "rm_host_register", "rm_host_unregister", "rm_probe_fp32_peak", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
 
 _LIB = None
 
@@ -111,6 +111,8 @@ def lib():
         L.rm_probe_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.rm_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.rm_host_free.argtypes = [vp, vp]
+        L.rm_host_register.argtypes = [vp, vp, C.c_size_t]
+        L.rm_host_unregister.argtypes = [vp, vp]
         L.rm_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
         L.rm_free.argtypes = [vp, vp]
         L.rm_ipc_export.argtypes = [vp, vp, vp]

@@ -60,12 +60,14 @@ struct rm_ctx {
     struct EarlyCopy {
         bool on = false;
         int n_bands = 0, band_rows = 0, band_h = 0, width = 0;
+        int stripe_rows = 0, stripe_count = 1, stripe_index = 0;  // row stripes: only the owned rows are copied
         struct Plane { char* dst; const char* src; size_t bpp; } planes[9];
         int n_planes = 0;
     } early;
-    // user allocations (rm_alloc / rm_host_alloc)
+    // user allocations (rm_alloc / rm_host_alloc) and caller memory page-locked by rm_host_register
     std::vector<void*> user_allocs;
     std::vector<std::pair<char*, size_t>> host_allocs;
+    std::vector<std::pair<char*, size_t>> host_registered;
 };
 
 namespace {
@@ -74,6 +76,67 @@ constexpr size_t kEarlyCopyMinBytes = 16u << 20;  // frames below this are downl
 bool early_copy_enabled() {  // RM_EARLY_COPY=0: test / measurement knob, read per call
     const char* e = std::getenv("RM_EARLY_COPY");
     return !(e && e[0] == '0');
+}
+
+// Rows of [y0, y1) this request owns, as maximal contiguous spans: everything without row stripes, else the pieces of
+// the owned stripes (stripe s covers rows [s * stripe_rows, (s + 1) * stripe_rows), owned when s % count == index).
+template <typename F>
+void for_owned_spans(int stripe_rows, int stripe_count, int stripe_index, int y0, int y1, F&& fn) {
+    if (y1 <= y0) return;
+    if (stripe_count <= 1) {
+        fn(y0, y1 - y0);
+        return;
+    }
+    for (int sIdx = y0 / stripe_rows; sIdx * stripe_rows < y1; ++sIdx) {
+        if (sIdx % stripe_count != stripe_index) continue;
+        const int a = std::max(y0, sIdx * stripe_rows), b = std::min(y1, (sIdx + 1) * stripe_rows);
+        if (b > a) fn(a, b - a);
+    }
+}
+
+// D2H of the owned rows of [y0, y1) of every plane.  With row stripes the full stripes of a plane go out as ONE strided
+// 2-D copy (pitch = one stripe period), so a band costs one or two copy calls per plane however many stripes it holds.
+cudaError_t copy_owned_rows(const rm_ctx::EarlyCopy& ec, int y0, int y1, cudaStream_t s) {
+    y1 = std::min(y1, ec.band_h);
+    if (y1 <= y0) return cudaSuccess;
+    for (int k = 0; k < ec.n_planes; ++k) {
+        const size_t rowB = (size_t)ec.width * ec.planes[k].bpp;
+        char* dst = ec.planes[k].dst;
+        const char* src = ec.planes[k].src;
+        if (ec.stripe_count <= 1) {
+            cudaError_t e = cudaMemcpyAsync(dst + y0 * rowB, src + y0 * rowB, (size_t)(y1 - y0) * rowB, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) return e;
+            continue;
+        }
+        // full owned stripes whose start rows are one period apart -> one 2-D copy; ragged pieces -> 1-D copies
+        int firstFull = -1, nFull = 0;
+        cudaError_t err = cudaSuccess;
+        const size_t period = (size_t)ec.stripe_rows * ec.stripe_count;
+        auto flush = [&]() {
+            if (nFull > 0 && err == cudaSuccess)
+                err = cudaMemcpy2DAsync(dst + firstFull * rowB, period * rowB, src + firstFull * rowB, period * rowB,
+                                        (size_t)ec.stripe_rows * rowB, (size_t)nFull, cudaMemcpyDeviceToHost, s);
+            nFull = 0;
+            firstFull = -1;
+        };
+        for_owned_spans(ec.stripe_rows, ec.stripe_count, ec.stripe_index, y0, y1, [&](int a, int rows) {
+            if (rows == ec.stripe_rows && (nFull == 0 || (size_t)a == firstFull + nFull * period)) {
+                if (nFull == 0) firstFull = a;
+                ++nFull;
+                return;
+            }
+            flush();
+            if (rows == ec.stripe_rows) {
+                firstFull = a;
+                nFull = 1;
+            } else if (err == cudaSuccess) {
+                err = cudaMemcpyAsync(dst + a * rowB, src + a * rowB, (size_t)rows * rowB, cudaMemcpyDeviceToHost, s);
+            }
+        });
+        flush();
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
 }
 
 int fail(rm_ctx* c, int code, const char* fmt, ...) {
@@ -229,7 +292,13 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     if (early) {
         P.band_flags = c->h_band_flags;
         P.band_rows = c->early.band_rows;
-        for (int b = 0; b < kMaxBands; ++b) c->h_band_flags[b] = 0u;
+        for (int b = 0; b < kMaxBands; ++b) {
+            c->h_band_flags[b] = 0u;
+            uint64_t rows = 0;
+            for_owned_spans(P.stripe_rows, P.stripe_count, P.stripe_index, b * P.band_rows, std::min((b + 1) * P.band_rows, bandH),
+                            [&](int, int n) { rows += (uint64_t)n; });
+            P.band_px[b] = b < c->early.n_bands ? (uint32_t)(rows * (uint64_t)rq->width) : 0u;
+        }
     }
 
     DevStats init{};
@@ -251,14 +320,8 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
         const rm_ctx::EarlyCopy& ec = c->early;
         bool sent[kMaxBands] = {};
         auto send = [&](int b) -> cudaError_t {
-            const size_t y0 = (size_t)b * ec.band_rows, y1 = std::min<size_t>(y0 + ec.band_rows, (size_t)ec.band_h);
-            for (int k = 0; k < ec.n_planes; ++k) {
-                const size_t off = y0 * ec.width * ec.planes[k].bpp, bytes = (y1 - y0) * ec.width * ec.planes[k].bpp;
-                cudaError_t e = cudaMemcpyAsync(ec.planes[k].dst + off, ec.planes[k].src + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream);
-                if (e != cudaSuccess) return e;
-            }
             sent[b] = true;
-            return cudaSuccess;
+            return copy_owned_rows(ec, b * ec.band_rows, (b + 1) * ec.band_rows, c->copy_stream);
         };
         for (;;) {
             const cudaError_t q = cudaStreamQuery(stream);
@@ -378,6 +441,7 @@ void rm_destroy(rm_ctx* c) {
     free_scene(c);
     for (void* p : c->user_allocs) cudaFree(p);
     for (auto& h : c->host_allocs) cudaFreeHost(h.first);
+    for (auto& h : c->host_registered) cudaHostUnregister(h.first);
     if (c->d_frame.p) cudaFree(c->d_frame.p);
     if (c->h_frame.p) cudaFreeHost(c->h_frame.p);
     if (c->d_stats) cudaFree(c->d_stats);
@@ -876,8 +940,9 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     dev.depth_f64 = out->depth_f64 ? (double*)(d + oD64) : nullptr;
     auto pinned = [&](const void* p, size_t bytes) {
         if (!p) return true;
-        for (auto& h : c->host_allocs)
-            if ((const char*)p >= h.first && (const char*)p + bytes <= h.first + h.second) return true;
+        for (auto* v : {&c->host_allocs, &c->host_registered})
+            for (auto& h : *v)
+                if ((const char*)p >= h.first && (const char*)p + bytes <= h.first + h.second) return true;
         return false;
     };
     const bool direct = pinned(out->depth, np) && pinned(out->normal, 3 * np) && pinned(out->sdf_eval, 2 * np) && pinned(out->iters, 2 * np) &&
@@ -886,12 +951,17 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     // big frames into page-locked planes: the D2H of finished row bands overlaps the rest of the render
     rm_ctx::EarlyCopy& ec = c->early;
     ec = rm_ctx::EarlyCopy();
-    if (direct && rq->stripe_count <= 1 && total >= kEarlyCopyMinBytes && early_copy_enabled()) {
-        ec.n_bands = (int)std::min<size_t>(kMaxBands, total / (kEarlyCopyMinBytes / 2));
-        ec.band_rows = (bandH + ec.n_bands - 1) / ec.n_bands;
-        ec.n_bands = (bandH + ec.band_rows - 1) / ec.band_rows;
-        ec.band_h = bandH;
-        ec.width = rq->width;
+    // With row stripes (rq->stripe_count > 1) only the OWNED rows of the band are ever written to the caller's planes, so
+    // several contexts (one per GPU, one process each) can fill one shared host frame without touching each other's rows.
+    const bool striped = rq->stripe_count > 1;
+    ec.band_h = bandH;
+    ec.width = rq->width;
+    if (striped) {
+        ec.stripe_rows = rq->stripe_rows;
+        ec.stripe_count = rq->stripe_count;
+        ec.stripe_index = rq->stripe_index;
+    }
+    {
         auto add = [&](void* dst, size_t off, size_t bpp) {
             if (dst) ec.planes[ec.n_planes++] = {(char*)dst, (const char*)d + off, bpp};
         };
@@ -904,6 +974,15 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
         add(out->depth_f32, oDf, 4);
         add(out->sdf_eval_u32, oSu, 4);
         add(out->depth_f64, oD64, 8);
+    }
+    if (direct && total >= kEarlyCopyMinBytes && early_copy_enabled()) {
+        ec.n_bands = (int)std::min<size_t>(kMaxBands, total / (kEarlyCopyMinBytes / 2));
+        ec.band_rows = (bandH + ec.n_bands - 1) / ec.n_bands;
+        if (striped) {  // whole stripe periods per band: every band then holds the same pattern of owned stripes
+            const int period = rq->stripe_rows * rq->stripe_count;
+            ec.band_rows = (ec.band_rows + period - 1) / period * period;
+        }
+        ec.n_bands = (bandH + ec.band_rows - 1) / ec.band_rows;
         ec.on = ec.n_bands > 1;
     }
     rc = render_device_locked(c, rq, &dev, c->stream);
@@ -913,33 +992,22 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     if (np > 0 && direct && copied) {
         // every band already went out during the render
     } else if (np > 0 && direct) {
-        // caller's planes are page-locked memory of this context: DMA straight into them
-        auto cp = [&](void* dst, size_t off, size_t bytes) { return dst ? cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
-        CU(c, cp(out->depth, oDepth, np));
-        CU(c, cp(out->normal, oNormal, 3 * np));
-        CU(c, cp(out->sdf_eval, oSdf, 2 * np));
-        CU(c, cp(out->iters, oIters, 2 * np));
-        CU(c, cp(wantRgba ? out->rgba : nullptr, oRgba, 4 * np));
-        CU(c, cp(wantRgba2 ? out->rgba_analytics : nullptr, oRgba2, 4 * np));
-        CU(c, cp(out->depth_f32, oDf, 4 * np));
-        CU(c, cp(out->sdf_eval_u32, oSu, 4 * np));
-        CU(c, cp(out->depth_f64, oD64, 8 * np));
+        // caller's planes are page-locked (rm_host_alloc / rm_host_register): DMA straight into them
+        CU(c, copy_owned_rows(ec, 0, bandH, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
     } else if (np > 0) {
-        // one D2H of the whole staging block into pinned memory, then scatter to the caller's planes
+        // one D2H of the whole staging block into pinned memory, then scatter the owned rows to the caller's planes
         if ((rc = ensure(c, c->h_frame, total + 256, true))) return rc;
         CU(c, cudaMemcpyAsync(c->h_frame.p, d, total, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
-        const uint8_t* h = (const uint8_t*)c->h_frame.p;
-        std::memcpy(out->depth, h + oDepth, np);
-        std::memcpy(out->normal, h + oNormal, 3 * np);
-        std::memcpy(out->sdf_eval, h + oSdf, 2 * np);
-        std::memcpy(out->iters, h + oIters, 2 * np);
-        if (wantRgba) std::memcpy(out->rgba, h + oRgba, 4 * np);
-        if (wantRgba2) std::memcpy(out->rgba_analytics, h + oRgba2, 4 * np);
-        if (out->depth_f32) std::memcpy(out->depth_f32, h + oDf, 4 * np);
-        if (out->sdf_eval_u32) std::memcpy(out->sdf_eval_u32, h + oSu, 4 * np);
-        if (out->depth_f64) std::memcpy(out->depth_f64, h + oD64, 8 * np);
+        const char* h = (const char*)c->h_frame.p;
+        for (int k = 0; k < ec.n_planes; ++k) {
+            const size_t rowB = (size_t)rq->width * ec.planes[k].bpp;
+            const char* src = h + (ec.planes[k].src - (const char*)d);
+            char* dst = ec.planes[k].dst;
+            for_owned_spans(ec.stripe_rows ? ec.stripe_rows : 1, ec.stripe_count, ec.stripe_index, 0, bandH,
+                            [&](int a, int rows) { std::memcpy(dst + a * rowB, src + a * rowB, (size_t)rows * rowB); });
+        }
     }
     c->last.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     return RM_OK;
@@ -1017,6 +1085,28 @@ int rm_host_free(rm_ctx* c, void* host_ptr) {
             return RM_OK;
         }
     return fail(c, RM_ERR_ARG, "pointer was not allocated by rm_host_alloc on this context");
+}
+
+int rm_host_register(rm_ctx* c, void* host_ptr, size_t bytes) {
+    if (!c || !host_ptr || !bytes) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    c->host_registered.emplace_back((char*)host_ptr, bytes);
+    return RM_OK;
+}
+int rm_host_unregister(rm_ctx* c, void* host_ptr) {
+    if (!c) return RM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (size_t i = 0; i < c->host_registered.size(); ++i)
+        if (c->host_registered[i].first == (char*)host_ptr) {
+            CU(c, cudaSetDevice(c->device));
+            CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaHostUnregister(host_ptr));
+            c->host_registered.erase(c->host_registered.begin() + (long)i);
+            return RM_OK;
+        }
+    return fail(c, RM_ERR_ARG, "pointer was not registered by rm_host_register on this context");
 }
 
 int rm_alloc(rm_ctx* c, size_t bytes, void** dev_ptr) {

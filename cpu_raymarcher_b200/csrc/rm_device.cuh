@@ -1761,12 +1761,11 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             const unsigned n = shBandFin[warpId][lane];
             if (n) {
                 shBandFin[warpId][lane] = 0u;
-                const int rows = min(P.band_rows, (P.y_end - P.y_start) - lane * P.band_rows);
                 // release at gpu scope: the pixel stores are performed before the count becomes visible.  Not
                 // __threadfence() + atomicAdd: that fence also invalidates the SM's L1 (CCTL.IVALL), once per tile
                 unsigned prev;
                 asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(prev) : "l"(&P.stats->band_done[lane]), "r"(n) : "memory");
-                if (prev + n == (unsigned)rows * (unsigned)P.width) {
+                if (prev + n == P.band_px[lane]) {
                     __threadfence_system();
                     *(volatile unsigned int*)&P.band_flags[lane] = 1u;
                 }

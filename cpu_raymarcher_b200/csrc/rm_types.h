@@ -160,6 +160,7 @@ struct RenderParams {
     // band_flags[band] in page-locked host memory, and the host starts that band's D2H while the kernel still runs
     unsigned int* band_flags;
     int32_t band_rows;
+    uint32_t band_px[kMaxBands];  // pixels of this launch inside each band (with row stripes: the owned rows only)
 };
 
 struct ShadeParams {

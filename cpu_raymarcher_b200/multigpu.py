@@ -13,7 +13,11 @@ copied into the full-frame buffers on the main thread and the diagnostics summed
     every other rank maps them through CUDA IPC and its render kernel stores its pixels straight into
     rank 0's HBM over NVLink — no staging buffer, no separate gather collective;
   * diagnostics "reduce" (main.ts:527-543): each kernel's epilogue leaves 12 words per GPU; one NCCL
-    all-reduce per operator (sum / max / min) combines them.
+    all-reduce per operator (sum / max / min) combines them;
+  * frames wanted in HOST memory (the main thread's frame buffers, main.ts:324-329): `render_frame_host`.
+    The frame lives in one shared-memory block that every rank maps and page-locks (rm_host_register);
+    each rank calls rm_render with its stripes and the shared planes, so every GPU downloads its own rows
+    over its own PCIe link while its kernel is still rendering — no gather at all, N links instead of one.
 
 With world_size == 1 every collective disappears and this is a thin wrapper over rm_render_device.
 `render_band` can be replaced (tests inject a CPU renderer to exercise the partition / merge logic
@@ -22,6 +26,8 @@ under gloo without a GPU).
 from __future__ import annotations
 
 import ctypes as C
+import mmap
+import os
 import time
 
 import numpy as np
@@ -78,6 +84,8 @@ class FrameSharder:
         self.frame_owned = False
         self.layout = None
         self.size = None
+        self.host_frame = None     # (mmap, uint8 view) of the shared host frame of render_frame_host
+        self.host_size = None
 
     # ------------------------------------------------------------------ scene
     def setup_scene(self, job: dict):
@@ -161,13 +169,27 @@ class FrameSharder:
             self.frame_ptr = self.ctx.ipc_open(h_t.cpu().numpy().tobytes())  # rank 0's planes, reachable over NVLink
             self.frame_owned = False
 
+    def _release_host(self):
+        if self.host_frame is not None:
+            mm, view = self.host_frame
+            self.ctx.host_unregister(view)
+            self.host_frame = None
+            self.host_size = None
+            del view
+            try:
+                mm.close()
+            except BufferError:  # a caller still holds plane views: the mapping goes when they do
+                pass
+
     def release(self):
+        self._release_host()
         if self.frame_ptr is not None:
             if self.frame_owned:
                 self.ctx.free(self.frame_ptr)
             else:
                 self.ctx.ipc_close(self.frame_ptr)
         self.frame_ptr = None
+        self.size = None
 
     def _result(self, shader):
         lay, base = self.layout, self.frame_ptr
@@ -196,7 +218,10 @@ class FrameSharder:
         self._ensure_frame(W, H)
         rq = self._request(job, shader)
         self.ctx.render_device(rq, self._result(shader))  # synchronises this rank's stream
-        st = self.ctx.stats()
+        return self._reduce_frame_stats(self.ctx.stats())
+
+    def _reduce_frame_stats(self, st: dict) -> dict:
+        """Frame-level diagnostics (main.ts:527-543) from this rank's share: three NCCL all-reduces."""
         st["n_prims"] = self.ctx.n_prims
         if self.world == 1:
             st["frame_ms"] = st["kernel_ms"]
@@ -240,10 +265,61 @@ class FrameSharder:
                 self.ctx.memcpy_d2h(out[k], self.frame_ptr + self.layout[name])
         return out
 
+    # ------------------------------------------------------------------ one frame into shared HOST planes
+    def _ensure_host_frame(self, width: int, height: int):
+        if self.host_size == (width, height):
+            return
+        self._release_host()
+        lay = plane_layout(width, height)
+        if self.world == 1:
+            name = None
+            mm = mmap.mmap(-1, lay["total"])
+        else:
+            import torch.distributed as dist
+            box = [f"/dev/shm/rm_b200_frame_{os.getpid()}_{width}x{height}" if self.rank == 0 else None]
+            if self.rank == 0:
+                fd = os.open(box[0], os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+                os.ftruncate(fd, lay["total"])
+            dist.broadcast_object_list(box, src=0)
+            name = box[0]
+            if self.rank != 0:
+                fd = os.open(name, os.O_RDWR)
+            mm = mmap.mmap(fd, lay["total"])
+            os.close(fd)
+            dist.barrier()  # every rank has mapped the block: the name can go, the memory stays until the last unmap
+            if self.rank == 0:
+                os.unlink(name)
+        view = np.frombuffer(mm, np.uint8)
+        self.ctx.host_register(view)
+        self.host_frame = (mm, view)
+        self.host_size = (width, height)
+        self.host_layout = lay
+
+    def host_planes(self, shader=None) -> dict:
+        """numpy views of the shared host frame (valid until the next size change / release)."""
+        W, H = self.host_size
+        n, lay, v = W * H, self.host_layout, self.host_frame[1]
+        out = {"depth": v[lay["depth"]:lay["depth"] + n], "normal": v[lay["normal"]:lay["normal"] + 3 * n],
+               "sdfEval": v[lay["sdf"]:lay["sdf"] + 2 * n].view(np.uint16), "iters": v[lay["iters"]:lay["iters"] + 2 * n].view(np.uint16)}
+        if shader is not None:
+            out["rgba"] = v[lay["rgba"]:lay["rgba"] + 4 * n]
+        return out
+
+    def render_frame_host(self, job: dict, shader=None):
+        """Every rank renders its stripes and downloads them itself (rm_render, band by band while the kernel runs) into
+        one shared page-locked host frame.  Returns (frame diagnostics, planes); the planes are complete on every rank
+        once the call returns (the stats all-reduce orders all ranks' downloads before anybody reads)."""
+        W, H = int(job["width"]), int(job["height"])
+        self._ensure_host_frame(W, H)
+        planes = self.host_planes(shader)
+        self.ctx.render_into(self._request(job, shader), planes)  # returns when this rank's rows are in host memory
+        st = self._reduce_frame_stats(self.ctx.stats())
+        return st, planes
+
     # ------------------------------------------------------------------ end-to-end frames (host buffers)
     def e2e_frames(self, job: dict, shader, steps: int = 3) -> dict:
         """The same frame through the reference-facing call with HOST buffers: request in, planes out.
-        world == 1: RaymarchWorker.on_message (rm_render).  world > 1: fused-gather render + rank 0 D2H."""
+        world == 1: RaymarchWorker.on_message (rm_render).  world > 1: render_frame_host (every rank downloads its own stripes into one shared host frame)."""
         W, H = int(job["width"]), int(job["height"])
         n = W * H
         d2h = n * (1 + 3 + 2 + 2 + (4 if shader else 0))
@@ -256,15 +332,11 @@ class FrameSharder:
             ms = (time.perf_counter() - t0) * 1e3 / steps
             return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h}
         import torch.distributed as dist
-        self.render_frame(job, shader)
-        if self.rank == 0:
-            self.download_frame(shader)  # warm-up allocates the page-locked planes
+        self.render_frame_host(job, shader)  # warm-up maps and page-locks the shared host frame
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            self.render_frame(job, shader)
-            if self.rank == 0:
-                self.download_frame(shader)
-            dist.barrier()
+            self.render_frame_host(job, shader)  # ends with the stats all-reduces: the frame is complete on every rank
+        dist.barrier()
         ms = (time.perf_counter() - t0) * 1e3 / steps
         return {"ms_per_frame": ms, "h2d_bytes": h2d * self.world, "d2h_bytes": d2h}

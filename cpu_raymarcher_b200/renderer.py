@@ -217,6 +217,23 @@ class Context:
         self._check(self._L.rm_render(self._h, C.byref(rq), C.byref(res)))
         return f
 
+    def render_into(self, rq: _lib.Request, planes: dict) -> None:
+        """rm_render into caller-owned host arrays (keys: depth, normal, sdfEval, iters and, with a shader, rgba).
+        With row stripes only the rows this request owns are written, so several contexts can fill one frame."""
+        res = _lib.Result()
+        res.depth, res.normal = _ptr(planes["depth"]), _ptr(planes["normal"])
+        res.sdf_eval, res.iters = _ptr(planes["sdfEval"]), _ptr(planes["iters"])
+        if rq.shader >= 0:
+            res.rgba = _ptr(planes["rgba"])
+        self._check(self._L.rm_render(self._h, C.byref(rq), C.byref(res)))
+
+    def host_register(self, arr: np.ndarray) -> None:
+        """rm_host_register: page-lock caller-owned memory so rm_render DMAs straight into planes inside it."""
+        self._check(self._L.rm_host_register(self._h, _ptr(arr), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray) -> None:
+        self._check(self._L.rm_host_unregister(self._h, _ptr(arr)))
+
     def render_device(self, rq: _lib.Request, res: _lib.Result, stream: int | None = None):
         """rm_render_device: planes are device pointers (e.g. torch tensors' data_ptr())."""
         self._check(self._L.rm_render_device(self._h, C.byref(rq), C.byref(res), stream))

@@ -245,6 +245,15 @@ int rm_probe_fp32_peak(rm_ctx* ctx, double* tflops);
 int rm_host_alloc(rm_ctx* ctx, size_t bytes, void** host_ptr);
 int rm_host_free(rm_ctx* ctx, void* host_ptr);
 
+/* Page-lock memory the CALLER owns (an existing ArrayBuffer, or a shared-memory frame that several processes map) so
+ * that rm_render treats planes inside it like rm_host_alloc memory.  With row stripes (rm_request.stripe_count > 1)
+ * rm_render writes only the rows this request owns, so one process per GPU can each call rm_render on the same
+ * shared frame: every GPU downloads its own stripes over its own PCIe link, overlapped with its render, and the
+ * frame is complete in host memory when the last call returns (the main thread's frame buffers, main.ts:324-329,
+ * filled by N workers, main.ts:452-490).  The memory must stay mapped until rm_host_unregister / rm_destroy. */
+int rm_host_register(rm_ctx* ctx, void* host_ptr, size_t bytes);
+int rm_host_unregister(rm_ctx* ctx, void* host_ptr);
+
 /* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "multi-GPU") -------------------- */
 /* Device allocation owned by the context (freed by rm_free / rm_destroy). */
 int rm_alloc(rm_ctx* ctx, size_t bytes, void** dev_ptr);

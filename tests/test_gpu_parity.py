@@ -503,6 +503,48 @@ def test_early_band_download_matches_pageable(fast_worker, monkeypatch, accel, W
         assert np.array_equal(getattr(d, k), getattr(e, k)), k
 
 
+@pytest.mark.parametrize("memory", ["pageable", "registered"])
+@pytest.mark.parametrize("W,H,world", [(64, 52, 3), (2048, 1100, 2), (1920, 1080, 8)])
+def test_striped_renders_fill_one_shared_host_frame(memory, W, H, world, monkeypatch):
+    """rm_render with row stripes writes ONLY the rows the request owns (include/rm.h), through every download path:
+    pageable staging, direct DMA into rm_host_register'ed memory, and the early band download with strided 2-D copies
+    (frames >= 16 MB).  N striped calls into one frame (what N ranks do on a shared-memory frame) == one plain call."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import multigpu
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    t, m, q = sm.get_preset(3).arrays()
+    ctx = rb.Context(0)
+    ctx.upload_scene(t, m, q, "Octree")
+    cam = Camera()
+    mk = lambda stripes: rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="phong", stripes=stripes)  # noqa: E731
+    solo = ctx.render(mk(None))
+    n = W * H
+    block = np.full(12 * n, 0xAB, np.uint8)
+    if memory == "registered":
+        ctx.host_register(block)
+    planes = {"depth": block[:n], "normal": block[n:4 * n], "sdfEval": block[4 * n:6 * n].view(np.uint16),
+              "iters": block[6 * n:8 * n].view(np.uint16), "rgba": block[8 * n:12 * n]}
+    for early in ("1", "0"):
+        monkeypatch.setenv("RM_EARLY_COPY", early)
+        block[:] = 0xAB
+        total = 0
+        for rank in range(world):
+            ctx.render_into(mk((8, world, rank)), planes)
+            total += ctx.stats()["sum_sdf"]
+            if rank == 0:  # nobody else's rows were touched
+                other = np.setdiff1d(np.arange(H), multigpu.stripe_rows_of(0, world, H, 8))
+                assert (planes["rgba"].reshape(H, -1)[other] == 0xAB).all() and (planes["sdfEval"].reshape(H, -1)[other] == 0xABAB).all()
+                own = multigpu.stripe_rows_of(0, world, H, 8)
+                assert np.array_equal(planes["normal"].reshape(H, -1)[own], solo.normal.reshape(H, -1)[own])
+        for k in ("depth", "normal", "sdfEval", "iters", "rgba"):
+            assert np.array_equal(planes[k], getattr(solo, k)), (k, early)
+        assert total == int(solo.sdfEval.astype(np.int64).sum())
+    if memory == "registered":
+        ctx.host_unregister(block)
+    ctx.close()
+
+
 def test_multi_gpu_fused_gather_matches_single_gpu():
     """N >= 2 GPUs only: torchrun, one process per GPU, CUDA-IPC fused gather + NCCL stats all-reduce."""
     import subprocess

@@ -1,5 +1,5 @@
 """Run under torchrun with N >= 2 GPUs: every rank renders its row stripes straight into rank 0's frame (CUDA-IPC
-fused gather); rank 0 compares the assembled frame and the all-reduced diagnostics with its own single-GPU render."""
+fused gather) and, a second time, into one shared page-locked host frame; rank 0 compares the assembled frames and the all-reduced diagnostics with its own single-GPU render."""
 import os
 import sys
 
@@ -19,12 +19,16 @@ ok = True
 for validate in (False, True):
     for job in (dict(width=640, height=356, scenePresetIndex=3, accelerationStructure="Octree", algorithm="adaptive-step-v3"),
                 dict(width=512, height=300, scenePresetIndex=1, accelerationStructure="BVH", algorithm="sphere-tracer", synthetic=(3000, 0x5EED0001)),
-                dict(width=333, height=97, scenePresetIndex=8, accelerationStructure="None", algorithm="fixed-step")):
+                dict(width=333, height=97, scenePresetIndex=8, accelerationStructure="None", algorithm="fixed-step"),
+                dict(width=2048, height=1100, scenePresetIndex=2, accelerationStructure="BVH", algorithm="sphere-tracer")):
         job = dict(job, time=0.0, yStart=0, yEnd=job["height"], camera=dict(pitch=0.1, yaw=0.5), overshootFactor=1.2, stepSize=0.1)
         w = rb.RaymarchWorker(device=local, validate_fp64=validate)
         sh = multigpu.FrameSharder(w, rank, world, local)
         sh.setup_scene(job)
         st = sh.render_frame(job, shader="phong")
+        # the same frame into the shared page-locked HOST frame: every rank downloads its own stripes (twice: reuse)
+        for _ in range(2):
+            st_h, host = sh.render_frame_host(job, shader="phong")
         if rank == 0:
             got = sh.download_frame("phong")
             solo = rb.RaymarchWorker(device=local, validate_fp64=validate)
@@ -32,8 +36,11 @@ for validate in (False, True):
             rs = solo.stats()
             same = all(np.array_equal(got[k], getattr(ref, k)) for k in ("depth", "normal", "sdfEval", "iters", "rgba"))
             stats_ok = all(st[k] == rs[k] for k in ("n_pixels", "sum_sdf", "sum_iters", "max_sdf", "min_sdf", "sum_sdf_full", "n_hit"))
-            print(f"world={world} validate={validate} preset={job['scenePresetIndex']} {job['accelerationStructure']}: frame {'OK' if same else 'MISMATCH'}, stats {'OK' if stats_ok else 'MISMATCH'}", flush=True)
-            ok = ok and same and stats_ok
+            same_h = all(np.array_equal(host[k], getattr(ref, k)) for k in ("depth", "normal", "sdfEval", "iters", "rgba"))
+            stats_ok = stats_ok and all(st_h[k] == rs[k] for k in ("n_pixels", "sum_sdf", "sum_iters", "max_sdf", "min_sdf", "sum_sdf_full", "n_hit"))
+            print(f"world={world} validate={validate} preset={job['scenePresetIndex']} {job['accelerationStructure']}: frame {'OK' if same else 'MISMATCH'}, "
+                  f"host frame {'OK' if same_h else 'MISMATCH'}, stats {'OK' if stats_ok else 'MISMATCH'}", flush=True)
+            ok = ok and same and same_h and stats_ok
             solo.close()
         dist.barrier()
         sh.release()

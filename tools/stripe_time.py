@@ -9,7 +9,7 @@ W, H = 3840, 2160
 job = dict(width=W, height=H, time=0.0, yStart=0, yEnd=H, camera=dict(pitch=0.0, yaw=0.0), algorithm="sphere-tracer",
            scenePresetIndex=1, accelerationStructure="BVH", overshootFactor=1.2, stepSize=0.1, synthetic=(100000, 0x5EED0001))
 sc = w._ensure_scene(1, "BVH", (100000, 0x5EED0001))
-for cnt in (1, 2, 4, 8):
+for cnt in (1, 2, 4, 8, 16, 32, 64, 135, 270):
     rq = rb.Context.make_request(W, H, sc.camera.get_rotation_matrix3(), sc.camera.get_position(), stripes=(8, cnt, 0), shader="iteration-heatmap")
     ts = []
     for _ in range(4):
