@@ -13,7 +13,7 @@ copied into the full-frame buffers on the main thread and the diagnostics summed
     every other rank maps them through CUDA IPC and its render kernel stores its pixels straight into
     rank 0's HBM over NVLink — no staging buffer, no separate gather collective;
   * diagnostics "reduce" (main.ts:527-543): each kernel's epilogue leaves 12 words per GPU; one NCCL
-    all-reduce per operator (sum / max / min) combines them;
+    all-reduce per operator combines them (sum; max, with the minima negated into the same call);
   * frames wanted in HOST memory (the main thread's frame buffers, main.ts:324-329): `render_frame_host`.
     The frame lives in one shared-memory block that every rank maps and page-locks (rm_host_register);
     each rank calls rm_render with its stripes and the shared planes, so every GPU downloads its own rows
@@ -221,7 +221,7 @@ class FrameSharder:
         return self._reduce_frame_stats(self.ctx.stats())
 
     def _reduce_frame_stats(self, st: dict) -> dict:
-        """Frame-level diagnostics (main.ts:527-543) from this rank's share: three NCCL all-reduces."""
+        """Frame-level diagnostics (main.ts:527-543) from this rank's share: two NCCL all-reduces (sum, max)."""
         st["n_prims"] = self.ctx.n_prims
         if self.world == 1:
             st["frame_ms"] = st["kernel_ms"]
@@ -229,22 +229,21 @@ class FrameSharder:
             return st
         import torch
         import torch.distributed as dist
-        dev = torch.device("cuda", self.local_rank)
+        dev = torch.device("cpu") if dist.get_backend() == "gloo" else torch.device("cuda", self.local_rank)  # gloo: CPU tests
+        # two all-reduces on packed int64 words: SUM (counters; FLOP totals are integer-valued) and MAX (minima negated)
         sums = torch.tensor([st["n_pixels"], st["sum_sdf"], st["sum_iters"], st["sum_sdf_full"], st["sum_iters_full"], st["n_hit"],
-                             st["n_launches"]] + list(st["evals_by_type"]), dtype=torch.int64, device=dev)
-        fsum = torch.tensor([st["algorithmic_flops"], st["executed_flops"], float(st["tc_passes"]), float(st["tc_requests"]),
-                             float(st["tc_items"])], dtype=torch.float64, device=dev)
-        maxs = torch.tensor([st["max_sdf"], st["max_iters"], int(st["kernel_ms"] * 1e6)], dtype=torch.int64, device=dev)
-        mins = torch.tensor([st["min_sdf"], st["min_iters"]], dtype=torch.int64, device=dev)
+                             st["n_launches"]] + list(st["evals_by_type"]) +
+                            [round(st["algorithmic_flops"]), round(st["executed_flops"]), st["tc_passes"], st["tc_requests"], st["tc_items"]],
+                            dtype=torch.int64, device=dev)
+        maxs = torch.tensor([st["max_sdf"], st["max_iters"], int(st["kernel_ms"] * 1e6), -st["min_sdf"], -st["min_iters"]],
+                            dtype=torch.int64, device=dev)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
-        dist.all_reduce(mins, op=dist.ReduceOp.MIN)  # also orders every rank's peer stores before rank 0 reads the frame
-        s, mx, mn = sums.tolist(), maxs.tolist(), mins.tolist()
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)  # also orders every rank's stores / downloads before anybody reads the frame
+        both = torch.cat([sums, maxs]).tolist()  # one read-back
+        s, mx = both[:15], both[15:]
         st.update(n_pixels=s[0], sum_sdf=s[1], sum_iters=s[2], sum_sdf_full=s[3], sum_iters_full=s[4], n_hit=s[5], n_launches=s[6],
-                  evals_by_type=s[7:10], algorithmic_flops=float(fsum[0].item()), executed_flops=float(fsum[1].item()),
-                  tc_passes=int(fsum[2].item()), tc_requests=int(fsum[3].item()), tc_items=int(fsum[4].item()), max_sdf=mx[0], max_iters=mx[1], min_sdf=mn[0],
-                  min_iters=mn[1])
+                  evals_by_type=s[7:10], algorithmic_flops=float(s[10]), executed_flops=float(s[11]),
+                  tc_passes=s[12], tc_requests=s[13], tc_items=s[14], max_sdf=mx[0], max_iters=mx[1], min_sdf=-mx[3], min_iters=-mx[4])
         st["kernel_ms_max"] = mx[2] / 1e6
         st["frame_ms"] = st["kernel_ms_max"]  # the gather is fused into the kernel: the slowest rank's kernel is the frame
         return st

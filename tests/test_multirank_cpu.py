@@ -37,8 +37,17 @@ def _worker(rank, world, port, q):
                  evals_by_type=[int(f.sdf_full.sum()), 0, 0], kernel_ms=1.0 + rank)
     gathered = [None] * world
     dist.all_gather_object(gathered, local)
+    # the product's own reduction (two packed all-reduces) must agree with the literal per-field merge
+    import types
+    sharder = multigpu.FrameSharder(types.SimpleNamespace(ctx=types.SimpleNamespace(n_prims=125)), rank, world, rank)
+    red = sharder._reduce_frame_stats(dict(local))
+    want = multigpu.reduce_stats(gathered)
+    for k in ("n_pixels", "sum_sdf", "sum_iters", "sum_sdf_full", "sum_iters_full", "n_hit", "n_launches", "max_sdf", "min_sdf",
+              "max_iters", "min_iters", "evals_by_type", "tc_passes"):
+        assert red[k] == want[k], (k, red[k], want[k])
+    assert red["kernel_ms_max"] == want["kernel_ms"] and red["frame_ms"] == want["kernel_ms"]
     if rank == 0:
-        q.put(({k: v.numpy() for k, v in frame.items()}, multigpu.reduce_stats(gathered)))
+        q.put(({k: v.numpy() for k, v in frame.items()}, want))
     dist.barrier()
     dist.destroy_process_group()
 
