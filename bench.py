@@ -330,7 +330,7 @@ def main():
         e2e = sharder.e2e_frames(job, wl["shader"], steps=max(1, min(args.steps, 3)))
         out["e2e"] = {"value": W * H / (e2e["ms_per_frame"] * 1e-3) / 1e6, "unit": "Mrays/s",
                       "h2d_bytes_per_step": e2e["h2d_bytes"], "d2h_bytes_per_step": e2e["d2h_bytes"],
-                      "ms_per_step": e2e["ms_per_frame"]}
+                      "ms_per_step": e2e["ms_per_frame"], "path": e2e["path"]}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle on a bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

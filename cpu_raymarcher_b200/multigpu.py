@@ -75,6 +75,10 @@ def reduce_stats(stats_list):
     return out
 
 
+class HostFrameUnavailable(RuntimeError):
+    """The shared host frame could not be created (raised on every rank alike)."""
+
+
 class FrameSharder:
     def __init__(self, worker, rank: int = 0, world: int = 1, local_rank: int = 0):
         self.worker = worker
@@ -275,12 +279,20 @@ class FrameSharder:
             mm = mmap.mmap(-1, lay["total"])
         else:
             import torch.distributed as dist
-            box = [f"/dev/shm/rm_b200_frame_{os.getpid()}_{width}x{height}" if self.rank == 0 else None]
+            box = [None]
             if self.rank == 0:
-                fd = os.open(box[0], os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
-                os.ftruncate(fd, lay["total"])
+                try:  # a container's /dev/shm can be tiny: refuse up front rather than SIGBUS on first touch
+                    vfs = os.statvfs("/dev/shm")
+                    if vfs.f_bavail * vfs.f_frsize >= lay["total"] + (16 << 20):
+                        box[0] = f"/dev/shm/rm_b200_frame_{os.getpid()}_{width}x{height}"
+                        fd = os.open(box[0], os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+                        os.ftruncate(fd, lay["total"])
+                except OSError:
+                    box[0] = None
             dist.broadcast_object_list(box, src=0)
             name = box[0]
+            if name is None:
+                raise HostFrameUnavailable(f"/dev/shm cannot hold a {lay['total'] >> 20} MiB frame")
             if self.rank != 0:
                 fd = os.open(name, os.O_RDWR)
             mm = mmap.mmap(fd, lay["total"])
@@ -329,13 +341,29 @@ class FrameSharder:
             for _ in range(steps):
                 self.worker.on_message(job, shader=shader, pinned=True)
             ms = (time.perf_counter() - t0) * 1e3 / steps
-            return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h}
+            return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h,
+                    "path": "RaymarchWorker.on_message -> rm_render into page-locked planes (row bands downloaded during the render)"}
         import torch.distributed as dist
-        self.render_frame_host(job, shader)  # warm-up maps and page-locks the shared host frame
+        try:
+            self.render_frame_host(job, shader)  # warm-up maps and page-locks the shared host frame
+
+            def frame():
+                self.render_frame_host(job, shader)  # ends with the stats all-reduces: the frame is complete on every rank
+            path = "shared page-locked host frame, every rank downloads its own stripes during its render"
+        except HostFrameUnavailable:
+            self.render_frame(job, shader)
+            if self.rank == 0:
+                self.download_frame(shader)  # warm-up allocates the page-locked planes
+
+            def frame():
+                self.render_frame(job, shader)
+                if self.rank == 0:
+                    self.download_frame(shader)
+            path = "fused peer-store gather into rank 0's HBM, then rank 0 downloads the frame"
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            self.render_frame_host(job, shader)  # ends with the stats all-reduces: the frame is complete on every rank
+            frame()
         dist.barrier()
         ms = (time.perf_counter() - t0) * 1e3 / steps
-        return {"ms_per_frame": ms, "h2d_bytes": h2d * self.world, "d2h_bytes": d2h}
+        return {"ms_per_frame": ms, "h2d_bytes": h2d * self.world, "d2h_bytes": d2h, "path": path}
