@@ -38,6 +38,8 @@ napi_status napi_create_double(napi_env, double, napi_value* result);
 napi_status napi_create_int32(napi_env, int32_t, napi_value* result);
 napi_status napi_create_string_utf8(napi_env, const char*, size_t, napi_value* result);
 napi_status napi_create_arraybuffer(napi_env, size_t byte_length, void** data, napi_value* result);
+typedef void (*napi_finalize)(napi_env env, void* finalize_data, void* finalize_hint);
+napi_status napi_create_external_arraybuffer(napi_env, void* external_data, size_t byte_length, napi_finalize finalize_cb, void* finalize_hint, napi_value* result);
 napi_status napi_create_typedarray(napi_env, napi_typedarray_type, size_t length, napi_value arraybuffer, size_t byte_offset, napi_value* result);
 napi_status napi_get_typedarray_info(napi_env, napi_value, napi_typedarray_type*, size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_create_promise(napi_env, napi_deferred*, napi_value* promise);

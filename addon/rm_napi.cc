@@ -6,12 +6,18 @@
 //       -> rm_upload_scene          (replaces `new Scene(accel); scene.loadPreset(i)`, raymarchWorker.ts:37-38)
 //   addon.render(job, camera{rot3: Float32Array(9), origin: Float32Array(3)}) : Promise<Result>
 //       -> rm_render on a libuv worker thread (the JS event loop never blocks on CUDA); Result carries the
-//          four typed arrays of raymarchWorker.ts:24-31 backed by fresh ArrayBuffers (ownership moves to JS,
-//          like the reference's transfer list :86-91)
+//          four typed arrays of raymarchWorker.ts:24-31 (ownership moves to JS, like the reference's transfer
+//          list :86-91).  They are views of ONE external ArrayBuffer over page-locked memory (rm_host_alloc), so
+//          rm_render DMAs straight into them and, for big bands, downloads finished rows while the kernel still
+//          runs; blocks return to a pool when JS garbage-collects the buffer.  Where the runtime forbids external
+//          buffers (V8 sandbox / recent Electron) the arrays fall back to plain ArrayBuffers (staged copy).
 //   addon.stats() -> rm_stats       (diagnostics of main.ts:527-548 for the last band)
 // The `Worker` shim that makes main.ts use this unchanged is ts/gpuWorkerShim.ts.
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #ifdef RM_HAVE_NODE_API_H
 #include <node_api.h>
@@ -97,6 +103,35 @@ napi_value UploadScene(napi_env env, napi_callback_info info) {
     return nullptr;
 }
 
+// Page-locked result blocks, recycled: cudaMallocHost costs milliseconds, a frame is rendered every few.
+std::mutex g_pool_mu;
+std::vector<std::pair<void*, size_t>> g_pool;
+void* pool_take(size_t bytes, size_t* cap) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].second >= bytes && g_pool[i].second <= 2 * bytes + 4096) {
+                void* p = g_pool[i].first;
+                *cap = g_pool[i].second;
+                g_pool.erase(g_pool.begin() + (long)i);
+                return p;
+            }
+    }
+    void* p = nullptr;
+    *cap = bytes;
+    return (g_ctx && rm_host_alloc(g_ctx, bytes, &p) == RM_OK) ? p : nullptr;
+}
+struct PoolBlock {
+    void* p;
+    size_t cap;
+};
+void pool_give(napi_env, void*, void* hint) {  // napi_finalize of the external ArrayBuffer (JS thread)
+    PoolBlock* b = (PoolBlock*)hint;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.emplace_back(b->p, b->cap);
+    delete b;
+}
+
 struct RenderWork {
     rm_request rq;
     rm_result out;
@@ -161,20 +196,36 @@ napi_value Render(napi_env env, napi_callback_info info) {
     std::memcpy(w->rq.origin, org, sizeof(w->rq.origin));
     const int th = w->rq.y_end > w->rq.y_start ? w->rq.y_end - w->rq.y_start : 0;
     w->npx = (size_t)w->rq.width * th;
-    // Result arrays (raymarchWorker.ts:42-46) allocated as JS ArrayBuffers; rm_render writes straight into them
+    // Result arrays (raymarchWorker.ts:42-46): four views of one ArrayBuffer, sections 256-byte aligned.  Preferred backing:
+    // a page-locked block (direct DMA + early band download); otherwise a plain ArrayBuffer (rm_render stages the copy).
     napi_value ab, ta, res, v;
     napi_create_object(env, &res);
-    napi_create_arraybuffer(env, w->npx, &w->depth, &ab);
-    napi_create_typedarray(env, napi_uint8_clamped_array, w->npx, ab, 0, &ta);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t oDepth = 0, oNormal = al(w->npx), oSdf = oNormal + al(3 * w->npx), oIters = oSdf + al(2 * w->npx);
+    const size_t total = oIters + al(2 * w->npx);
+    size_t cap = 0;
+    void* base = pool_take(total, &cap);
+    bool external = false;
+    if (base) {
+        PoolBlock* blk = new PoolBlock{base, cap};
+        external = napi_create_external_arraybuffer(env, base, total, pool_give, blk, &ab) == napi_ok;
+        if (!external) {  // napi_no_external_buffers_allowed: keep the block for later, use JS memory
+            pool_give(env, nullptr, blk);
+            base = nullptr;
+        }
+    }
+    if (!external) napi_create_arraybuffer(env, total, &base, &ab);
+    w->depth = (char*)base + oDepth;
+    w->normal = (char*)base + oNormal;
+    w->sdf = (char*)base + oSdf;
+    w->iters = (char*)base + oIters;
+    napi_create_typedarray(env, napi_uint8_clamped_array, w->npx, ab, oDepth, &ta);
     napi_set_named_property(env, res, "depth", ta);
-    napi_create_arraybuffer(env, 3 * w->npx, &w->normal, &ab);
-    napi_create_typedarray(env, napi_uint8_clamped_array, 3 * w->npx, ab, 0, &ta);
+    napi_create_typedarray(env, napi_uint8_clamped_array, 3 * w->npx, ab, oNormal, &ta);
     napi_set_named_property(env, res, "normal", ta);
-    napi_create_arraybuffer(env, 2 * w->npx, &w->sdf, &ab);
-    napi_create_typedarray(env, napi_uint16_array, w->npx, ab, 0, &ta);
+    napi_create_typedarray(env, napi_uint16_array, w->npx, ab, oSdf, &ta);
     napi_set_named_property(env, res, "sdfEval", ta);
-    napi_create_arraybuffer(env, 2 * w->npx, &w->iters, &ab);
-    napi_create_typedarray(env, napi_uint16_array, w->npx, ab, 0, &ta);
+    napi_create_typedarray(env, napi_uint16_array, w->npx, ab, oIters, &ta);
     napi_set_named_property(env, res, "iters", ta);
     napi_create_int32(env, w->rq.y_start, &v);
     napi_set_named_property(env, res, "yStart", v);
