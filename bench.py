@@ -307,7 +307,9 @@ def main():
                      "flops_per_eval": "reference-equivalent: every SDF call the reference counts x translation-only sphere 7 (screened "
                                        "search, >= 512 spheres) / 11 | general sphere 26 / box 38 / torus 29",
                      "executed_tflops": xflops / (kern_ms * 1e-3) / 1e12 / world,
-                     "note": ("achieved = reference-equivalent SDF work / kernel time. With translation-only spheres behind a BVH "
+                     "frac_executed": (xflops / (kern_ms * 1e-3) / 1e12 / world) / peak_tflops if peak_tflops else None,
+                     "note": ("achieved / frac = the north star's figure: SDF evals/s as the reference counts them x FLOPs per evaluation / FP32 peak "
+                              "(reference-equivalent work); frac_executed = FLOPs this kernel really issued / peak. With translation-only spheres behind a BVH "
                               "the all-primitives fallback is answered exactly by a tensor-core cluster screen, so far fewer "
                               "FLOPs are executed than the reference's brute force implies (executed_tflops); the kernel is then "
                               "bound by the divergent ray/BVH control path, not by the FP32 pipe") if last.get("tc_passes") else None,
