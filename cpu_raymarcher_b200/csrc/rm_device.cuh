@@ -1821,7 +1821,11 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                     // halve the shared-memory wavefronts per evaluation)
                     constexpr int NQ = (int)(kBatch / 32u);
                     float rq[NQ][3];
+#ifdef RM_EXP_TC_ONLY  // experiment (profiles/prof_cfg4_100k_r01j_stalls.txt): the tensor-core kernel without its FFMA fallback body
+                    if (!tcDone && !kTC) {
+#else
                     if (!tcDone) {
+#endif
 #pragma unroll
                     for (int k = 0; k < NQ; ++k) {
                         rq[k][0] = rq[k][1] = rq[k][2] = 0.f;
