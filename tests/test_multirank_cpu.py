@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the N>1 host logic (stripe partition, frame merge, stats reduce) with a CPU band
+"""world_size-2 gloo test of the N>1 host logic (stripe partition, frame merge, shared host frame, stats reduce) with a CPU band
 renderer injected in place of the GPU kernel.  The renderer here is the oracle — legitimate inside tests/ —
 so the merged 2-rank frame must equal the 1-rank oracle frame bit for bit."""
 import os
@@ -46,6 +46,41 @@ def _worker(rank, world, port, q):
               "max_iters", "min_iters", "evals_by_type", "tc_passes"):
         assert red[k] == want[k], (k, red[k], want[k])
     assert red["kernel_ms_max"] == want["kernel_ms"] and red["frame_ms"] == want["kernel_ms"]
+    # render_frame_host: one shared-memory frame mapped by both ranks (created by rank 0, name broadcast, unlinked once
+    # mapped), each rank's renderer writes ONLY its stripes into it; the stats all-reduce orders the writes.  The GPU
+    # context is replaced by a stub whose render_into is the oracle, so this is the product's host logic end to end.
+    from cpu_raymarcher_b200.scene import Scene
+
+    class StubCtx:
+        n_prims = 125
+
+        def host_register(self, arr):
+            self.registered = (arr.ctypes.data, arr.nbytes)
+
+        def host_unregister(self, arr):
+            assert self.registered[0] == arr.ctypes.data
+
+        def render_into(self, rq, planes):
+            assert (rq.stripe_rows, rq.stripe_count, rq.stripe_index) == (multigpu.STRIPE_ROWS, world, rank)
+            lo, hi = planes["depth"].ctypes.data, planes["rgba"].ctypes.data + planes["rgba"].nbytes if "rgba" in planes else 0
+            assert self.registered[0] <= lo and (hi == 0 or hi <= self.registered[0] + self.registered[1])
+            for k, c in (("depth", 1), ("normal", 3), ("sdfEval", 1), ("iters", 1)):
+                planes[k].reshape(H, W * c)[rows] = getattr(f, k).reshape(len(rows), W * c)
+
+        def stats(self):
+            return dict(local)
+
+    stub_worker = types.SimpleNamespace(ctx=StubCtx(), scene=Scene("Octree"))
+    host_sharder = multigpu.FrameSharder(stub_worker, rank, world, rank)
+    job = dict(width=W, height=H, camera=dict(pitch=0.1, yaw=0.4), algorithm="sphere-tracer")
+    for _ in range(2):  # the second frame reuses the mapping
+        st_h, planes = host_sharder.render_frame_host(job)
+    assert st_h["sum_sdf"] == want["sum_sdf"] and st_h["n_pixels"] == W * H
+    host = {k: np.array(v, dtype=np.int32) for k, v in planes.items()}  # every rank sees the complete frame
+    for k in ("depth", "normal", "sdfEval", "iters"):
+        assert np.array_equal(host[k], frame[k].numpy()), k
+    del planes
+    host_sharder.release()
     if rank == 0:
         q.put(({k: v.numpy() for k, v in frame.items()}, want))
     dist.barrier()
