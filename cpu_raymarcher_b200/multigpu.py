@@ -99,12 +99,13 @@ class FrameSharder:
             return
         import torch
         import torch.distributed as dist
-        from .renderer import build_bvh, build_octree
+        from .renderer import OP_NODE_DTYPE, build_bvh_scene, build_octree_scene
         from .scene import Scene
 
         accel = job.get("accelerationStructure", "None")
         accel = accel if accel in ("Octree", "BVH") else "None"
-        dev = torch.device("cuda", self.local_rank)
+        dev = torch.device("cpu") if dist.get_backend() == "gloo" else torch.device("cuda", self.local_rank)  # gloo: CPU tests
+        # blob sections: types | world->local | params | operator-tree nodes | object roots | accel nodes | leaf lists
         if self.rank == 0:
             sc = Scene(accel)
             if job.get("synthetic"):
@@ -112,40 +113,54 @@ class FrameSharder:
             else:
                 sc.load_preset(int(job.get("scenePresetIndex", 0)))
             t, m, q = sc.primitives.arrays()
-            parts = [t.tobytes(), m.tobytes(), q.tobytes()]
+            ops, roots = sc.primitives.op_nodes, sc.primitives.object_root
+            has_tree = roots is not None and len(roots) > 0
+            ops_b = np.ascontiguousarray(ops, OP_NODE_DTYPE).tobytes() if has_tree else b""
+            roots_b = np.ascontiguousarray(roots, np.int32).tobytes() if has_tree else b""
+            parts = [t.tobytes(), m.tobytes(), q.tobytes(), ops_b, roots_b, b"", b""]
             n_nodes = 0
             if accel != "None":
-                nodes, n_nodes, leaf = (build_bvh if accel == "BVH" else build_octree)(t, m, q, self.ctx.flags)
+                # the structure indexes scene OBJECTS (operator trees included): the *_scene builders
+                build = build_bvh_scene if accel == "BVH" else build_octree_scene
+                nodes, n_nodes, leaf = build(t, m, q, ops if has_tree else None, roots if has_tree else None, self.ctx.flags)
                 node_size = C.sizeof(_lib.BvhNode if accel == "BVH" else _lib.OctreeNode)
-                parts += [bytes(C.string_at(C.addressof(nodes), n_nodes * node_size)), leaf.tobytes()]
-            hdr = np.array([len(t), n_nodes] + [len(p) for p in parts] + [0] * (6 - len(parts)), np.int64)
+                parts[5] = bytes(C.string_at(C.addressof(nodes), n_nodes * node_size))
+                parts[6] = np.ascontiguousarray(leaf, np.int32).tobytes()
+            hdr = np.array([len(t), n_nodes] + [len(p) for p in parts], np.int64)
             blob = np.frombuffer(b"".join(parts), np.uint8)
         else:
-            hdr = np.zeros(8, np.int64)
+            hdr = np.zeros(9, np.int64)
             blob = None
         hdr_t = torch.from_numpy(hdr.copy()).to(dev)
         dist.broadcast(hdr_t, src=0)
         hdr = hdr_t.cpu().numpy()
         total = int(hdr[2:].sum())
         blob_t = torch.from_numpy(blob.copy()).to(dev) if self.rank == 0 else torch.empty(total, dtype=torch.uint8, device=dev)
-        dist.broadcast(blob_t, src=0)  # NCCL over NVLink: primitives + flattened acceleration structure
+        dist.broadcast(blob_t, src=0)  # NCCL over NVLink: primitives + operator trees + flattened acceleration structure
         raw = blob_t.cpu().numpy().tobytes()
+        self._upload_blob(raw, hdr, accel)
+        self.worker.scene = Scene(accel)
+        self.worker._scene_key = (int(job.get("scenePresetIndex", 0)), job.get("synthetic"), accel)
+
+    def _upload_blob(self, raw: bytes, hdr, accel: str):
+        """Every rank: unpack the broadcast scene blob and make it resident (rm_upload_scene)."""
+        from .renderer import OP_NODE_DTYPE
         n, n_nodes = int(hdr[0]), int(hdr[1])
-        sizes = [int(x) for x in hdr[2:] if x > 0]
-        offs = np.cumsum([0] + sizes)
-        t = np.frombuffer(raw[offs[0]:offs[1]], np.uint8)
-        m = np.frombuffer(raw[offs[1]:offs[2]], np.float32).reshape(n, 16)
-        q = np.frombuffer(raw[offs[2]:offs[3]], np.float64).reshape(n, 4)
+        offs = np.cumsum([0] + [int(x) for x in hdr[2:9]])
+        sec = lambda i: raw[offs[i]:offs[i + 1]]  # noqa: E731
+        t = np.frombuffer(sec(0), np.uint8)
+        m = np.frombuffer(sec(1), np.float32).reshape(n, 16)
+        q = np.frombuffer(sec(2), np.float64).reshape(n, 4)
+        ops = np.frombuffer(sec(3), OP_NODE_DTYPE) if len(sec(3)) else None
+        roots = np.frombuffer(sec(4), np.int32) if len(sec(4)) else None
+        kw = dict(op_nodes=ops, object_root=roots)
         if accel != "None":
             node_t = _lib.BvhNode if accel == "BVH" else _lib.OctreeNode
-            nodes = (node_t * n_nodes).from_buffer_copy(raw[offs[3]:offs[4]])
-            leaf = np.frombuffer(raw[offs[4]:offs[5]], np.int32)
-            self.ctx.upload_scene(t, m, q, accel, nodes=nodes, n_nodes=n_nodes, leaf=leaf)
+            nodes = (node_t * max(n_nodes, 1)).from_buffer_copy(sec(5).ljust(C.sizeof(node_t), b"\0"))
+            leaf = np.frombuffer(sec(6), np.int32)
+            self.ctx.upload_scene(t, m, q, accel, nodes=nodes, n_nodes=n_nodes, leaf=leaf, **kw)
         else:
-            self.ctx.upload_scene(t, m, q, accel)
-        sc = Scene(accel)
-        self.worker.scene = sc
-        self.worker._scene_key = (int(job.get("scenePresetIndex", 0)), job.get("synthetic"), accel)
+            self.ctx.upload_scene(t, m, q, accel, **kw)
 
     # ------------------------------------------------------------------ frame planes
     def _ensure_frame(self, width: int, height: int):
@@ -211,7 +226,8 @@ class FrameSharder:
         W, H = int(job["width"]), int(job["height"])
         return Context.make_request(W, H, scene.camera.get_rotation_matrix3(), scene.camera.get_position(),
                                     algorithm=job.get("algorithm", "sphere-tracer"), y_start=0, y_end=H,
-                                    step_size=float(job.get("stepSize") or 0.1), overshoot=float(job.get("overshootFactor") or 1.2),
+                                    step_size=float(job["stepSize"]) if job.get("stepSize") is not None else 0.1,  # only `undefined` defaults (raymarchWorker.ts)
+                                    overshoot=float(job["overshootFactor"]) if job.get("overshootFactor") is not None else 1.2,
                                     shader=shader, time=float(job.get("time", 0.0)),
                                     stripes=(STRIPE_ROWS, self.world, self.rank) if self.world > 1 else None)
 
@@ -221,8 +237,18 @@ class FrameSharder:
         W, H = int(job["width"]), int(job["height"])
         self._ensure_frame(W, H)
         rq = self._request(job, shader)
+        self._frame_fence()
         self.ctx.render_device(rq, self._result(shader))  # synchronises this rank's stream
         return self._reduce_frame_stats(self.ctx.stats())
+
+    def _frame_fence(self):
+        """Frame k+1 must not be stored into the shared planes (rank 0's HBM, or the shared host frame) while the
+        consumer still reads frame k: every rank waits here until ALL ranks — rank 0, the consumer, included — have
+        come back for the next frame.  The planes a render_frame* call returns are therefore valid until the same
+        rank calls render_frame* again."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
 
     def _reduce_frame_stats(self, st: dict) -> dict:
         """Frame-level diagnostics (main.ts:527-543) from this rank's share: two NCCL all-reduces (sum, max)."""
@@ -284,9 +310,14 @@ class FrameSharder:
                 try:  # a container's /dev/shm can be tiny: refuse up front rather than SIGBUS on first touch
                     vfs = os.statvfs("/dev/shm")
                     if vfs.f_bavail * vfs.f_frsize >= lay["total"] + (16 << 20):
-                        box[0] = f"/dev/shm/rm_b200_frame_{os.getpid()}_{width}x{height}"
-                        fd = os.open(box[0], os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
-                        os.ftruncate(fd, lay["total"])
+                        box[0] = f"/dev/shm/rm_b200_frame_{os.getpid()}_{os.urandom(8).hex()}_{width}x{height}"
+                        fd = os.open(box[0], os.O_CREAT | os.O_EXCL | os.O_NOFOLLOW | os.O_RDWR, 0o600)  # never an existing file / link
+                        try:
+                            os.ftruncate(fd, lay["total"])
+                        except OSError:
+                            os.close(fd)
+                            os.unlink(box[0])
+                            raise
                 except OSError:
                     box[0] = None
             dist.broadcast_object_list(box, src=0)
@@ -323,6 +354,7 @@ class FrameSharder:
         W, H = int(job["width"]), int(job["height"])
         self._ensure_host_frame(W, H)
         planes = self.host_planes(shader)
+        self._frame_fence()
         self.ctx.render_into(self._request(job, shader), planes)  # returns when this rank's rows are in host memory
         st = self._reduce_frame_stats(self.ctx.stats())
         return st, planes

@@ -81,6 +81,37 @@ def _worker(rank, world, port, q):
         assert np.array_equal(host[k], frame[k].numpy()), k
     del planes
     host_sharder.release()
+    # setup_scene at world 2: the broadcast blob must carry the operator trees (they were dropped, so operator
+    # presets rendered as a plain union on N > 1 GPUs) and the acceleration structure built over scene OBJECTS.
+    from cpu_raymarcher_b200.renderer import OP_NODE_DTYPE, build_bvh_scene, build_octree_scene
+
+    class CaptureCtx:
+        flags = 0
+
+        def upload_scene(self, t, m, q_, accel, nodes=None, n_nodes=0, leaf=None, op_nodes=None, object_root=None):
+            self.got = dict(t=np.array(t), m=np.array(m), q=np.array(q_), accel=accel, n_nodes=n_nodes,
+                            nodes=bytes(nodes)[: n_nodes * (40 if accel == "BVH" else 48)] if nodes is not None else b"",
+                            leaf=None if leaf is None else np.array(leaf), ops=None if op_nodes is None else np.array(op_nodes),
+                            roots=None if object_root is None else np.array(object_root))
+
+    for preset, accel in ((11, "BVH"), (16, "Octree"), (17, "None"), (2, "BVH")):
+        cw = types.SimpleNamespace(ctx=CaptureCtx(), scene=None, _scene_key=None)
+        multigpu.FrameSharder(cw, rank, world, rank).setup_scene(dict(scenePresetIndex=preset, accelerationStructure=accel))
+        got = cw.ctx.got
+        sc = Scene(accel)
+        sc.load_preset(preset)
+        t, m, q_ = sc.primitives.arrays()
+        assert np.array_equal(got["t"], t) and np.array_equal(got["m"].reshape(-1), m.reshape(-1)) and np.array_equal(got["q"].reshape(-1), q_.reshape(-1))
+        ops, roots = sc.primitives.op_nodes, sc.primitives.object_root
+        if roots is not None and len(roots):
+            assert got["ops"].tobytes() == np.ascontiguousarray(ops, OP_NODE_DTYPE).tobytes() and np.array_equal(got["roots"], roots), preset
+        else:
+            assert got["ops"] is None and got["roots"] is None
+        if accel != "None":
+            build = build_bvh_scene if accel == "BVH" else build_octree_scene
+            nodes, nn, leaf = build(t, m, q_, ops, roots, 0)
+            assert got["n_nodes"] == nn and got["nodes"] == bytes(nodes)[: len(got["nodes"])] and np.array_equal(got["leaf"], leaf), (preset, accel)
+        assert cw._scene_key == (preset, None, accel)
     if rank == 0:
         q.put(({k: v.numpy() for k, v in frame.items()}, want))
     dist.barrier()

@@ -20,8 +20,13 @@ for validate in (False, True):
     for job in (dict(width=640, height=356, scenePresetIndex=3, accelerationStructure="Octree", algorithm="adaptive-step-v3"),
                 dict(width=512, height=300, scenePresetIndex=1, accelerationStructure="BVH", algorithm="sphere-tracer", synthetic=(3000, 0x5EED0001)),
                 dict(width=333, height=97, scenePresetIndex=8, accelerationStructure="None", algorithm="fixed-step"),
-                dict(width=2048, height=1100, scenePresetIndex=2, accelerationStructure="BVH", algorithm="sphere-tracer")):
-        job = dict(job, time=0.0, yStart=0, yEnd=job["height"], camera=dict(pitch=0.1, yaw=0.5), overshootFactor=1.2, stepSize=0.1)
+                dict(width=2048, height=1100, scenePresetIndex=2, accelerationStructure="BVH", algorithm="sphere-tracer"),
+                # operator trees travel in the scene broadcast too (presets 11 SmoothSubtraction, 12 SmoothUnion [animated], 16 Screw)
+                dict(width=320, height=184, scenePresetIndex=11, accelerationStructure="BVH", algorithm="sphere-tracer", time=1234.5),
+                dict(width=320, height=184, scenePresetIndex=12, accelerationStructure="Octree", algorithm="adaptive-step-v2", time=777.0),
+                dict(width=320, height=184, scenePresetIndex=16, accelerationStructure="None", algorithm="sphere-tracer")):
+        job = dict(dict(time=0.0), **job)
+        job = dict(job, yStart=0, yEnd=job["height"], camera=dict(pitch=0.1, yaw=0.5), overshootFactor=1.2, stepSize=0.1)
         w = rb.RaymarchWorker(device=local, validate_fp64=validate)
         sh = multigpu.FrameSharder(w, rank, world, local)
         sh.setup_scene(job)
