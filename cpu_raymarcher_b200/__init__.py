@@ -5,4 +5,5 @@ from ._lib import ACCELS, ALGORITHMS, LIB_PATH, SHADERS, RmError  # noqa: F401
 from .camera import Camera  # noqa: F401
 from .renderer import Context, Frame, build_bvh, build_bvh_scene, build_octree, build_octree_scene  # noqa: F401
 from .scene import Scene  # noqa: F401
+from .pool import RaymarchPool  # noqa: F401
 from .worker import RaymarchWorker  # noqa: F401

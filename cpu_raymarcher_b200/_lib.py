@@ -7,6 +7,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librm_b200.so")
+if os.environ.get("RM_B200_LIB"):  # A/B experiments (tools/ab_bench.py): another build of the SAME library, e.g. build/exp/librm_b200_<variant>.so
+    LIB_PATH = os.path.abspath(os.environ["RM_B200_LIB"])
 
 RM_OK = 0
 RM_ERR_ARG, RM_ERR_UNSUPPORTED_PRIMITIVE, RM_ERR_CUDA, RM_ERR_STATE, RM_ERR_NOMEM = -1, -2, -3, -4, -5
@@ -73,13 +75,17 @@ class Stats(C.Structure):
                 ("sum_sdf_full", C.c_uint64), ("sum_iters_full", C.c_uint64), ("evals_by_type", C.c_uint64 * 3),
                 ("n_hit", C.c_uint64), ("operator_flops", C.c_double), ("algorithmic_flops", C.c_double), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
                 ("device", C.c_int32), ("tc_passes", C.c_uint64), ("tc_requests", C.c_uint64), ("tc_items", C.c_uint64),
-                ("executed_flops", C.c_double)]
+                ("executed_flops", C.c_double), ("fp32_pipe_flops", C.c_double), ("tensor_flops", C.c_double),
+                ("n_devices", C.c_int32), ("pad_", C.c_int32)]
 
 
 # every symbol include/rm.h declares
 EXPORTS = ["rm_abi_version", "rm_device_count", "rm_create", "rm_destroy", "rm_last_error", "rm_upload_scene",
            "rm_build_bvh", "rm_build_octree", "rm_build_bvh_scene", "rm_build_octree_scene", "rm_render", "rm_render_device", "rm_stats", "rm_shade", "rm_alloc",
-           "rm_free", "rm_host_alloc", "rm_host_free", "rm_host_register", "rm_host_unregister", "rm_probe_fp32_peak", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d"]
+           "rm_free", "rm_host_alloc", "rm_host_free", "rm_host_register", "rm_host_unregister", "rm_probe_fp32_peak", "rm_ipc_export", "rm_ipc_open", "rm_ipc_close", "rm_memcpy_d2h", "rm_memcpy_h2d",
+           "rm_pool_create", "rm_pool_destroy", "rm_pool_last_error", "rm_pool_device_count", "rm_pool_upload_scene", "rm_pool_render",
+           "rm_pool_render_device", "rm_pool_render_frames", "rm_pool_stats", "rm_pool_device_stats", "rm_pool_host_alloc", "rm_pool_host_free",
+           "rm_pool_host_register", "rm_pool_host_unregister", "rm_pool_alloc", "rm_pool_free", "rm_pool_memcpy_d2h", "rm_pool_probe_fp32_peak"]
 
 _LIB = None
 
@@ -120,5 +126,25 @@ def lib():
         L.rm_ipc_close.argtypes = [vp, vp]
         L.rm_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
         L.rm_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+        L.rm_pool_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, u32]
+        L.rm_pool_destroy.argtypes = [vp]
+        L.rm_pool_destroy.restype = None
+        L.rm_pool_last_error.argtypes = [vp]
+        L.rm_pool_last_error.restype = C.c_char_p
+        L.rm_pool_device_count.argtypes = [vp]
+        L.rm_pool_upload_scene.argtypes = [vp, C.POINTER(Scene)]
+        L.rm_pool_render.argtypes = [vp, C.POINTER(Request), C.POINTER(Result)]
+        L.rm_pool_render_device.argtypes = [vp, C.POINTER(Request), C.POINTER(Result)]
+        L.rm_pool_render_frames.argtypes = [vp, C.POINTER(Request), i32, C.POINTER(Result), C.POINTER(Stats)]
+        L.rm_pool_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.rm_pool_device_stats.argtypes = [vp, i32, C.POINTER(Stats)]
+        L.rm_pool_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.rm_pool_host_free.argtypes = [vp, vp]
+        L.rm_pool_host_register.argtypes = [vp, vp, C.c_size_t]
+        L.rm_pool_host_unregister.argtypes = [vp, vp]
+        L.rm_pool_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.rm_pool_free.argtypes = [vp, vp]
+        L.rm_pool_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+        L.rm_pool_probe_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
         _LIB = L
     return _LIB

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "rm_ctx.h"
 #include "rm_host.h"
 #include "rm_types.h"
 
@@ -24,51 +25,7 @@ using namespace rm;
 
 namespace {
 thread_local std::string g_create_error;
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
 }  // namespace
-
-struct rm_ctx {
-    int device = 0;
-    unsigned flags = 0;
-    int n_sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::mutex mu;
-    std::string err;
-    // scene
-    bool has_scene = false;
-    bool exact_only = false;  // operator trees / mandelbulb: always the exact (fp64) kernels
-    DevScene scene{};
-    std::vector<void*> scene_allocs;
-    TreeProgram tree;            // operator-tree scenes: compiled programs (host copy, for the per-frame animation offsets)
-    float* d_anim = nullptr;     // device copy of the AnimatedTranslate offsets (inside scene_allocs)
-    double anim_time = 0.0;
-    bool anim_valid = false;
-    // per-launch stats
-    DevStats* d_stats = nullptr;
-    DevStats* h_stats = nullptr;  // pinned
-    rm_stats_t last{};
-    // band staging for rm_render (device planes + pinned host mirror)
-    DevBuf d_frame, h_frame;
-    // early download of finished row bands (rm_render into page-locked planes)
-    cudaStream_t copy_stream = nullptr;
-    unsigned int* h_band_flags = nullptr;  // page-locked, written by the kernel (kMaxBands words)
-    struct EarlyCopy {
-        bool on = false;
-        int n_bands = 0, band_rows = 0, band_h = 0, width = 0;
-        int stripe_rows = 0, stripe_count = 1, stripe_index = 0;  // row stripes: only the owned rows are copied
-        struct Plane { char* dst; const char* src; size_t bpp; } planes[9];
-        int n_planes = 0;
-    } early;
-    // user allocations (rm_alloc / rm_host_alloc) and caller memory page-locked by rm_host_register
-    std::vector<void*> user_allocs;
-    std::vector<std::pair<char*, size_t>> host_allocs;
-    std::vector<std::pair<char*, size_t>> host_registered;
-};
 
 namespace {
 
@@ -155,8 +112,9 @@ int fail(rm_ctx* c, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(c, RM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-void free_scene(rm_ctx* c) {
-    for (void* p : c->scene_allocs) cudaFree(p);
+}  // namespace
+void rm::free_scene(rm_ctx* c) {
+    for (const SceneAlloc& a : c->scene_allocs) cudaFree(a.p);
     c->scene_allocs.clear();
     c->has_scene = false;
     c->exact_only = false;
@@ -165,6 +123,7 @@ void free_scene(rm_ctx* c) {
     c->anim_valid = false;
     std::memset(&c->scene, 0, sizeof(c->scene));
 }
+namespace {
 
 template <class T>
 int upload(rm_ctx* c, const T* host, size_t n, const T** dev_out) {
@@ -172,7 +131,7 @@ int upload(rm_ctx* c, const T* host, size_t n, const T** dev_out) {
     if (n == 0) return RM_OK;
     void* d = nullptr;
     CU(c, cudaMalloc(&d, n * sizeof(T)));
-    c->scene_allocs.push_back(d);
+    c->scene_allocs.push_back({d, n * sizeof(T), (ptrdiff_t)((const char*)dev_out - c->build_base)});
     CU(c, cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     *dev_out = (const T*)d;
     return RM_OK;
@@ -287,6 +246,10 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.depth_f32 = out->depth_f32;
     P.sdf_u32 = out->sdf_eval_u32;
     P.depth_f64 = out->depth_f64;
+    {
+        auto al16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+        P.vec_store = (rq->width % kTileW == 0 && al16(P.depth) && al16(P.normal) && al16(P.sdf) && al16(P.iters) && al16(P.rgba) && al16(P.rgba2)) ? 1 : 0;
+    }
     P.stats = c->d_stats;
     const bool early = c->early.on && P.n_tiles > 0;
     if (early) {
@@ -366,13 +329,17 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     L.tc_passes = s.tc_passes;
     L.tc_requests = s.tc_requests;
     L.tc_items = s.tc_items;
-    L.executed_flops = L.algorithmic_flops;
+    L.fp32_pipe_flops = L.algorithmic_flops;  // every counted evaluation was performed (validation build: in fp64)
+    L.tensor_flops = 0.0;
     if (s.tc_passes) {
-        // leaf evaluations (11 FLOP) + two tf32 sweeps of 128 x 128 x 16 MACs per cluster block + 128 spheres per work item
+        // leaf evaluations (11 FLOP) + 128 spheres per work item on the FP32 pipe; two tf32 sweeps of 128 x 128 x 16 MACs per
+        // cluster block on the tensor cores
         const double leafEvals = (double)s.evals_sphere - (double)s.tc_requests * (double)c->scene.n_prims;
-        L.executed_flops = 11.0 * leafEvals + (double)s.tc_passes * (double)c->scene.n_tc_blocks * 2.0 * (2.0 * 128 * 128 * 16) +
-                           (double)s.tc_items * 128.0 * 11.0;
+        L.fp32_pipe_flops = 11.0 * leafEvals + (double)s.tc_items * 128.0 * 11.0;
+        L.tensor_flops = (double)s.tc_passes * (double)c->scene.n_tc_blocks * 2.0 * (2.0 * 128 * 128 * 16);
     }
+    L.executed_flops = L.fp32_pipe_flops + L.tensor_flops;
+    L.n_devices = 1;
     L.kernel_ms = ms;
     L.n_launches = launches;
     L.device = c->device;
@@ -580,6 +547,7 @@ int rm_upload_scene(rm_ctx* c, const rm_scene* s) {
     free_scene(c);
 
     DevScene ds{};
+    c->build_base = (const char*)&ds;  // every upload() below fills a pointer field of `ds`
     ds.n_prims = nObj;
     ds.accel_kind = s->accel_kind;
     ds.prim_kind = allTS ? PK_TSPHERE : PK_GENERAL;
@@ -940,7 +908,7 @@ int rm_render(rm_ctx* c, const rm_request* rq, const rm_result* out) {
     dev.depth_f64 = out->depth_f64 ? (double*)(d + oD64) : nullptr;
     auto pinned = [&](const void* p, size_t bytes) {
         if (!p) return true;
-        for (auto* v : {&c->host_allocs, &c->host_registered})
+        for (auto* v : {&c->host_allocs, &c->host_registered, &c->host_shared})
             for (auto& h : *v)
                 if ((const char*)p >= h.first && (const char*)p + bytes <= h.first + h.second) return true;
         return false;

@@ -53,6 +53,12 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RM_TC_BATCH
 #define RM_TC_BATCH 128  // requests that trigger a tensor-core pass (<= 128)
 #endif
+#ifndef RM_VEC_EPILOGUE
+#define RM_VEC_EPILOGUE 0  // staged (shared-memory) tile epilogue with 16-byte vector stores: measured SLOWER (cfg4 +18 %, cfg5 +53 %, profiles/r02b_ab.jsonl): off
+#endif
+#ifndef RM_SLAB_PRETEST
+#define RM_SLAB_PRETEST 1  // fp32 conservative pre-test in front of the fp64 slab test of the lazy grid walk (0: A/B switch)
+#endif
 #ifndef RM_TC_WARPS
 #define RM_TC_WARPS 16  // warps per CTA of the translation-only-sphere BVH kernel (one CTA per SM; the first 16 run the tensor-core sweeps)
 #endif
@@ -1222,6 +1228,7 @@ struct Ray {
     int i;                     // march loop index
     int phase;
     int px, py;  // pixel (x, band-local y)
+    int slot;    // tile staging slot of the vectorised epilogue this pixel is written through, or -1: scalar stores
     bool done;   // rayMarch has returned (depth is valid)
     bool pending;  // parked on the dense all-primitives pass
     int cur, nIv;  // BVH interval cursor (bvh.ts:204-240)
@@ -1299,6 +1306,8 @@ RM_DEV bool cell_in_range(uint32_t lo, uint32_t hi, int x, int y, int z) {
 constexpr int kPendCap = RM_PEND_CAP;  // rm_types.h
 struct LazyIv {
     double tNext[3], tDelta[3], invD[3];  // invD = 1 / direction, computed once per ray
+    float invDf[3];                       // (float)invD and whether the fp32 pre-test of the slab test applies to this ray
+    bool f32ok;                           // (no axis-parallel component: |d_i| >= 1e-10 on every axis)
     double tEnd, safeT;
     double pEnter[kPendCap], pExit[kPendCap];
     int pNode[kPendCap];
@@ -1337,6 +1346,24 @@ RM_DEV void lazy_insert(LazyIv& lz, double enter, double exit_, int node) {
     lz.count++;
 }
 
+// Conservative fp32 form of BoundingBox.intersectRay + the [0, 10] clip for a ray with no axis-parallel component.  Every fp32
+// slab parameter is within 2e-7 (relative) of the fp64 one the reference computes (f32 difference of two f32 values, f32
+// reciprocal of the direction, one product: three roundings of 6e-8), so with m = 4e-7 x the largest |t| of the six planes the
+// tests below only reject boxes the exact test rejects too; everything else goes on to the exact fp64 test.  NaN never rejects.
+RM_DEV bool slab_certain_miss_f32(const float4 bmn, const float4 bmx, const float* __restrict__ of, const float (&invDf)[3]) {
+    const float bl[3] = {bmn.x, bmn.y, bmn.z}, bh[3] = {bmx.x, bmx.y, bmx.z};
+    float tMin = -3.0e38f, tMax = 3.0e38f, mag = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float t0 = (bl[i] - of[i]) * invDf[i], t1 = (bh[i] - of[i]) * invDf[i];
+        tMin = fmaxf(tMin, fminf(t0, t1));
+        tMax = fminf(tMax, fmaxf(t0, t1));
+        mag = fmaxf(mag, fmaxf(fabsf(t0), fabsf(t1)));
+    }
+    const float m = 4.0e-7f * mag + 1.0e-30f;
+    return (tMin - tMax > 2.f * m) || (tMax < -m) || (tMin > 10.f + m);
+}
+
 // returns false when the ray misses the root box (=> no intervals at all)
 static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz) {
     lz.head = 0;
@@ -1345,10 +1372,13 @@ static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o
     lz.overflow = false;
     lz.safeT = -1.0;
     double invD[3];
+    lz.f32ok = true;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         invD[i] = 1.0 / (double)d[i];
         lz.invD[i] = invD[i];
+        lz.invDf[i] = (float)invD[i];
+        lz.f32ok = lz.f32ok && !(fabs((double)d[i]) < 1e-10);
     }
     double tE, tX;
     const rm_bvh_node* root = sc.bvh;
@@ -1385,7 +1415,7 @@ static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o
 }
 
 // examine the current cell, then step to the next one
-static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz) {
+static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const double o[3], const float* __restrict__ of, const float d[3], LazyIv& lz) {
     const double invD[3] = {lz.invD[0], lz.invD[1], lz.invD[2]};
     const int cx = lz.cell[0], cy = lz.cell[1], cz = lz.cell[2];
     const size_t c = ((size_t)cz * sc.grid_dims[1] + cy) * sc.grid_dims[0] + cx;
@@ -1410,11 +1440,23 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
         for (int k = 1; k < 6; ++k) len = (k == code) ? cnt[k] : len;
         e1 = e0 + len;
     }
+    const bool pre = lz.f32ok && RM_SLAB_PRETEST;
+    const float invDf[3] = {lz.invDf[0], lz.invDf[1], lz.invDf[2]};
+    const float4* __restrict__ lrec = reinterpret_cast<const float4*>(sc.grid_leafrec);
     for (uint32_t e = e0; e < e1; ++e) {
         const uint32_t node = __ldg(list + e);
-        const rm_bvh_node* nd = sc.bvh + node;
         double tE, tX;
-        if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tE, tX)) continue;
+        if (lrec != nullptr) {
+            // translation-only spheres: the box comes from the 80-byte leaf record the point query reads too (two LDG.128,
+            // same cache lines) and first meets the fp32 pre-test: most leaves of a cell are missed by the ray
+            const float4 bmn = __ldg(lrec + 5u * (size_t)node), bmx = __ldg(lrec + 5u * (size_t)node + 1);
+            if (pre && slab_certain_miss_f32(bmn, bmx, of, invDf)) continue;
+            const float bl[3] = {bmn.x, bmn.y, bmn.z}, bh[3] = {bmx.x, bmx.y, bmx.z};
+            if (!box_intersect_ray(bl, bh, o, d, invD, tE, tX)) continue;
+        } else {
+            const rm_bvh_node* nd = sc.bvh + node;
+            if (!box_intersect_ray(nd->bmin, nd->bmax, o, d, invD, tE, tX)) continue;
+        }
         if (tX < 0.0 || tE > 10.0) continue;
         if (lz.overflow) break;
         lazy_insert(lz, tE > 0.0 ? tE : 0.0, tX < 10.0 ? tX : 10.0, (int)node);
@@ -1443,7 +1485,7 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
 }
 
 // next interval of the sorted list, or false when the list is exhausted
-RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz, double& enter, double& exit_) {
+RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float* __restrict__ of, const float d[3], LazyIv& lz, double& enter, double& exit_) {
     for (;;) {
         if (lz.count > 0 && (lz.done || lz.pEnter[lz.head] < lz.safeT)) {
             enter = lz.pEnter[lz.head];
@@ -1454,18 +1496,18 @@ RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float d[3], La
             return true;
         }
         if (lz.done || lz.overflow) return false;
-        lazy_advance_cell(sc, o, d, lz);
+        lazy_advance_cell(sc, o, of, d, lz);
     }
 }
 
 // Move the interval cursor to the next entry of the sorted list (currentIntervalIdx++).  Lazy mode pulls it
 // from the grid walk; if the walk's buffer overflowed, the ray falls back to the literal eager list.
 template <class NP, bool kLazy>
-RM_DEV void bvh_advance(const DevScene& sc, const double o[3], Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
+RM_DEV void bvh_advance(const DevScene& sc, const double o[3], const float* __restrict__ of, Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
     r.cur++;
     if constexpr (kLazy) {
         if (r.lazy) {
-            r.curValid = lazy_pop(sc, o, r.d, lz, r.curEnter, r.curExit);
+            r.curValid = lazy_pop(sc, o, of, r.d, lz, r.curEnter, r.curExit);
             if (r.curValid || !lz.overflow) return;
             r.nIv = bvh_collect(sc.bvh, o, r.d, iv, cap);  // overflow: rebuild the list the reference's way
             r.lazy = false;
@@ -1480,11 +1522,11 @@ RM_DEV void bvh_advance(const DevScene& sc, const double o[3], Ray<NP>& r, IvLis
 
 // BVH.onRayMarchStep (bvh.ts:204-240).
 template <class NP, bool kLazy>
-RM_DEV double bvh_step(const DevScene& sc, const double o[3], Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
+RM_DEV double bvh_step(const DevScene& sc, const double o[3], const float* __restrict__ of, Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
     if (!r.curValid) return -1.0;  // currentIntervalIdx >= intervals.length
     if (r.t < r.curEnter) return r.curEnter - r.t;
     if (r.t > r.curExit) {
-        bvh_advance<NP, kLazy>(sc, o, r, iv, lz, cap);
+        bvh_advance<NP, kLazy>(sc, o, of, r, iv, lz, cap);
         if (r.curValid) {
             if (r.curEnter > r.t) return r.curEnter - r.t;
         } else {
@@ -1624,7 +1666,12 @@ template <class NP, int ACCEL, int PK>
 struct CtaShape {
     static constexpr int kWarps = (!NP::kExact && ACCEL == RM_ACCEL_BVH) ? (PK == PK_TSPHERE ? RM_TC_WARPS : 8) : 4;
 };
-template <class NP, int ACCEL, int PK>
+// TCK: the instance whose all-primitives pass is the tensor-core cluster screen (translation-only spheres behind a BVH with the
+//      cluster data uploaded); its FFMA search body is compiled out — scenes without cluster data (RM_DISABLE_TC, < 256 spheres)
+//      launch the TCK = false instance instead.  113 KB less SASS in the hot kernel: -2.9 % frame time (profiles/r01_ab_tconly.log).
+// ALGT: >= 0 fixes Job.algorithm at compile time (0 = sphere tracer, the BASELINE configs' algorithm): the V2 / V3 / fixed-step
+//      state and branches fold away; -1 = run-time switch.
+template <class NP, int ACCEL, int PK, bool TCK = false, int ALGT = -1>
 __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                                   (ACCEL == RM_ACCEL_BVH) ? ((RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL, PK>::kWarps > 0 ? (RM_MIN_BLOCKS_BVH * 4) / CtaShape<NP, ACCEL, PK>::kWarps : 1) : RM_MIN_BLOCKS_OTHER)
     render_kernel(const __grid_constant__ RenderParams P) {
@@ -1632,14 +1679,15 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     constexpr int kQueueCap = kWarpsPerCta * 32;  // each thread has at most one request outstanding
     constexpr unsigned kBatch = (kWarpsPerCta >= 8) ? 64u : 32u;  // requests served per cooperative pass (FFMA search)
     // translation-only spheres behind a BVH: the pass runs on the tensor cores, 128 requests at a time (tc_pass)
-    constexpr bool kTC = !NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE && kWarpsPerCta >= 16;
+    static_assert(!TCK || (!NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE && kWarpsPerCta >= 16), "TCK needs the 16-warp sphere/BVH shape");
+    constexpr bool kTC = TCK;
     constexpr unsigned kBatchMax = kTC ? (unsigned)kTcBlock : kBatch;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     const double o[3] = {(double)P.origin[0], (double)P.origin[1], (double)P.origin[2]};
     const double MAX_DIST = 10.0, EPSILON = 0.001;
-    const int alg = P.algorithm;
+    const int alg = (ALGT >= 0) ? ALGT : P.algorithm;
     const bool hitOnly = (alg == RM_ALG_FIXED_STEP || alg == RM_ALG_ADAPTIVE_STEP);  // return hit ? t : MAX_DIST
     const int maxSteps = hitOnly ? kMaxStepsFixed : kMaxStepsSphere;
     const double stepSize = P.step_size, overshoot = P.overshoot;
@@ -1672,7 +1720,17 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     __shared__ unsigned long long shTcKey[kTcBlock];  // per request: (flipped fp32 distance << 32 | sorted sphere index), atomicMin
     __shared__ unsigned shTcItems;
     __shared__ uint32_t shTmemBase;
+    // Vectorised tile epilogue: a retiring ray parks its quantised outputs in its tile's 512-byte staging slot; when the last
+    // ray of the 8x4 tile has retired the warp writes the tile out with 16-byte stores (u16 planes 16 B and RGBA 2 x 16 B per
+    // tile row) and 8-byte stores (depth 8 B, normal 3 x 8 B per tile row): 2 store instructions per tile instead of ~7 scalar
+    // stores per pixel issued lane by lane.  Slot layout: depth[32] | sdf u16[32] | iters u16[32] | rgba u32[32] | rgba2 u32[32] |
+    // normal[96].  Two slots per warp (rays of an older tile may still be in flight when the next tile is fetched); a tile that
+    // finds no free slot, an edge tile or unaligned planes (P.vec_store == 0) fall back to the scalar stores.
+    constexpr int kEpiSlotBytes = 512, kEpiSdf = 32, kEpiIters = 96, kEpiRgba = 160, kEpiRgba2 = 288, kEpiNormal = 416;
+    __shared__ __align__(16) unsigned char shEpi[kWarpsPerCta][2][kEpiSlotBytes];
     const int warpId = threadIdx.x >> 5;
+    const bool vecOK = RM_VEC_EPILOGUE && P.vec_store != 0;
+    int epiRem0 = 0, epiRem1 = 0, epiTile0 = 0, epiTile1 = 0, curSlot = -1;  // warp-uniform
     WarpStage ws;
     ws.phase = 0u;
 #pragma unroll
@@ -1774,6 +1832,51 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         __syncwarp();
     };
 
+    // Write a retired tile out of its staging slot (called warp-uniformly).  Instruction A (st.global.v4, 16 B): lanes 0-3 the
+    // SDF-call rows, 4-7 the iteration rows, 8-15 the RGBA rows (two halves each), 16-23 the analytics RGBA rows.  Instruction B
+    // (st.global.v2, 8 B): lanes 0-3 the depth rows, 4-15 the normal rows (three parts each).
+    auto flush_tile = [&](int slot, int tileId) {
+        __syncwarp();  // every lane's staging stores are visible to the lanes that read them below
+        const int os = tileId / P.tiles_per_stripe, rem = tileId - os * P.tiles_per_stripe;
+        const int tyIn = rem / P.tiles_x, tx = rem - tyIn * P.tiles_x;
+        const int x0 = tx * kTileW, y0 = (os * P.stripe_count + P.stripe_index) * P.stripe_rows + tyIn * kTileH;
+        const unsigned char* sl = &shEpi[warpId][slot][0];
+        {
+            char* dst = nullptr;
+            int src = 0;
+            const int j = lane & 7, row16 = lane & 3;
+            if (lane < 4) {
+                dst = reinterpret_cast<char*>(P.sdf) + 2 * ((size_t)(y0 + row16) * P.width + x0);
+                src = kEpiSdf + 16 * row16;
+            } else if (lane < 8) {
+                dst = reinterpret_cast<char*>(P.iters) + 2 * ((size_t)(y0 + row16) * P.width + x0);
+                src = kEpiIters + 16 * row16;
+            } else if (lane < 16) {
+                if (P.rgba) dst = reinterpret_cast<char*>(P.rgba) + 4 * ((size_t)(y0 + (j >> 1)) * P.width + x0) + 16 * (j & 1);
+                src = kEpiRgba + 16 * j;
+            } else if (lane < 24) {
+                if (P.rgba2) dst = reinterpret_cast<char*>(P.rgba2) + 4 * ((size_t)(y0 + (j >> 1)) * P.width + x0) + 16 * (j & 1);
+                src = kEpiRgba2 + 16 * j;
+            }
+            if (dst) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(sl + src);
+        }
+        {
+            char* dst = nullptr;
+            int src = 0;
+            if (lane < 4) {
+                dst = reinterpret_cast<char*>(P.depth) + ((size_t)(y0 + lane) * P.width + x0);
+                src = 8 * lane;
+            } else if (lane < 16) {
+                const int j = lane - 4, row = j / 3, part = j - 3 * row;
+                dst = reinterpret_cast<char*>(P.normal) + 3 * ((size_t)(y0 + row) * P.width + x0) + 8 * part;
+                src = kEpiNormal + 24 * row + 8 * part;
+            }
+            if (dst) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(sl + src);
+        }
+        if (P.band_flags && lane < kTileH) atomicAdd(&shBandFin[warpId][(y0 + lane) / P.band_rows], (unsigned)kTileW);  // early download
+        __syncwarp();  // the slot may be handed to the next tile
+    };
+
     // Warp scheduler.  Expensive, warp-serialising stages are deferred until enough lanes want them: BVH
     // ray set-up (a full tree traversal) runs when initLanes lanes are free or nothing else can progress;
     // the all-primitives pass goes through the CTA-wide request queue below.
@@ -1821,11 +1924,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                     // halve the shared-memory wavefronts per evaluation)
                     constexpr int NQ = (int)(kBatch / 32u);
                     float rq[NQ][3];
-#ifdef RM_EXP_TC_ONLY  // experiment (profiles/prof_cfg4_100k_r01j_stalls.txt): the tensor-core kernel without its FFMA fallback body
-                    if (!tcDone && !kTC) {
-#else
-                    if (!tcDone) {
-#endif
+                    if constexpr (!kTC) {  // (the tensor-core instance carries no FFMA search body)
 #pragma unroll
                     for (int k = 0; k < NQ; ++k) {
                         rq[k][0] = rq[k][1] = rq[k][2] = 0.f;
@@ -1942,6 +2041,22 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 }
                 tile = (int)t;
                 tilePos = 0;
+                curSlot = -1;
+                if (vecOK) {  // a full tile inside the band (the width is a multiple of 8 when vec_store is set) takes a free staging slot
+                    const int os = tile / P.tiles_per_stripe, tyIn = (tile - os * P.tiles_per_stripe) / P.tiles_x;
+                    const int y0 = (os * P.stripe_count + P.stripe_index) * P.stripe_rows + tyIn * kTileH;
+                    if (y0 + kTileH <= bandH) {
+                        if (epiRem0 == 0) {
+                            curSlot = 0;
+                            epiRem0 = kTileW * kTileH;
+                            epiTile0 = tile;
+                        } else if (epiRem1 == 0) {
+                            curSlot = 1;
+                            epiRem1 = kTileW * kTileH;
+                            epiTile1 = tile;
+                        }
+                    }
+                }
             }
             int avail = kTileW * kTileH - tilePos;
             int nIdle = __popc(idle);
@@ -1957,6 +2072,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 if (x < P.width && yl < bandH) {  // edge tiles: out-of-range pixels are skipped
                     r.px = x;
                     r.py = yl;
+                    r.slot = curSlot;
                     r.phase = PH_NEW;
                 }
             }
@@ -2009,7 +2125,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 } else {
                     r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
                 }
-                bvh_advance<NP, kLazy>(P.scene, o, r, iv, lz, maxSteps + 1);  // cursor -> interval 0
+                bvh_advance<NP, kLazy>(P.scene, o, P.origin, r, iv, lz, maxSteps + 1);  // cursor -> interval 0
                 if (!r.curValid) {  // {terminate:true} -> return MAX_DIST (sphereTracer.ts:38-40)
                     r.depth = MAX_DIST;
                     r.done = true;
@@ -2029,7 +2145,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                               f32r(o[2] + (double)r.d[2] * r.t)};
                 if constexpr (ACCEL != RM_ACCEL_NONE) {
                     double skip;
-                    if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP, kLazy>(P.scene, o, r, iv, lz, maxSteps + 1);
+                    if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP, kLazy>(P.scene, o, P.origin, r, iv, lz, maxSteps + 1);
                     else skip = octree_march(P.scene.oct, o, r.d, r.t, p);
                     if (skip == -1.0) {  // nothing left: `return MAX_DIST`
                         r.depth = MAX_DIST;
@@ -2351,21 +2467,36 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
 
         // ---- (f) finalize: quantise, shade, store, accumulate diagnostics (raymarcher.ts:103-106) ----
-        if (r.phase == PH_FINAL) {
+        const bool finNow = r.phase == PH_FINAL;
+        if (finNow) {
             size_t idx = (size_t)r.py * P.width + r.px;
             unsigned nb0 = to_u8_clamp(((double)r.n0 + 1.0) * 0.5 * 255.0);
             unsigned nb1 = to_u8_clamp(((double)r.n1 + 1.0) * 0.5 * 255.0);
             unsigned nb2 = to_u8_clamp(((double)r.n2 + 1.0) * 0.5 * 255.0);
             unsigned db = to_u8_clamp(r.depth);
             unsigned sdf16 = r.sdf & 0xffffu, it16 = r.iters & 0xffffu;
-            P.depth[idx] = (uint8_t)db;
-            P.normal[3 * idx + 0] = (uint8_t)nb0;
-            P.normal[3 * idx + 1] = (uint8_t)nb1;
-            P.normal[3 * idx + 2] = (uint8_t)nb2;
-            P.sdf[idx] = (uint16_t)sdf16;
-            P.iters[idx] = (uint16_t)it16;
-            if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[idx] = shade_pixel<NP>(P.shader, db, nb0, nb1, nb2, sdf16, it16);
-            if (P.rgba2) reinterpret_cast<uchar4*>(P.rgba2)[idx] = shade_pixel<NP>(P.shader2, db, nb0, nb1, nb2, sdf16, it16);
+            if (vecOK && r.slot >= 0) {  // park the pixel in its tile's staging slot (written out when the tile has retired)
+                unsigned char* sl = &shEpi[warpId][r.slot][0];
+                const int k = ((r.py & (kTileH - 1)) * kTileW) | (r.px & (kTileW - 1));
+                sl[k] = (unsigned char)db;
+                sl[kEpiNormal + 3 * k + 0] = (unsigned char)nb0;
+                sl[kEpiNormal + 3 * k + 1] = (unsigned char)nb1;
+                sl[kEpiNormal + 3 * k + 2] = (unsigned char)nb2;
+                reinterpret_cast<uint16_t*>(sl + kEpiSdf)[k] = (uint16_t)sdf16;
+                reinterpret_cast<uint16_t*>(sl + kEpiIters)[k] = (uint16_t)it16;
+                if (P.rgba) reinterpret_cast<uchar4*>(sl + kEpiRgba)[k] = shade_pixel<NP>(P.shader, db, nb0, nb1, nb2, sdf16, it16);
+                if (P.rgba2) reinterpret_cast<uchar4*>(sl + kEpiRgba2)[k] = shade_pixel<NP>(P.shader2, db, nb0, nb1, nb2, sdf16, it16);
+            } else {
+                P.depth[idx] = (uint8_t)db;
+                P.normal[3 * idx + 0] = (uint8_t)nb0;
+                P.normal[3 * idx + 1] = (uint8_t)nb1;
+                P.normal[3 * idx + 2] = (uint8_t)nb2;
+                P.sdf[idx] = (uint16_t)sdf16;
+                P.iters[idx] = (uint16_t)it16;
+                if (P.rgba) reinterpret_cast<uchar4*>(P.rgba)[idx] = shade_pixel<NP>(P.shader, db, nb0, nb1, nb2, sdf16, it16);
+                if (P.rgba2) reinterpret_cast<uchar4*>(P.rgba2)[idx] = shade_pixel<NP>(P.shader2, db, nb0, nb1, nb2, sdf16, it16);
+                if (P.band_flags) atomicAdd(&shBandFin[warpId][r.py / P.band_rows], 1u);  // early download, flushed per tile
+            }
             if (P.depth_f32) P.depth_f32[idx] = (float)r.depth;
             if (P.depth_f64) P.depth_f64[idx] = r.depth;
             if (P.sdf_u32) P.sdf_u32[idx] = r.sdf;
@@ -2387,7 +2518,17 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             st.max_iters = max(st.max_iters, it16);
             st.min_iters = min(st.min_iters, it16);
             r.phase = PH_IDLE;
-            if (P.band_flags) atomicAdd(&shBandFin[warpId][r.py / P.band_rows], 1u);  // early download, flushed per tile
+        }
+        if (vecOK) {  // warp-uniform: tiles whose last ray has just retired are written out
+            const unsigned f0 = __ballot_sync(kFull, finNow && r.slot == 0), f1 = __ballot_sync(kFull, finNow && r.slot == 1);
+            if (f0) {
+                epiRem0 -= __popc(f0);
+                if (epiRem0 == 0) flush_tile(0, epiTile0);
+            }
+            if (f1) {
+                epiRem1 -= __popc(f1);
+                if (epiRem1 == 0) flush_tile(1, epiTile1);
+            }
         }
 
         // ---- (g) cooperative mode: publish whether this warp can still make progress on its own ----

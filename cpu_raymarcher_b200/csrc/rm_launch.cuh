@@ -7,9 +7,9 @@
 
 namespace rm {
 
-template <class NP, int ACCEL, int PK>
+template <class NP, int ACCEL, int PK, bool TCK = false, int ALGT = -1>
 static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
-    auto kern = render_kernel<NP, ACCEL, PK>;
+    auto kern = render_kernel<NP, ACCEL, PK, TCK, ALGT>;
     constexpr int kWarps = CtaShape<NP, ACCEL, PK>::kWarps;
     constexpr int kThreads = 32 * kWarps;
     constexpr size_t kDynSmem = (size_t)kWarps * 2 * kStageBytes;  // per-warp double-buffered TMA stages
@@ -42,6 +42,12 @@ static int launch_render_t(const RenderParams& p, int n_sms, void* stream_) {
         if constexpr (!NP::kExact) {
             if (ak == RM_ACCEL_NONE) return launch_one<NP, RM_ACCEL_NONE, PK_TSPHERE>(p, n_sms, stream);
             if (ak == RM_ACCEL_OCTREE) return launch_one<NP, RM_ACCEL_OCTREE, PK_TSPHERE>(p, n_sms, stream);
+            // cluster data uploaded (>= 256 spheres, RM_DISABLE_TC unset): the tensor-core instance, specialised for the
+            // sphere tracer (every BASELINE config's algorithm); otherwise the FFMA-search instance
+            if (p.scene.tc_tiles != nullptr && p.scene.n_prims >= 256) {
+                if (p.algorithm == RM_ALG_SPHERE_TRACER) return launch_one<NP, RM_ACCEL_BVH, PK_TSPHERE, true, RM_ALG_SPHERE_TRACER>(p, n_sms, stream);
+                return launch_one<NP, RM_ACCEL_BVH, PK_TSPHERE, true, -1>(p, n_sms, stream);
+            }
             return launch_one<NP, RM_ACCEL_BVH, PK_TSPHERE>(p, n_sms, stream);
         }
     }

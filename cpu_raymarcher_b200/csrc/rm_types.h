@@ -144,6 +144,7 @@ struct RenderParams {
     int32_t shader, shader2;
     int32_t length_sqrt;  // validation: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot
     int32_t n_tiles, tiles_x;
+    int32_t vec_store;  // width % 8 == 0 and every output plane 16-byte aligned: whole tiles are written with vector stores
     int32_t stripe_rows, stripe_count, stripe_index, tiles_per_stripe;  // row-stripe interleave (multi-GPU)
     // outputs (device pointers; optional ones may be null)
     uint8_t* depth;

@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 2 /* v2: operator trees (rm_op_node, rm_scene.n_objects...), rm_build_*_scene, rm_stats_t.operator_flops */
+#define RM_ABI_VERSION 3 /* v2: operator trees (rm_op_node, rm_scene.n_objects...), rm_build_*_scene, rm_stats_t.operator_flops
+                            v3: rm_pool_* (one process drives every GPU of the box), rm_stats_t.fp32_pipe_flops / tensor_flops / n_devices */
 
 typedef struct rm_ctx rm_ctx; /* opaque: one CUDA device, its stream, device-resident scene + frame buffers */
 
@@ -191,6 +192,12 @@ typedef struct rm_stats_t {
     uint64_t tc_requests;      /* fallback requests served                                                      */
     uint64_t tc_items;         /* (request, 128-sphere cluster) pairs evaluated sphere by sphere                 */
     double executed_flops;     /* FLOPs actually executed for SDF work: leaf evaluations + tf32 MMAs + work items */
+    /* executed_flops split by the pipe that ran them (ABI v3): the roofline numerator is fp32_pipe_flops */
+    double fp32_pipe_flops;    /* FP32 (non-tensor) pipe: primitive evaluations actually performed (leaf candidates, streamed
+                                  search, cluster-screen work items) x their executed FLOP count                        */
+    double tensor_flops;       /* tcgen05 tf32 MMAs of the cluster screen: 2 sweeps x 128 x 128 x 16 MACs per cluster block  */
+    int32_t n_devices;         /* 1, or the number of GPUs a pool call used (rm_pool_stats)                               */
+    int32_t pad_;
 } rm_stats_t;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -253,6 +260,49 @@ int rm_host_free(rm_ctx* ctx, void* host_ptr);
  * filled by N workers, main.ts:452-490).  The memory must stay mapped until rm_host_unregister / rm_destroy. */
 int rm_host_register(rm_ctx* ctx, void* host_ptr, size_t bytes);
 int rm_host_unregister(rm_ctx* ctx, void* host_ptr);
+
+/* ---- multi-GPU inside ONE process: rm_pool (ABI v3) ---------------------------------------------------------
+ * The reference's worker pool lives in one process: main.ts:318-321 creates the workers, main.ts:444-490 deals one row
+ * band of the frame to each and awaits them all, main.ts:527-548 reduces the diagnostics over the assembled frame.  An
+ * rm_pool is that pool with GPUs for workers: one rm_ctx and one host thread per device, all owned by the library.
+ *   - rm_pool_upload_scene: the scene is compiled and uploaded ONCE (device 0: operator programs, BVH/octree, leaf grid,
+ *     cluster data) and replicated to the other devices with peer-to-peer copies over NVLink — "each worker rebuilds the
+ *     scene" (raymarchWorker.ts:37-38) becomes one build + N-1 device-to-device copies;
+ *   - rm_pool_render: the band is dealt to the devices as interleaved 8-row stripes, all devices render concurrently and
+ *     every device downloads its own stripes over its own PCIe link into the caller's planes while its kernel still runs
+ *     (page-lock the planes with rm_pool_host_alloc / rm_pool_host_register for that);
+ *   - band requests of one frame (the <= 4 concurrent Jobs of main.ts:452-486) share ONE render: the first band request of
+ *     a new (camera, algorithm, parameters, size, time) key renders the whole frame across all devices into a frame cache
+ *     of the pool, the others copy their rows out — callable concurrently from several host threads (N-API async workers);
+ *   - rm_pool_render_device: planes in device 0's HBM; the other devices' kernels store their pixels straight into them
+ *     through peer access (the tile gather of main.ts:461-468 fused into the render kernel);
+ *   - rm_pool_render_frames: different frames on different devices (the Analytics rotation sweep, main.ts:438-441);
+ *   - rm_pool_stats: main.ts:527-548 over the whole frame — sums, maxima and minima combined over the devices, kernel_ms =
+ *     the slowest device.  The 14 words per device are already in page-locked host memory when the kernels finish, so the
+ *     reduction is a host loop: a device collective would add a launch and a synchronisation per frame for 112 bytes.
+ * devices == NULL or n_devices <= 0: every visible device.  A device may be listed more than once (several contexts, each with
+ * its own stripe share, on one GPU — how the single-GPU test box exercises the N-way path). */
+typedef struct rm_pool rm_pool;
+int rm_pool_create(rm_pool** out, const int* devices, int n_devices, unsigned flags);
+void rm_pool_destroy(rm_pool* pool);
+const char* rm_pool_last_error(rm_pool* pool); /* pool may be NULL: error of the last failed rm_pool_create on this thread */
+int rm_pool_device_count(rm_pool* pool);
+int rm_pool_upload_scene(rm_pool* pool, const rm_scene* scene);
+int rm_pool_render(rm_pool* pool, const rm_request* rq, const rm_result* host_out);
+int rm_pool_render_device(rm_pool* pool, const rm_request* rq, const rm_result* device0_out);
+/* n requests (whole frames or bands), request i rendered by device i % n_devices; host_out may be NULL (diagnostics only,
+ * planes stay in device scratch) or an array of n results; stats_out (optional) receives n per-frame diagnostics. */
+int rm_pool_render_frames(rm_pool* pool, const rm_request* rqs, int32_t n, const rm_result* host_out, rm_stats_t* stats_out);
+int rm_pool_stats(rm_pool* pool, rm_stats_t* out);                    /* of the last rm_pool_render / _device call, whole frame */
+int rm_pool_device_stats(rm_pool* pool, int32_t i, rm_stats_t* out); /* device i's share of it (load balance, per-rank kernel ms) */
+int rm_pool_host_alloc(rm_pool* pool, size_t bytes, void** host_ptr);  /* page-locked for every device of the pool */
+int rm_pool_host_free(rm_pool* pool, void* host_ptr);
+int rm_pool_host_register(rm_pool* pool, void* host_ptr, size_t bytes);
+int rm_pool_host_unregister(rm_pool* pool, void* host_ptr);
+int rm_pool_alloc(rm_pool* pool, size_t bytes, void** device0_ptr);    /* device-0 memory every device of the pool can store into */
+int rm_pool_free(rm_pool* pool, void* device0_ptr);
+int rm_pool_memcpy_d2h(rm_pool* pool, void* host, const void* device0_ptr, size_t bytes);
+int rm_pool_probe_fp32_peak(rm_pool* pool, double* tflops);           /* device 0 */
 
 /* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "multi-GPU") -------------------- */
 /* Device allocation owned by the context (freed by rm_free / rm_destroy). */

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/rm.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert L.rm_abi_version() == 2
+    assert L.rm_abi_version() == 3
 
 
 def test_struct_layouts_match_c_abi():
