@@ -16,7 +16,7 @@ typedef struct napi_async_work__* napi_async_work;
 typedef struct napi_deferred__* napi_deferred;
 typedef struct napi_ref__* napi_ref;
 typedef enum { napi_ok = 0 } napi_status;
-typedef enum { napi_uint8_array = 1, napi_uint8_clamped_array = 2, napi_uint16_array = 4, napi_float32_array = 9, napi_float64_array = 10 } napi_typedarray_type;
+typedef enum { napi_uint8_array = 1, napi_uint8_clamped_array = 2, napi_uint16_array = 4, napi_int32_array = 5, napi_float32_array = 9, napi_float64_array = 10 } napi_typedarray_type;
 typedef napi_value (*napi_callback)(napi_env env, napi_callback_info info);
 typedef void (*napi_async_execute_callback)(napi_env env, void* data);
 typedef void (*napi_async_complete_callback)(napi_env env, napi_status status, void* data);
@@ -50,6 +50,9 @@ napi_status napi_throw_error(napi_env, const char* code, const char* msg);
 napi_status napi_create_async_work(napi_env, napi_value async_resource, napi_value async_resource_name, napi_async_execute_callback, napi_async_complete_callback, void* data, napi_async_work* result);
 napi_status napi_queue_async_work(napi_env, napi_async_work);
 napi_status napi_delete_async_work(napi_env, napi_async_work);
+napi_status napi_create_reference(napi_env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+napi_status napi_delete_reference(napi_env, napi_ref ref);
+napi_status napi_get_reference_value(napi_env, napi_ref ref, napi_value* result);
 napi_status napi_define_properties(napi_env, napi_value object, size_t property_count, const napi_property_descriptor* properties);
 void napi_module_register(napi_module*);
 #ifdef __cplusplus

@@ -1,18 +1,23 @@
-// rm_napi.cc — Node N-API addon over the C ABI of include/rm.h (COMPILE-ONLY in this image: no Node.js).
+// rm_napi.cc — Node N-API addon over the C ABI of include/rm.h.
 //
-// Exposes to JavaScript exactly what the reference's worker did (src/workers/raymarchWorker.ts):
+// Exposes to JavaScript exactly what the reference's worker pool did (src/main.ts:318-321,444-490 + src/workers/raymarchWorker.ts):
 //   addon.uploadScene({type: Uint8Array, worldToLocal: Float32Array, params: Float64Array, accel: 'None'|'Octree'|'BVH',
 //                      opNodes?: Uint8Array (rm_op_node records, 128 B each), objectRoot?: Int32Array})
-//       -> rm_upload_scene          (replaces `new Scene(accel); scene.loadPreset(i)`, raymarchWorker.ts:37-38)
+//       -> rm_pool_upload_scene     (replaces `new Scene(accel); scene.loadPreset(i)`, raymarchWorker.ts:37-38, once for every GPU)
 //   addon.render(job, camera{rot3: Float32Array(9), origin: Float32Array(3)}) : Promise<Result>
-//       -> rm_render on a libuv worker thread (the JS event loop never blocks on CUDA); Result carries the
-//          four typed arrays of raymarchWorker.ts:24-31 (ownership moves to JS, like the reference's transfer
-//          list :86-91).  They are views of ONE external ArrayBuffer over page-locked memory (rm_host_alloc), so
-//          rm_render DMAs straight into them and, for big bands, downloads finished rows while the kernel still
-//          runs; blocks return to a pool when JS garbage-collects the buffer.  Where the runtime forbids external
-//          buffers (V8 sandbox / recent Electron) the arrays fall back to plain ArrayBuffers (staged copy).
-//   addon.stats() -> rm_stats       (diagnostics of main.ts:527-548 for the last band)
-// The `Worker` shim that makes main.ts use this unchanged is ts/gpuWorkerShim.ts.
+//       -> rm_pool_render on a libuv worker thread (the JS event loop never blocks on CUDA).  The library owns every GPU of the
+//          box (RM_DEVICES=0,1,... restricts it): a band Job is served from the pool's frame cache, so the <= 4 concurrent band
+//          jobs of one frame (main.ts:452-486) cost ONE render across all GPUs.  Result carries the four typed arrays of
+//          raymarchWorker.ts:24-31 (ownership moves to JS, like the reference's transfer list :86-91): views of ONE external
+//          ArrayBuffer over page-locked memory (rm_pool_host_alloc); blocks return to a free list when JS garbage-collects the
+//          buffer.  Where the runtime forbids external buffers (V8 sandbox / recent Electron) they are plain ArrayBuffers.
+//          The Result object is held by a napi_ref while the worker thread fills it.
+//   addon.stats() -> rm_pool_stats  (diagnostics of main.ts:527-548 over the whole frame of the last band)
+//   addon.deviceCount()
+// The `Worker` shim that makes main.ts use this unchanged is ts/gpuWorkerShim.ts.  No Node.js exists in the build image: the
+// addon is compiled against addon/napi_min.h and EXECUTED under the mock N-API runtime of tests/napi_mock.cc (tests/
+// test_gpu_addon.py), which enforces handle scopes; tools/node_harness.mjs is the one-command check on a box with Node >= 18.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -27,7 +32,29 @@
 #include "../include/rm.h"
 
 namespace {
-rm_ctx* g_ctx = nullptr;
+rm_pool* g_rm = nullptr;  // every GPU of the box (or RM_DEVICES) behind one object
+std::mutex g_rm_mu;
+
+bool ensure_pool(napi_env env) {
+    std::lock_guard<std::mutex> lk(g_rm_mu);
+    if (g_rm) return true;
+    std::vector<int> devs;
+    if (const char* e = std::getenv("RM_DEVICES")) {
+        for (const char* p = e; *p;) {
+            char* end = nullptr;
+            const long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            devs.push_back((int)v);
+            p = (*end == ',') ? end + 1 : end;
+        }
+    }
+    if (rm_pool_create(&g_rm, devs.empty() ? nullptr : devs.data(), (int)devs.size(), 0) != RM_OK) {
+        napi_throw_error(env, "RM_ERR_CUDA", rm_pool_last_error(nullptr));
+        g_rm = nullptr;
+        return false;
+    }
+    return true;
+}
 
 double get_num(napi_env env, napi_value obj, const char* key, double dflt) {
     bool has = false;
@@ -69,10 +96,7 @@ napi_value UploadScene(napi_env env, napi_callback_info info) {
     size_t argc = 1;
     napi_value arg;
     napi_get_cb_info(env, info, &argc, &arg, nullptr, nullptr);
-    if (!g_ctx && rm_create(&g_ctx, 0, 0) != RM_OK) {
-        napi_throw_error(env, "RM_ERR_CUDA", rm_last_error(nullptr));
-        return nullptr;
-    }
+    if (!ensure_pool(env)) return nullptr;
     rm_scene s;
     std::memset(&s, 0, sizeof(s));
     size_t nt, nm, np;
@@ -99,7 +123,7 @@ napi_value UploadScene(napi_env env, napi_callback_info info) {
         s.object_root = (const int32_t*)roots;
         s.n_objects = (int32_t)nr;
     }
-    if (rm_upload_scene(g_ctx, &s) != RM_OK) napi_throw_error(env, "RM_ERR", rm_last_error(g_ctx));
+    if (rm_pool_upload_scene(g_rm, &s) != RM_OK) napi_throw_error(env, "RM_ERR", rm_pool_last_error(g_rm));
     return nullptr;
 }
 
@@ -119,7 +143,7 @@ void* pool_take(size_t bytes, size_t* cap) {
     }
     void* p = nullptr;
     *cap = bytes;
-    return (g_ctx && rm_host_alloc(g_ctx, bytes, &p) == RM_OK) ? p : nullptr;
+    return (g_rm && rm_pool_host_alloc(g_rm, bytes, &p) == RM_OK) ? p : nullptr;
 }
 struct PoolBlock {
     void* p;
@@ -135,33 +159,37 @@ void pool_give(napi_env, void*, void* hint) {  // napi_finalize of the external 
 struct RenderWork {
     rm_request rq;
     rm_result out;
-    napi_value unused;
     napi_deferred deferred;
     napi_async_work work;
+    // The Result object (and through it the ArrayBuffer the worker thread writes into) must outlive the native call that
+    // created it: a napi_value dies with its handle scope, so a strong reference carries it to the completion callback.
     napi_ref keep;
     int rc;
     std::string err;
     size_t npx;
     // ArrayBuffers are created on the JS thread before the work is queued; the worker thread only fills them
     void *depth, *normal, *sdf, *iters;
-    napi_value result_obj;
 };
 
 void RenderExecute(napi_env, void* data) {  // libuv worker thread: no JS here
     RenderWork* w = (RenderWork*)data;
-    w->rc = rm_render(g_ctx, &w->rq, &w->out);
-    if (w->rc != RM_OK) w->err = rm_last_error(g_ctx);
+    w->rc = rm_pool_render(g_rm, &w->rq, &w->out);
+    if (w->rc != RM_OK) w->err = rm_pool_last_error(g_rm);
 }
-void RenderComplete(napi_env env, napi_status, void* data) {
+void RenderComplete(napi_env env, napi_status, void* data) {  // JS thread, inside a fresh handle scope
     RenderWork* w = (RenderWork*)data;
-    if (w->rc == RM_OK) {
-        napi_resolve_deferred(env, w->deferred, w->result_obj);
+    napi_value result_obj = nullptr;
+    const bool have = napi_get_reference_value(env, w->keep, &result_obj) == napi_ok && result_obj != nullptr;
+    if (w->rc == RM_OK && have) {
+        napi_resolve_deferred(env, w->deferred, result_obj);
     } else {
+        if (w->rc == RM_OK) w->err = "the Result object was lost";
         napi_value msg, e;
         napi_create_string_utf8(env, w->err.c_str(), w->err.size(), &msg);
         napi_create_error(env, nullptr, msg, &e);
         napi_reject_deferred(env, w->deferred, e);
     }
+    napi_delete_reference(env, w->keep);
     napi_delete_async_work(env, w->work);
     delete w;
 }
@@ -171,6 +199,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
     napi_value argv[2];
     napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
     napi_value job = argv[0], cam = argv[1];
+    if (!ensure_pool(env)) return nullptr;
     RenderWork* w = new RenderWork();
     std::memset(&w->rq, 0, sizeof(w->rq));
     std::memset(&w->out, 0, sizeof(w->out));
@@ -198,7 +227,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
     w->npx = (size_t)w->rq.width * th;
     // Result arrays (raymarchWorker.ts:42-46): four views of one ArrayBuffer, sections 256-byte aligned.  Preferred backing:
     // a page-locked block (direct DMA + early band download); otherwise a plain ArrayBuffer (rm_render stages the copy).
-    napi_value ab, ta, res, v;
+    napi_value ab = nullptr, ta = nullptr, res = nullptr, v = nullptr;
     napi_create_object(env, &res);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t oDepth = 0, oNormal = al(w->npx), oSdf = oNormal + al(3 * w->npx), oIters = oSdf + al(2 * w->npx);
@@ -235,7 +264,11 @@ napi_value Render(napi_env env, napi_callback_info info) {
     w->out.normal = (uint8_t*)w->normal;
     w->out.sdf_eval = (uint16_t*)w->sdf;
     w->out.iters = (uint16_t*)w->iters;
-    w->result_obj = res;  // kept alive by the promise resolution below (a napi_ref would be used in production)
+    if (napi_create_reference(env, res, 1, &w->keep) != napi_ok) {
+        delete w;
+        napi_throw_error(env, "RM_ERR", "napi_create_reference failed");
+        return nullptr;
+    }
     napi_value promise, name;
     napi_create_promise(env, &w->deferred, &promise);
     napi_create_string_utf8(env, "rm_render", 9, &name);
@@ -248,7 +281,7 @@ napi_value Stats(napi_env env, napi_callback_info) {
     rm_stats_t st;
     napi_value o, v;
     napi_create_object(env, &o);
-    if (!g_ctx || rm_stats(g_ctx, &st) != RM_OK) return o;
+    if (!g_rm || rm_pool_stats(g_rm, &st) != RM_OK) return o;
     napi_create_double(env, (double)st.sum_sdf, &v);
     napi_set_named_property(env, o, "totalSDFCalls", v);
     napi_create_double(env, (double)st.max_sdf, &v);
@@ -259,21 +292,28 @@ napi_value Stats(napi_env env, napi_callback_info) {
     napi_set_named_property(env, o, "totalIterations", v);
     napi_create_double(env, st.kernel_ms, &v);
     napi_set_named_property(env, o, "kernelMs", v);
+    napi_create_double(env, (double)st.n_pixels, &v);
+    napi_set_named_property(env, o, "totalPixels", v);
+    napi_create_int32(env, st.n_devices, &v);
+    napi_set_named_property(env, o, "devices", v);
     return o;
+}
+
+napi_value DeviceCount(napi_env env, napi_callback_info) {
+    napi_value v;
+    napi_create_int32(env, ensure_pool(env) ? rm_pool_device_count(g_rm) : 0, &v);
+    return v;
 }
 
 napi_value Init(napi_env env, napi_value exports) {
     napi_property_descriptor d[] = {{"uploadScene", nullptr, UploadScene, nullptr, nullptr, nullptr, 0, nullptr},
                                     {"render", nullptr, Render, nullptr, nullptr, nullptr, 0, nullptr},
-                                    {"stats", nullptr, Stats, nullptr, nullptr, nullptr, 0, nullptr}};
-    napi_define_properties(env, exports, 3, d);
+                                    {"stats", nullptr, Stats, nullptr, nullptr, nullptr, 0, nullptr},
+                                    {"deviceCount", nullptr, DeviceCount, nullptr, nullptr, nullptr, 0, nullptr}};
+    napi_define_properties(env, exports, 4, d);
     return exports;
 }
-napi_module g_mod = {1, 0, __FILE__, Init, "rm_napi", nullptr, {nullptr, nullptr, nullptr, nullptr}};
-struct Registrar {
-    Registrar() { napi_module_register(&g_mod); }
-};
-#ifdef RM_HAVE_NODE_API_H
-Registrar g_registrar;  // NAPI_MODULE(rm_napi, Init)
-#endif
 }  // namespace
+
+// Module entry: the well-known symbol Node resolves when it dlopens the .node file (what NAPI_MODULE_INIT() expands to).
+extern "C" __attribute__((visibility("default"))) napi_value napi_register_module_v1(napi_env env, napi_value exports) { return Init(env, exports); }

@@ -126,6 +126,9 @@ def lib():
         L.rm_ipc_close.argtypes = [vp, vp]
         L.rm_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
         L.rm_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+        if os.environ.get("RM_B200_LIB") and not hasattr(L, "rm_pool_create"):
+            _LIB = L  # an older A/B build of the library (tools/ab_bench.py) without the rm_pool entry points
+            return _LIB
         L.rm_pool_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, u32]
         L.rm_pool_destroy.argtypes = [vp]
         L.rm_pool_destroy.restype = None

@@ -54,7 +54,10 @@ constexpr unsigned kFull = 0xffffffffu;
 #define RM_TC_BATCH 128  // requests that trigger a tensor-core pass (<= 128)
 #endif
 #ifndef RM_VEC_EPILOGUE
-#define RM_VEC_EPILOGUE 0  // staged (shared-memory) tile epilogue with 16-byte vector stores: measured SLOWER (cfg4 +18 %, cfg5 +53 %, profiles/r02b_ab.jsonl): off
+#define RM_VEC_EPILOGUE 0  // 1: retired pixels are held in registers and written per whole tile with 16-byte vector stores (shuffle transpose).  Parity-green (profiles/r02c_gpu_tests_vec_epilogue.log) but SLOWER on every config (cfg4 +2 %, cfg5 +14 %, profiles/r02c_ab.jsonl): the scalar stores at retirement are fire-and-forget, the tile write sits on the refill path.  Default 0.
+#endif
+#ifndef RM_TC_STATIC_QUEUE
+#define RM_TC_STATIC_QUEUE 0  // 1: tensor-core instance treats the cooperative queue as a compile-time fact, dropping the warp-local search body (211 -> 146 KB of SASS).  Measured SLOWER (cfg4 33.4 -> 39.2 ms, profiles/r02d_ab.jsonl): ptxas then spills 544 B instead of 138 B at the 128-register cap.  Default 0.
 #endif
 #ifndef RM_SLAB_PRETEST
 #define RM_SLAB_PRETEST 1  // fp32 conservative pre-test in front of the fp64 slab test of the lazy grid walk (0: A/B switch)
@@ -73,7 +76,8 @@ enum Phase : int {
     PH_WAIT_N1,
     PH_WAIT_N2,
     PH_WAIT_N3,
-    PH_FINAL  // march + normal done: quantise and store
+    PH_FINAL,  // march + normal done: quantise and store
+    PH_HELD    // vectorised epilogue: retired, quantised outputs held in registers until the warp's next refill point
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1110,11 +1114,11 @@ RM_DEV void search_stages(const RenderParams& P, const float q[3], WarpStage& ws
 
 // Turn the search result into the scene distance: recover the index inside the winning chunk, then ONE
 // fp64 evaluation of that primitive (the "polish"), clamped to MAX_DIST like scene.ts:145-146.
-template <int PK>
+template <int PK, bool kExactIndexOnly = false>
 RM_DEV double finish_search(const RenderParams& P, const float q[3], int code) {
     if (code < 0) return 10.0;  // nothing closer than MAX_DIST
     int idx = code;
-    if (code & kChunkFlag) {
+    if (!kExactIndexOnly && (code & kChunkFlag)) {  // (the cluster screen always returns an exact index)
         const int chunk = code & ~kChunkFlag;
         float mm = 3.0e38f;
         for (int k = 0; k < kChunk; ++k) {
@@ -1228,7 +1232,6 @@ struct Ray {
     int i;                     // march loop index
     int phase;
     int px, py;  // pixel (x, band-local y)
-    int slot;    // tile staging slot of the vectorised epilogue this pixel is written through, or -1: scalar stores
     bool done;   // rayMarch has returned (depth is valid)
     bool pending;  // parked on the dense all-primitives pass
     int cur, nIv;  // BVH interval cursor (bvh.ts:204-240)
@@ -1720,17 +1723,16 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     __shared__ unsigned long long shTcKey[kTcBlock];  // per request: (flipped fp32 distance << 32 | sorted sphere index), atomicMin
     __shared__ unsigned shTcItems;
     __shared__ uint32_t shTmemBase;
-    // Vectorised tile epilogue: a retiring ray parks its quantised outputs in its tile's 512-byte staging slot; when the last
-    // ray of the 8x4 tile has retired the warp writes the tile out with 16-byte stores (u16 planes 16 B and RGBA 2 x 16 B per
-    // tile row) and 8-byte stores (depth 8 B, normal 3 x 8 B per tile row): 2 store instructions per tile instead of ~7 scalar
-    // stores per pixel issued lane by lane.  Slot layout: depth[32] | sdf u16[32] | iters u16[32] | rgba u32[32] | rgba2 u32[32] |
-    // normal[96].  Two slots per warp (rays of an older tile may still be in flight when the next tile is fetched); a tile that
-    // finds no free slot, an edge tile or unaligned planes (P.vec_store == 0) fall back to the scalar stores.
-    constexpr int kEpiSlotBytes = 512, kEpiSdf = 32, kEpiIters = 96, kEpiRgba = 160, kEpiRgba2 = 288, kEpiNormal = 416;
-    __shared__ __align__(16) unsigned char shEpi[kWarpsPerCta][2][kEpiSlotBytes];
     const int warpId = threadIdx.x >> 5;
-    const bool vecOK = RM_VEC_EPILOGUE && P.vec_store != 0;
-    int epiRem0 = 0, epiRem1 = 0, epiTile0 = 0, epiTile1 = 0, curSlot = -1;  // warp-uniform
+    // Vectorised tile epilogue.  A retiring ray does not store its pixel: it keeps the quantised outputs packed in four registers
+    // of its (now dead) ray state and waits as PH_HELD.  When the warp next wants to refill, the held pixels are written together:
+    // if all 32 lanes hold the pixels of one whole 8x4 tile claimed in one go (lane = pixel index), the tile is transposed with
+    // warp shuffles and written with 16-byte stores (u16 planes: one per tile row; RGBA: two per tile row) and 8-byte stores
+    // (depth: one per tile row; normal: three per tile row); otherwise (edge tiles, tiles claimed piecewise while lanes were
+    // parked on the all-primitives pass, unaligned planes) every held lane writes its own pixel as before.
+    constexpr bool kHeldEpi = RM_VEC_EPILOGUE != 0;
+    const bool vecOK = kHeldEpi && P.vec_store != 0;
+    bool curWhole = false;  // warp-uniform: the current tile was claimed by all 32 lanes at once
     WarpStage ws;
     ws.phase = 0u;
 #pragma unroll
@@ -1740,7 +1742,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         ws.bar[sgi] = smem_u32(&shBar[warpId][sgi]);
     }
     ws.resident = false;
-    if constexpr (!NP::kExact) {
+    if constexpr (!NP::kExact && !(kTC && RM_TC_STATIC_QUEUE)) {  // (the tensor-core instance never streams primitives through the per-warp stages)
         if (lane == 0) {
             mbar_init(ws.bar[0], 1);
             mbar_init(ws.bar[1], 1);
@@ -1772,8 +1774,10 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     __syncthreads();
     bool wasStuck = false, wasFinished = false;  // this warp's contribution to shStuck / shFinished
     // the shared queue pays off when one all-primitives pass is much more expensive than a march step
-    const bool useQueue = !NP::kExact && (ACCEL == RM_ACCEL_BVH) && P.scene.n_prims >= 256;
-    const bool useTC = kTC && useQueue && P.scene.tc_tiles != nullptr;
+    // (the tensor-core instance is only launched for >= 256 spheres with the cluster data uploaded: a compile-time `true`
+    // drops the warp-local streamed search — a quarter of this instance's SASS — from the kernel)
+    const bool useQueue = (kTC && RM_TC_STATIC_QUEUE) ? true : (!NP::kExact && (ACCEL == RM_ACCEL_BVH) && P.scene.n_prims >= 256);
+    const bool useTC = kTC;
     const unsigned batchCap = useTC ? min(kBatchMax, (unsigned)RM_TC_BATCH) : kBatch;
     TcCtx tc;
     if constexpr (kTC) {
@@ -1832,49 +1836,64 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         __syncwarp();
     };
 
-    // Write a retired tile out of its staging slot (called warp-uniformly).  Instruction A (st.global.v4, 16 B): lanes 0-3 the
-    // SDF-call rows, 4-7 the iteration rows, 8-15 the RGBA rows (two halves each), 16-23 the analytics RGBA rows.  Instruction B
-    // (st.global.v2, 8 B): lanes 0-3 the depth rows, 4-15 the normal rows (three parts each).
-    auto flush_tile = [&](int slot, int tileId) {
-        __syncwarp();  // every lane's staging stores are visible to the lanes that read them below
-        const int os = tileId / P.tiles_per_stripe, rem = tileId - os * P.tiles_per_stripe;
-        const int tyIn = rem / P.tiles_x, tx = rem - tyIn * P.tiles_x;
-        const int x0 = tx * kTileW, y0 = (os * P.stripe_count + P.stripe_index) * P.stripe_rows + tyIn * kTileH;
-        const unsigned char* sl = &shEpi[warpId][slot][0];
-        {
-            char* dst = nullptr;
-            int src = 0;
-            const int j = lane & 7, row16 = lane & 3;
-            if (lane < 4) {
-                dst = reinterpret_cast<char*>(P.sdf) + 2 * ((size_t)(y0 + row16) * P.width + x0);
-                src = kEpiSdf + 16 * row16;
-            } else if (lane < 8) {
-                dst = reinterpret_cast<char*>(P.iters) + 2 * ((size_t)(y0 + row16) * P.width + x0);
-                src = kEpiIters + 16 * row16;
-            } else if (lane < 16) {
-                if (P.rgba) dst = reinterpret_cast<char*>(P.rgba) + 4 * ((size_t)(y0 + (j >> 1)) * P.width + x0) + 16 * (j & 1);
-                src = kEpiRgba + 16 * j;
-            } else if (lane < 24) {
-                if (P.rgba2) dst = reinterpret_cast<char*>(P.rgba2) + 4 * ((size_t)(y0 + (j >> 1)) * P.width + x0) + 16 * (j & 1);
-                src = kEpiRgba2 + 16 * j;
+    // Write the held pixels (called warp-uniformly with the ballot of PH_HELD lanes); their lanes become PH_IDLE.
+    auto flush_held = [&](unsigned heldM) {
+        const bool held = r.phase == PH_HELD;
+        const unsigned w0 = __float_as_uint(r.q[0]), w1 = __float_as_uint(r.q[1]), c1 = __float_as_uint(r.q[2]), c2 = __float_as_uint(r.h[0]);
+        const size_t idx = held ? (size_t)r.py * P.width + r.px : 0;
+        if (vecOK && curWhole && heldM == kFull) {
+            // one whole tile, lane = pixel index (row = lane >> 3, column = lane & 7): transpose with shuffles, store vectors
+            const bool q4 = (lane & 3) == 0, q8 = (lane & 7) == 0;
+            if (P.rgba) {  // 4 pixels = 16 bytes per store, two per tile row
+                const unsigned y = __shfl_down_sync(kFull, c1, 1), z = __shfl_down_sync(kFull, c1, 2), w = __shfl_down_sync(kFull, c1, 3);
+                if (q4) *reinterpret_cast<uint4*>(P.rgba + 4 * idx) = make_uint4(c1, y, z, w);
             }
-            if (dst) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(sl + src);
-        }
-        {
-            char* dst = nullptr;
-            int src = 0;
-            if (lane < 4) {
-                dst = reinterpret_cast<char*>(P.depth) + ((size_t)(y0 + lane) * P.width + x0);
-                src = 8 * lane;
-            } else if (lane < 16) {
-                const int j = lane - 4, row = j / 3, part = j - 3 * row;
-                dst = reinterpret_cast<char*>(P.normal) + 3 * ((size_t)(y0 + row) * P.width + x0) + 8 * part;
-                src = kEpiNormal + 24 * row + 8 * part;
+            if (P.rgba2) {
+                const unsigned y = __shfl_down_sync(kFull, c2, 1), z = __shfl_down_sync(kFull, c2, 2), w = __shfl_down_sync(kFull, c2, 3);
+                if (q4) *reinterpret_cast<uint4*>(P.rgba2 + 4 * idx) = make_uint4(c2, y, z, w);
             }
-            if (dst) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(sl + src);
+            {  // the two u16 planes: 8 pixels = 16 bytes = one store per tile row each
+                const unsigned a = __shfl_down_sync(kFull, w1, 1);
+                const unsigned sp = __byte_perm(w1, a, 0x5410), ip = __byte_perm(w1, a, 0x7632);  // (even lane, odd lane) pairs
+                const unsigned s1 = __shfl_down_sync(kFull, sp, 2), s2 = __shfl_down_sync(kFull, sp, 4), s3 = __shfl_down_sync(kFull, sp, 6);
+                const unsigned i1 = __shfl_down_sync(kFull, ip, 2), i2 = __shfl_down_sync(kFull, ip, 4), i3 = __shfl_down_sync(kFull, ip, 6);
+                if (q8) {
+                    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(P.sdf) + 2 * idx) = make_uint4(sp, s1, s2, s3);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(P.iters) + 2 * idx) = make_uint4(ip, i1, i2, i3);
+                }
+            }
+            {  // depth: 8 pixels = 8 bytes per tile row
+                const unsigned d1 = __shfl_down_sync(kFull, w0, 1);
+                const unsigned b2 = __byte_perm(w0, d1, 0x0040) & 0xffffu;  // bytes (own depth, next lane's depth)
+                const unsigned b4 = b2 | (__shfl_down_sync(kFull, b2, 2) << 16);
+                const unsigned b8 = __shfl_down_sync(kFull, b4, 4);
+                if (q8) *reinterpret_cast<uint2*>(P.depth + idx) = make_uint2(b4, b8);
+            }
+            {  // normal: 3 bytes per pixel, 8 pixels = 24 bytes = three 8-byte stores per tile row
+                const unsigned t = w0 >> 8;
+                const unsigned t1 = __shfl_down_sync(kFull, t, 1), t2 = __shfl_down_sync(kFull, t, 2), t3 = __shfl_down_sync(kFull, t, 3);
+                const unsigned W0 = t | (t1 << 24), W1 = (t1 >> 8) | (t2 << 16), W2 = (t2 >> 16) | (t3 << 8);  // 4 pixels = 12 bytes
+                const unsigned X0 = __shfl_down_sync(kFull, W0, 4), X1 = __shfl_down_sync(kFull, W1, 4), X2 = __shfl_down_sync(kFull, W2, 4);
+                if (q8) {
+                    char* n = reinterpret_cast<char*>(P.normal) + 3 * idx;
+                    *reinterpret_cast<uint2*>(n) = make_uint2(W0, W1);
+                    *reinterpret_cast<uint2*>(n + 8) = make_uint2(W2, X0);
+                    *reinterpret_cast<uint2*>(n + 16) = make_uint2(X1, X2);
+                }
+            }
+            if (P.band_flags && q8) atomicAdd(&shBandFin[warpId][r.py / P.band_rows], (unsigned)kTileW);  // early download
+        } else if (held) {
+            P.depth[idx] = (uint8_t)(w0 & 0xffu);
+            P.normal[3 * idx + 0] = (uint8_t)((w0 >> 8) & 0xffu);
+            P.normal[3 * idx + 1] = (uint8_t)((w0 >> 16) & 0xffu);
+            P.normal[3 * idx + 2] = (uint8_t)(w0 >> 24);
+            P.sdf[idx] = (uint16_t)(w1 & 0xffffu);
+            P.iters[idx] = (uint16_t)(w1 >> 16);
+            if (P.rgba) reinterpret_cast<unsigned*>(P.rgba)[idx] = c1;
+            if (P.rgba2) reinterpret_cast<unsigned*>(P.rgba2)[idx] = c2;
+            if (P.band_flags) atomicAdd(&shBandFin[warpId][r.py / P.band_rows], 1u);
         }
-        if (P.band_flags && lane < kTileH) atomicAdd(&shBandFin[warpId][(y0 + lane) / P.band_rows], (unsigned)kTileW);  // early download
-        __syncwarp();  // the slot may be handed to the next tile
+        if (held) r.phase = PH_IDLE;
     };
 
     // Warp scheduler.  Expensive, warp-serialising stages are deferred until enough lanes want them: BVH
@@ -1984,7 +2003,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                                     bc = shPartCode[w * pStride + (int)threadIdx.x];
                                 }
                             }
-                            res = finish_search<PK>(P, q3, bc);
+                            res = finish_search<PK, kTC>(P, q3, bc);
                         } else {
                             res = 10.0;
                             for (int j = 0; j < P.scene.n_prims; ++j)
@@ -2021,13 +2040,15 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
 
         // ---- (a) refill: lanes without a ray claim the next pixels of the warp's current tile ----
-        unsigned idle = __ballot_sync(kFull, r.phase == PH_IDLE);
+        unsigned idle;
         {
-            const int nIdle = __popc(idle);
+            const unsigned heldM = kHeldEpi ? __ballot_sync(kFull, r.phase == PH_HELD) : 0u;
+            const int nIdle = __popc(__ballot_sync(kFull, r.phase == PH_IDLE) | heldM);
             const int nPend = __popc(__ballot_sync(kFull, r.pending));
             const int nAct = 32 - nIdle - nPend;
             const bool doRefill = (nAct == 0) || (nIdle >= initLanes);
-            if (!doRefill) idle = 0u;
+            if (kHeldEpi && doRefill && heldM) flush_held(heldM);  // held pixels are written before their lanes take new ones
+            idle = doRefill ? __ballot_sync(kFull, r.phase == PH_IDLE) : 0u;
         }
         while (idle && !queueEmpty) {
             if (tilePos >= kTileW * kTileH) {
@@ -2041,26 +2062,11 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 }
                 tile = (int)t;
                 tilePos = 0;
-                curSlot = -1;
-                if (vecOK) {  // a full tile inside the band (the width is a multiple of 8 when vec_store is set) takes a free staging slot
-                    const int os = tile / P.tiles_per_stripe, tyIn = (tile - os * P.tiles_per_stripe) / P.tiles_x;
-                    const int y0 = (os * P.stripe_count + P.stripe_index) * P.stripe_rows + tyIn * kTileH;
-                    if (y0 + kTileH <= bandH) {
-                        if (epiRem0 == 0) {
-                            curSlot = 0;
-                            epiRem0 = kTileW * kTileH;
-                            epiTile0 = tile;
-                        } else if (epiRem1 == 0) {
-                            curSlot = 1;
-                            epiRem1 = kTileW * kTileH;
-                            epiTile1 = tile;
-                        }
-                    }
-                }
             }
             int avail = kTileW * kTileH - tilePos;
             int nIdle = __popc(idle);
             int take = avail < nIdle ? avail : nIdle;
+            if (tilePos == 0) curWhole = (take == kTileW * kTileH);  // all 32 lanes at once: lane = pixel index within the tile
             int rank = __popc(idle & lt_mask);
             if (r.phase == PH_IDLE && rank < take) {
                 int k = tilePos + rank;
@@ -2072,7 +2078,6 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 if (x < P.width && yl < bandH) {  // edge tiles: out-of-range pixels are skipped
                     r.px = x;
                     r.py = yl;
-                    r.slot = curSlot;
                     r.phase = PH_NEW;
                 }
             }
@@ -2467,25 +2472,21 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
 
         // ---- (f) finalize: quantise, shade, store, accumulate diagnostics (raymarcher.ts:103-106) ----
-        const bool finNow = r.phase == PH_FINAL;
-        if (finNow) {
+        if (r.phase == PH_FINAL) {
             size_t idx = (size_t)r.py * P.width + r.px;
             unsigned nb0 = to_u8_clamp(((double)r.n0 + 1.0) * 0.5 * 255.0);
             unsigned nb1 = to_u8_clamp(((double)r.n1 + 1.0) * 0.5 * 255.0);
             unsigned nb2 = to_u8_clamp(((double)r.n2 + 1.0) * 0.5 * 255.0);
             unsigned db = to_u8_clamp(r.depth);
             unsigned sdf16 = r.sdf & 0xffffu, it16 = r.iters & 0xffffu;
-            if (vecOK && r.slot >= 0) {  // park the pixel in its tile's staging slot (written out when the tile has retired)
-                unsigned char* sl = &shEpi[warpId][r.slot][0];
-                const int k = ((r.py & (kTileH - 1)) * kTileW) | (r.px & (kTileW - 1));
-                sl[k] = (unsigned char)db;
-                sl[kEpiNormal + 3 * k + 0] = (unsigned char)nb0;
-                sl[kEpiNormal + 3 * k + 1] = (unsigned char)nb1;
-                sl[kEpiNormal + 3 * k + 2] = (unsigned char)nb2;
-                reinterpret_cast<uint16_t*>(sl + kEpiSdf)[k] = (uint16_t)sdf16;
-                reinterpret_cast<uint16_t*>(sl + kEpiIters)[k] = (uint16_t)it16;
-                if (P.rgba) reinterpret_cast<uchar4*>(sl + kEpiRgba)[k] = shade_pixel<NP>(P.shader, db, nb0, nb1, nb2, sdf16, it16);
-                if (P.rgba2) reinterpret_cast<uchar4*>(sl + kEpiRgba2)[k] = shade_pixel<NP>(P.shader2, db, nb0, nb1, nb2, sdf16, it16);
+            if constexpr (kHeldEpi) {
+                // keep the pixel packed in the dead ray state (q[0..2], h[0]); it is written at the warp's next refill point
+                const uchar4 c1 = P.rgba ? shade_pixel<NP>(P.shader, db, nb0, nb1, nb2, sdf16, it16) : make_uchar4(0, 0, 0, 0);
+                const uchar4 c2 = P.rgba2 ? shade_pixel<NP>(P.shader2, db, nb0, nb1, nb2, sdf16, it16) : make_uchar4(0, 0, 0, 0);
+                r.q[0] = __uint_as_float(db | (nb0 << 8) | (nb1 << 16) | (nb2 << 24));
+                r.q[1] = __uint_as_float(sdf16 | (it16 << 16));
+                r.q[2] = __uint_as_float((unsigned)c1.x | ((unsigned)c1.y << 8) | ((unsigned)c1.z << 16) | ((unsigned)c1.w << 24));
+                r.h[0] = __uint_as_float((unsigned)c2.x | ((unsigned)c2.y << 8) | ((unsigned)c2.z << 16) | ((unsigned)c2.w << 24));
             } else {
                 P.depth[idx] = (uint8_t)db;
                 P.normal[3 * idx + 0] = (uint8_t)nb0;
@@ -2517,18 +2518,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             st.min_sdf = min(st.min_sdf, sdf16);
             st.max_iters = max(st.max_iters, it16);
             st.min_iters = min(st.min_iters, it16);
-            r.phase = PH_IDLE;
-        }
-        if (vecOK) {  // warp-uniform: tiles whose last ray has just retired are written out
-            const unsigned f0 = __ballot_sync(kFull, finNow && r.slot == 0), f1 = __ballot_sync(kFull, finNow && r.slot == 1);
-            if (f0) {
-                epiRem0 -= __popc(f0);
-                if (epiRem0 == 0) flush_tile(0, epiTile0);
-            }
-            if (f1) {
-                epiRem1 -= __popc(f1);
-                if (epiRem1 == 0) flush_tile(1, epiTile1);
-            }
+            r.phase = kHeldEpi ? PH_HELD : PH_IDLE;
         }
 
         // ---- (g) cooperative mode: publish whether this warp can still make progress on its own ----
@@ -2568,6 +2558,10 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             __syncthreads();
             if (warpId == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(512u) : "memory");
         }
+    }
+    if constexpr (kHeldEpi) {  // (every path out of the loop has passed a refill point with no active lane; kept as a safety net)
+        const unsigned heldM = __ballot_sync(kFull, r.phase == PH_HELD);
+        if (heldM) flush_held(heldM);
     }
     publish_bands();  // pixels finalised since the warp's last tile fetch
     // ---- epilogue: diagnostics (main.ts:527-548) — warp reduce, one atomic set per warp ----

@@ -263,17 +263,18 @@ class FrameSharder:
         # two all-reduces on packed int64 words: SUM (counters; FLOP totals are integer-valued) and MAX (minima negated)
         sums = torch.tensor([st["n_pixels"], st["sum_sdf"], st["sum_iters"], st["sum_sdf_full"], st["sum_iters_full"], st["n_hit"],
                              st["n_launches"]] + list(st["evals_by_type"]) +
-                            [round(st["algorithmic_flops"]), round(st["executed_flops"]), st["tc_passes"], st["tc_requests"], st["tc_items"]],
+                            [round(st["algorithmic_flops"]), round(st["executed_flops"]), st["tc_passes"], st["tc_requests"], st["tc_items"],
+                             round(st.get("fp32_pipe_flops", 0.0)), round(st.get("tensor_flops", 0.0))],
                             dtype=torch.int64, device=dev)
         maxs = torch.tensor([st["max_sdf"], st["max_iters"], int(st["kernel_ms"] * 1e6), -st["min_sdf"], -st["min_iters"]],
                             dtype=torch.int64, device=dev)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         dist.all_reduce(maxs, op=dist.ReduceOp.MAX)  # also orders every rank's stores / downloads before anybody reads the frame
         both = torch.cat([sums, maxs]).tolist()  # one read-back
-        s, mx = both[:15], both[15:]
+        s, mx = both[:17], both[17:]
         st.update(n_pixels=s[0], sum_sdf=s[1], sum_iters=s[2], sum_sdf_full=s[3], sum_iters_full=s[4], n_hit=s[5], n_launches=s[6],
                   evals_by_type=s[7:10], algorithmic_flops=float(s[10]), executed_flops=float(s[11]),
-                  tc_passes=s[12], tc_requests=s[13], tc_items=s[14], max_sdf=mx[0], max_iters=mx[1], min_sdf=-mx[3], min_iters=-mx[4])
+                  tc_passes=s[12], tc_requests=s[13], tc_items=s[14], fp32_pipe_flops=float(s[15]), tensor_flops=float(s[16]), max_sdf=mx[0], max_iters=mx[1], min_sdf=-mx[3], min_iters=-mx[4])
         st["kernel_ms_max"] = mx[2] / 1e6
         st["frame_ms"] = st["kernel_ms_max"]  # the gather is fused into the kernel: the slowest rank's kernel is the frame
         return st
