@@ -47,6 +47,11 @@ struct rm_ctx {
     rm::DevStats* d_stats = nullptr;
     rm::DevStats* h_stats = nullptr;  // pinned
     rm_stats_t last{};
+    // cost-ordered tile queue: per-tile cycle counts of the last frame and the tile order derived from them; reused while the
+    // frame geometry (size, band, stripes) stays the same
+    rm::DevBuf d_tile_cost, d_tile_order;
+    int order_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool order_valid = false;
     // band staging for rm_render (device planes + pinned host mirror)
     rm::DevBuf d_frame, h_frame;
     // early download of finished row bands (rm_render into page-locked planes)

@@ -56,8 +56,11 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RM_VEC_EPILOGUE
 #define RM_VEC_EPILOGUE 0  // 1: retired pixels are held in registers and written per whole tile with 16-byte vector stores (shuffle transpose).  Parity-green (profiles/r02c_gpu_tests_vec_epilogue.log) but SLOWER on every config (cfg4 +2 %, cfg5 +14 %, profiles/r02c_ab.jsonl): the scalar stores at retirement are fire-and-forget, the tile write sits on the refill path.  Default 0.
 #endif
+#ifndef RM_SMEM_STATS
+#define RM_SMEM_STATS 1  // diagnostics accumulators per warp in shared memory (0: per-lane registers; A/B switch)
+#endif
 #ifndef RM_TC_STATIC_QUEUE
-#define RM_TC_STATIC_QUEUE 0  // 1: tensor-core instance treats the cooperative queue as a compile-time fact, dropping the warp-local search body (211 -> 146 KB of SASS).  Measured SLOWER (cfg4 33.4 -> 39.2 ms, profiles/r02d_ab.jsonl): ptxas then spills 544 B instead of 138 B at the 128-register cap.  Default 0.
+#define RM_TC_STATIC_QUEUE 1  // tensor-core instance: the cooperative queue is a compile-time fact, the warp-local search body is dropped (211 -> 146 KB of SASS).  With the ray state scalar-replaced: cfg4 32.4 -> 30.0 ms (profiles/r02g_ab.jsonl); before that change the same switch cost +18 % (spills, profiles/r02d_ab.jsonl).  0: A/B switch.
 #endif
 #ifndef RM_SLAB_PRETEST
 #define RM_SLAB_PRETEST 1  // fp32 conservative pre-test in front of the fp64 slab test of the lazy grid walk (0: A/B switch)
@@ -1248,8 +1251,12 @@ struct IvList {
 };
 
 // BVH.findRayIntersections + onRayMarchStart (bvh.ts:126-202).  Returns the number of kept intervals.
-static __device__ __noinline__ int bvh_collect(const rm_bvh_node* __restrict__ nodes, const double o[3], const float d[3], IvList& iv,
-                                        int cap) {
+// (Called out of line: the ray origin comes as a pointer into the kernel parameters and the direction BY VALUE, so that no
+// address of the per-lane ray state escapes — an escaping pointer would pin the whole Ray struct in local memory.)
+static __device__ __noinline__ int bvh_collect(const rm_bvh_node* __restrict__ nodes, const float* __restrict__ of, float dx, float dy, float dz,
+                                        IvList& iv, int cap) {
+    const double o[3] = {(double)of[0], (double)of[1], (double)of[2]};
+    const float d[3] = {dx, dy, dz};
     int stack[kBvhStack];
     int sp = 0;
     stack[sp++] = 0;
@@ -1368,7 +1375,9 @@ RM_DEV bool slab_certain_miss_f32(const float4 bmn, const float4 bmx, const floa
 }
 
 // returns false when the ray misses the root box (=> no intervals at all)
-static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o[3], const float d[3], LazyIv& lz) {
+static __device__ __noinline__ bool lazy_init(const DevScene& sc, const float* __restrict__ of, float dx, float dy, float dz, LazyIv& lz) {
+    const double o[3] = {(double)of[0], (double)of[1], (double)of[2]};
+    const float d[3] = {dx, dy, dz};
     lz.head = 0;
     lz.count = 0;
     lz.done = false;
@@ -1418,7 +1427,9 @@ static __device__ __noinline__ bool lazy_init(const DevScene& sc, const double o
 }
 
 // examine the current cell, then step to the next one
-static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const double o[3], const float* __restrict__ of, const float d[3], LazyIv& lz) {
+static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const float* __restrict__ of, float dx, float dy, float dz, LazyIv& lz) {
+    const double o[3] = {(double)of[0], (double)of[1], (double)of[2]};
+    const float d[3] = {dx, dy, dz};
     const double invD[3] = {lz.invD[0], lz.invD[1], lz.invD[2]};
     const int cx = lz.cell[0], cy = lz.cell[1], cz = lz.cell[2];
     const size_t c = ((size_t)cz * sc.grid_dims[1] + cy) * sc.grid_dims[0] + cx;
@@ -1488,7 +1499,7 @@ static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const 
 }
 
 // next interval of the sorted list, or false when the list is exhausted
-RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float* __restrict__ of, const float d[3], LazyIv& lz, double& enter, double& exit_) {
+RM_DEV bool lazy_pop(const DevScene& sc, const float* __restrict__ of, float dx, float dy, float dz, LazyIv& lz, double& enter, double& exit_) {
     for (;;) {
         if (lz.count > 0 && (lz.done || lz.pEnter[lz.head] < lz.safeT)) {
             enter = lz.pEnter[lz.head];
@@ -1499,20 +1510,25 @@ RM_DEV bool lazy_pop(const DevScene& sc, const double o[3], const float* __restr
             return true;
         }
         if (lz.done || lz.overflow) return false;
-        lazy_advance_cell(sc, o, of, d, lz);
+        lazy_advance_cell(sc, of, dx, dy, dz, lz);
     }
 }
 
 // Move the interval cursor to the next entry of the sorted list (currentIntervalIdx++).  Lazy mode pulls it
 // from the grid walk; if the walk's buffer overflowed, the ray falls back to the literal eager list.
 template <class NP, bool kLazy>
-RM_DEV void bvh_advance(const DevScene& sc, const double o[3], const float* __restrict__ of, Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
+RM_DEV void bvh_advance(const DevScene& sc, const float* __restrict__ of, Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
     r.cur++;
     if constexpr (kLazy) {
         if (r.lazy) {
-            r.curValid = lazy_pop(sc, o, of, r.d, lz, r.curEnter, r.curExit);
+            double enter = 0.0, exit_ = 0.0;
+            r.curValid = lazy_pop(sc, of, r.d[0], r.d[1], r.d[2], lz, enter, exit_);
+            if (r.curValid) {
+                r.curEnter = enter;
+                r.curExit = exit_;
+            }
             if (r.curValid || !lz.overflow) return;
-            r.nIv = bvh_collect(sc.bvh, o, r.d, iv, cap);  // overflow: rebuild the list the reference's way
+            r.nIv = bvh_collect(sc.bvh, of, r.d[0], r.d[1], r.d[2], iv, cap);  // overflow: rebuild the list the reference's way
             r.lazy = false;
         }
     }
@@ -1525,11 +1541,11 @@ RM_DEV void bvh_advance(const DevScene& sc, const double o[3], const float* __re
 
 // BVH.onRayMarchStep (bvh.ts:204-240).
 template <class NP, bool kLazy>
-RM_DEV double bvh_step(const DevScene& sc, const double o[3], const float* __restrict__ of, Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
+RM_DEV double bvh_step(const DevScene& sc, const float* __restrict__ of, Ray<NP>& r, IvList& iv, LazyIv& lz, int cap) {
     if (!r.curValid) return -1.0;  // currentIntervalIdx >= intervals.length
     if (r.t < r.curEnter) return r.curEnter - r.t;
     if (r.t > r.curExit) {
-        bvh_advance<NP, kLazy>(sc, o, of, r, iv, lz, cap);
+        bvh_advance<NP, kLazy>(sc, of, r, iv, lz, cap);
         if (r.curValid) {
             if (r.curEnter > r.t) return r.curEnter - r.t;
         } else {
@@ -1704,6 +1720,19 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     LazyIv lz;  // fast-path BVH: grid walk state (local memory)
     constexpr bool kLazy = !NP::kExact && ACCEL == RM_ACCEL_BVH;
     LaneStats st;
+    // Diagnostics accumulators.  Per-lane registers (13 values that stay live across the whole state machine) or — the default —
+    // one set per warp in shared memory, updated with shared atomics when a pixel retires: the accumulators are touched once per
+    // pixel, the registers they would pin are needed by the march on every iteration.
+    // (measured, profiles/r02g_ab.jsonl: shared accumulators win on every kernel — cfg2 -25 %, cfg3 -17 %, cfg5 -5 % — except the
+    // tensor-core instance, where per-lane registers are 1.5 % faster)
+    constexpr bool kSmemStats = RM_SMEM_STATS != 0 && !TCK;
+    __shared__ unsigned long long shStatSum[kSmemStats ? CtaShape<NP, ACCEL, PK>::kWarps : 1][9];
+    __shared__ unsigned shStatMM[kSmemStats ? CtaShape<NP, ACCEL, PK>::kWarps : 1][4];
+    if constexpr (kSmemStats) {
+        if ((threadIdx.x & 31) < 9) shStatSum[threadIdx.x >> 5][threadIdx.x & 31] = 0ull;
+        if ((threadIdx.x & 31) < 4) shStatMM[threadIdx.x >> 5][threadIdx.x & 31] = ((threadIdx.x & 1) ? 0xffffffffu : 0u);  // max, min, max, min
+        __syncwarp();
+    }
 
     // ---- shared memory: per-warp TMA stages for the primitive stream, and the CTA-wide request queue of
     //      the all-primitives service (requests are just a point, so they can move between warps even
@@ -1811,6 +1840,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
 
     // warp-uniform work-queue cursor
     int tile = -1, tilePos = kTileW * kTileH;
+    unsigned tileT0 = 0u;  // clock() at the fetch of the current tile (cost-ordered queue)
     bool queueEmpty = false;
 
     // Early download (rm_render into page-locked planes): publish this warp's finished-pixel counts per row band;
@@ -2060,7 +2090,14 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                     queueEmpty = true;
                     break;
                 }
-                tile = (int)t;
+                // cost-ordered queue: ticket t -> the t-th most expensive tile of the previous frame of this geometry (so the frame ends
+                // on cheap tiles and the end-of-frame tail shrinks); every warp records what its tiles cost for the next frame
+                if (P.tile_cost) {
+                    const unsigned now = (unsigned)clock();
+                    if (tile >= 0 && lane == 0) P.tile_cost[tile] = now - tileT0;
+                    tileT0 = now;
+                }
+                tile = P.tile_order ? (int)__ldg(P.tile_order + t) : (int)t;
                 tilePos = 0;
             }
             int avail = kTileW * kTileH - tilePos;
@@ -2123,14 +2160,14 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 if constexpr (kLazy) {
                     if (P.scene.grid_cell_dir == nullptr) {  // no direction lists (counts beyond 16 bits): the literal list
                         r.lazy = false;
-                        r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
-                    } else if (!lazy_init(P.scene, o, r.d, lz)) {
+                        r.nIv = bvh_collect(P.scene.bvh, P.origin, r.d[0], r.d[1], r.d[2], iv, maxSteps + 1);
+                    } else if (!lazy_init(P.scene, P.origin, r.d[0], r.d[1], r.d[2], lz)) {
                         r.lazy = true;  // missed the root box: lz.done, empty list
                     }
                 } else {
-                    r.nIv = bvh_collect(P.scene.bvh, o, r.d, iv, maxSteps + 1);
+                    r.nIv = bvh_collect(P.scene.bvh, P.origin, r.d[0], r.d[1], r.d[2], iv, maxSteps + 1);
                 }
-                bvh_advance<NP, kLazy>(P.scene, o, P.origin, r, iv, lz, maxSteps + 1);  // cursor -> interval 0
+                bvh_advance<NP, kLazy>(P.scene, P.origin, r, iv, lz, maxSteps + 1);  // cursor -> interval 0
                 if (!r.curValid) {  // {terminate:true} -> return MAX_DIST (sphereTracer.ts:38-40)
                     r.depth = MAX_DIST;
                     r.done = true;
@@ -2150,7 +2187,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                               f32r(o[2] + (double)r.d[2] * r.t)};
                 if constexpr (ACCEL != RM_ACCEL_NONE) {
                     double skip;
-                    if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP, kLazy>(P.scene, o, P.origin, r, iv, lz, maxSteps + 1);
+                    if constexpr (ACCEL == RM_ACCEL_BVH) skip = bvh_step<NP, kLazy>(P.scene, P.origin, r, iv, lz, maxSteps + 1);
                     else skip = octree_march(P.scene.oct, o, r.d, r.t, p);
                     if (skip == -1.0) {  // nothing left: `return MAX_DIST`
                         r.depth = MAX_DIST;
@@ -2501,6 +2538,51 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             if (P.depth_f32) P.depth_f32[idx] = (float)r.depth;
             if (P.depth_f64) P.depth_f64[idx] = r.depth;
             if (P.sdf_u32) P.sdf_u32[idx] = r.sdf;
+            if constexpr (!NP::kExact && PK == PK_TSPHERE) {  // every evaluation is a sphere: the per-type counters are dead weight
+                r.nSphere = r.sdf;
+                r.nBox = 0u;
+            }
+            if constexpr (kSmemStats) {
+                // warp-aggregated: the lanes retiring together reduce their values with REDUX and one of them updates the warp's
+                // accumulators (atomics: another divergent group of the same warp may be doing the same)
+                const unsigned am = __activemask();
+                const bool lead = lane == (__ffs(am) - 1);
+                const unsigned hitv = (r.depth < MAX_DIST) ? 1u : 0u;
+                unsigned v5 = r.nBox, v6, v8 = 0u;
+                if constexpr (NP::kExact) {
+                    v6 = r.ex.nTorus;
+                    v8 = r.ex.opFlops;
+                } else {
+                    v6 = r.sdf - r.nSphere - r.nBox;
+                }
+                const unsigned a0 = __reduce_add_sync(am, sdf16), a1 = __reduce_add_sync(am, it16), a3 = __reduce_add_sync(am, r.iters);
+                const unsigned a7 = __reduce_add_sync(am, hitv);
+                // counters that can exceed 2^27 per pixel (n_prims x steps) are summed in two 16-bit halves
+                const unsigned long long a2 = (unsigned long long)__reduce_add_sync(am, r.sdf & 0xffffu) + ((unsigned long long)__reduce_add_sync(am, r.sdf >> 16) << 16);
+                const unsigned long long a4 = (unsigned long long)__reduce_add_sync(am, r.nSphere & 0xffffu) + ((unsigned long long)__reduce_add_sync(am, r.nSphere >> 16) << 16);
+                const unsigned long long a5 = (unsigned long long)__reduce_add_sync(am, v5 & 0xffffu) + ((unsigned long long)__reduce_add_sync(am, v5 >> 16) << 16);
+                const unsigned long long a6 = (unsigned long long)__reduce_add_sync(am, v6 & 0xffffu) + ((unsigned long long)__reduce_add_sync(am, v6 >> 16) << 16);
+                unsigned long long a8 = 0ull;
+                if constexpr (NP::kExact) a8 = (unsigned long long)__reduce_add_sync(am, v8 & 0xffffu) + ((unsigned long long)__reduce_add_sync(am, v8 >> 16) << 16);
+                const unsigned m0 = __reduce_max_sync(am, sdf16), m1 = __reduce_min_sync(am, sdf16), m2 = __reduce_max_sync(am, it16), m3 = __reduce_min_sync(am, it16);
+                if (lead) {
+                    unsigned long long* ss = shStatSum[threadIdx.x >> 5];
+                    unsigned* mm = shStatMM[threadIdx.x >> 5];
+                    atomicAdd(&ss[0], (unsigned long long)a0);
+                    atomicAdd(&ss[1], (unsigned long long)a1);
+                    atomicAdd(&ss[2], a2);
+                    atomicAdd(&ss[3], (unsigned long long)a3);
+                    atomicAdd(&ss[4], a4);
+                    if (a5) atomicAdd(&ss[5], a5);
+                    if (a6) atomicAdd(&ss[6], a6);
+                    if (a7) atomicAdd(&ss[7], (unsigned long long)a7);
+                    if (a8) atomicAdd(&ss[8], a8);
+                    atomicMax(&mm[0], m0);
+                    atomicMin(&mm[1], m1);
+                    atomicMax(&mm[2], m2);
+                    atomicMin(&mm[3], m3);
+                }
+            } else {
             st.sum_sdf += sdf16;
             st.sum_iters += it16;
             st.sum_sdf_full += r.sdf;
@@ -2518,6 +2600,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             st.min_sdf = min(st.min_sdf, sdf16);
             st.max_iters = max(st.max_iters, it16);
             st.min_iters = min(st.min_iters, it16);
+            }
             r.phase = kHeldEpi ? PH_HELD : PH_IDLE;
         }
 
@@ -2563,16 +2646,26 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         const unsigned heldM = __ballot_sync(kFull, r.phase == PH_HELD);
         if (heldM) flush_held(heldM);
     }
+    if (P.tile_cost && tile >= 0 && lane == 0) P.tile_cost[tile] = (unsigned)clock() - tileT0;  // the warp's last tile
     publish_bands();  // pixels finalised since the warp's last tile fetch
     // ---- epilogue: diagnostics (main.ts:527-548) — warp reduce, one atomic set per warp ----
-    unsigned long long s0 = warp_sum_u64(st.sum_sdf), s1 = warp_sum_u64(st.sum_iters);
-    unsigned long long s2 = warp_sum_u64(st.sum_sdf_full), s3 = warp_sum_u64(st.sum_iters_full);
-    unsigned long long s4 = warp_sum_u64(st.ev_sphere), s5 = warp_sum_u64(st.ev_box), s6 = warp_sum_u64(st.ev_torus);
-    unsigned long long s7 = warp_sum_u64(st.n_hit);
-    unsigned long long s8 = 0;
-    if constexpr (NP::kExact) s8 = warp_sum_u64(st.op_flops);
-    unsigned mx0 = __reduce_max_sync(kFull, st.max_sdf), mn0 = __reduce_min_sync(kFull, st.min_sdf);
-    unsigned mx1 = __reduce_max_sync(kFull, st.max_iters), mn1 = __reduce_min_sync(kFull, st.min_iters);
+    unsigned long long s0, s1, s2, s3, s4, s5, s6, s7, s8 = 0;
+    unsigned mx0, mn0, mx1, mn1;
+    if constexpr (kSmemStats) {
+        __syncwarp();
+        const unsigned long long* ss = shStatSum[threadIdx.x >> 5];
+        const unsigned* mm = shStatMM[threadIdx.x >> 5];
+        s0 = ss[0], s1 = ss[1], s2 = ss[2], s3 = ss[3], s4 = ss[4], s5 = ss[5], s6 = ss[6], s7 = ss[7], s8 = ss[8];
+        mx0 = mm[0], mn0 = mm[1], mx1 = mm[2], mn1 = mm[3];
+    } else {
+        s0 = warp_sum_u64(st.sum_sdf), s1 = warp_sum_u64(st.sum_iters);
+        s2 = warp_sum_u64(st.sum_sdf_full), s3 = warp_sum_u64(st.sum_iters_full);
+        s4 = warp_sum_u64(st.ev_sphere), s5 = warp_sum_u64(st.ev_box), s6 = warp_sum_u64(st.ev_torus);
+        s7 = warp_sum_u64(st.n_hit);
+        if constexpr (NP::kExact) s8 = warp_sum_u64(st.op_flops);
+        mx0 = __reduce_max_sync(kFull, st.max_sdf), mn0 = __reduce_min_sync(kFull, st.min_sdf);
+        mx1 = __reduce_max_sync(kFull, st.max_iters), mn1 = __reduce_min_sync(kFull, st.min_iters);
+    }
     if (lane == 0) {
         DevStats* g = P.stats;
         atomicAdd(&g->sum_sdf, s0);
@@ -2591,6 +2684,35 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         atomicMax(&g->max_iters, mx1);
         atomicMin(&g->min_iters, mn1);
     }
+}
+
+// Cost-ordered tile queue: one CTA turns the per-tile cycle counts a frame recorded into the tile order of the next frame of the
+// same geometry — most expensive first — by a counting sort over 256 logarithmic-free linear buckets (max-scaled).  Ties keep an
+// arbitrary order; the image does not depend on the schedule.
+static __global__ void __launch_bounds__(1024) order_tiles_kernel(const unsigned* __restrict__ cost, unsigned* __restrict__ order, int n) {
+    __shared__ unsigned shMax, hist[256], cursor[256];
+    const int tid = threadIdx.x;
+    if (tid == 0) shMax = 1u;
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    unsigned m = 1u;
+    for (int i = tid; i < n; i += blockDim.x) m = max(m, __ldg(cost + i));
+    m = __reduce_max_sync(kFull, m);
+    if ((tid & 31) == 0) atomicMax(&shMax, m);
+    __syncthreads();
+    const unsigned long long mx = shMax;
+    auto bucket = [&](unsigned c) { return 255u - (unsigned)(((unsigned long long)c * 255ull) / mx); };  // 0 = most expensive
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[bucket(__ldg(cost + i))], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned acc = 0u;
+        for (int b = 0; b < 256; ++b) {
+            cursor[b] = acc;
+            acc += hist[b];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) order[atomicAdd(&cursor[bucket(__ldg(cost + i))], 1u)] = (unsigned)i;
 }
 
 }  // namespace rm

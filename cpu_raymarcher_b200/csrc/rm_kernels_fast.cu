@@ -4,4 +4,9 @@
 namespace rm {
 int launch_render_fast(const RenderParams& p, int n_sms, void* stream) { return launch_render_t<NumFast>(p, n_sms, stream); }
 int launch_shade_fast(const ShadeParams& p, void* stream) { return launch_shade_t<NumFast>(p, stream); }
+int launch_order_tiles(const unsigned int* cost, unsigned int* order, int n_tiles, void* stream) {
+    if (n_tiles <= 0) return 0;
+    order_tiles_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(cost, order, n_tiles);
+    return (int)cudaGetLastError();
+}
 }  // namespace rm

@@ -200,6 +200,7 @@ int clone_scene(rm_ctx* dst, const rm_ctx* src) {
         return RM_ERR_CUDA;
     }
     dst->scene = ds;
+    dst->order_valid = false;
     dst->tree = src->tree;
     dst->d_anim = const_cast<float*>(ds.anim);
     dst->anim_time = src->anim_time;

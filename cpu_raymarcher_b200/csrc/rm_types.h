@@ -144,6 +144,9 @@ struct RenderParams {
     int32_t shader, shader2;
     int32_t length_sqrt;  // validation: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot
     int32_t n_tiles, tiles_x;
+    // cost-ordered tile queue (both optional): tile_order[t] = tile handed out with ticket t; tile_cost[tile] = cycles it took
+    const unsigned int* tile_order;
+    unsigned int* tile_cost;
     int32_t vec_store;  // width % 8 == 0 and every output plane 16-byte aligned: whole tiles are written with vector stores
     int32_t stripe_rows, stripe_count, stripe_index, tiles_per_stripe;  // row-stripe interleave (multi-GPU)
     // outputs (device pointers; optional ones may be null)
@@ -180,5 +183,6 @@ int launch_render_fast(const RenderParams& p, int n_sms, void* stream);
 int launch_shade_val(const ShadeParams& p, void* stream);
 int launch_shade_fast(const ShadeParams& p, void* stream);
 int probe_fp32_peak(int n_sms, void* stream, float* scratch, double* tflops);
+int launch_order_tiles(const unsigned int* cost, unsigned int* order, int n_tiles, void* stream);  // rm_kernels_fast.cu
 
 }  // namespace rm

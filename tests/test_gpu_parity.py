@@ -817,3 +817,37 @@ def test_empty_scene(oracle, accel):
             ctx.close()
             assert np.array_equal(f.sdfEval, ref.sdfEval) and np.array_equal(f.iters, ref.iters), (accel, alg, val)
             assert np.array_equal(f.depth, ref.depth) and np.array_equal(f.normal, ref.normal), (accel, alg, val)
+
+
+def test_cost_ordered_tile_queue_does_not_change_the_frame(monkeypatch):
+    """From the second frame of a geometry on, tiles are handed out most-expensive-first by the previous frame's per-tile cost
+    (rm_api.cu, order_tiles_kernel).  The image must not depend on the schedule: frames 1-3 (identity order, then ordered by
+    frame 1's and frame 2's costs), a frame with a moved camera rendered under the stale order, and RM_TILE_ORDER=0 are all
+    compared plane by plane; the order array itself must be a permutation (every pixel written exactly once is implied by the
+    equality of every plane and of the diagnostics)."""
+    import cpu_raymarcher_b200 as rb
+    from cpu_raymarcher_b200 import scene_manager as sm
+    from cpu_raymarcher_b200.camera import Camera
+    t, m, q = sm.synthetic_spheres(10000).arrays()
+    W, H = 1920, 1080
+    cam = Camera()
+    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap")
+    cam.set_angles(0.1, 0.3)
+    rq2 = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap")
+    ctx = rb.Context(0)
+    ctx.upload_scene(t, m, q, "BVH")
+    frames = [ctx.render(rq) for _ in range(3)]
+    st = ctx.stats()
+    assert st["n_launches"] == 2  # render kernel + the one-CTA ordering kernel
+    moved = ctx.render(rq2)  # ordered by the costs of the OTHER camera's frame
+    ctx.close()
+    monkeypatch.setenv("RM_TILE_ORDER", "0")
+    ctx = rb.Context(0)
+    ctx.upload_scene(t, m, q, "BVH")
+    plain, plain_moved = ctx.render(rq), ctx.render(rq2)
+    assert ctx.stats()["n_launches"] == 1
+    ctx.close()
+    for k in ("depth", "normal", "sdfEval", "iters", "rgba"):
+        for f in frames:
+            assert np.array_equal(getattr(f, k), getattr(plain, k)), k
+        assert np.array_equal(getattr(moved, k), getattr(plain_moved, k)), k

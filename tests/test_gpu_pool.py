@@ -59,7 +59,8 @@ def test_pool_frame_equals_single_context_frame(validate):
                 st = pool.stats()
                 for k in STAT_KEYS:
                     assert st[k] == rs[k], (devices, j, k, st[k], rs[k])
-                assert st["n_devices"] == len(devices) and st["n_launches"] == len(devices)
+                # one render kernel per device (+ the one-CTA tile-ordering kernel after it on frames of >= 8192 tiles per device)
+                assert st["n_devices"] == len(devices) and st["n_launches"] in (len(devices), 2 * len(devices))
                 shares = [pool.device_stats(i) for i in range(len(devices))]
                 assert sum(s["n_pixels"] for s in shares) == j["W"] * j["H"]
                 assert abs(max(s["kernel_ms"] for s in shares) - st["kernel_ms"]) < 1e-9
