@@ -2,6 +2,7 @@
 // Included with RM_NUM (numeric policy) and RM_SUFFIX (val / fast) defined.
 #pragma once
 #include <algorithm>
+#include <mutex>
 
 #include "rm_device.cuh"
 
@@ -13,22 +14,33 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     constexpr int kWarps = CtaShape<NP, ACCEL, PK>::kWarps;
     constexpr int kThreads = 32 * kWarps;
     constexpr size_t kDynSmem = (size_t)kWarps * 2 * kStageBytes;  // per-warp double-buffered TMA stages
-    static int blocksPerSM = 0;  // per instantiation
-    if (blocksPerSM == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+    // per instantiation; function attributes are PER DEVICE, and several devices launch from several host threads (rm_pool)
+    static std::mutex mu;
+    static int blocksPerSM = 0;
+    static unsigned long long devDone = 0ull;
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return (int)e;
-        int b = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, kDynSmem);
-        if (e != cudaSuccess) return (int)e;
-        blocksPerSM = std::max(b, 1);
-        // the tensor-core search allocates all 512 TMEM columns of the SM: exactly one (16-warp) CTA per SM
-        if (!NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE) blocksPerSM = 1;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!((devDone >> (dev & 63)) & 1ull)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+            if (e != cudaSuccess) return (int)e;
+            int b = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, kDynSmem);
+            if (e != cudaSuccess) return (int)e;
+            blocksPerSM = std::max(b, 1);
+            // the tensor-core search allocates all 512 TMEM columns of the SM: exactly one (16-warp) CTA per SM
+            if (!NP::kExact && ACCEL == RM_ACCEL_BVH && PK == PK_TSPHERE) blocksPerSM = 1;
+            devDone |= 1ull << (dev & 63);
+        }
     }
     // persistent grid: a multiple of the SM count, never more warps than there are tiles
     long long warpsWanted = p.n_tiles;
     int maxBlocks = n_sms * blocksPerSM;
     int blocks = (int)std::min<long long>(maxBlocks, (warpsWanted + kWarps - 1) / kWarps);
     if (blocks < 1) blocks = 1;
+    (void)cudaGetLastError();  // a stale error of an unrelated earlier call on this thread must not be blamed on this launch
     kern<<<blocks, kThreads, kDynSmem, stream>>>(p);
     return (int)cudaGetLastError();
 }

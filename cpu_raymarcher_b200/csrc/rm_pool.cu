@@ -326,12 +326,7 @@ void rm_pool_destroy(rm_pool* p) {
         if (t->th.joinable()) t->th.join();
         delete t;
     }
-    for (size_t i = 0; i < p->ctx.size(); ++i) {
-        if (i < p->scratch.size() && p->scratch[i]) {
-            cudaSetDevice(p->ctx[i]->device);
-            cudaFree(p->scratch[i]);
-        }
-    }
+    // (the per-device scratch planes were allocated with rm_alloc: their contexts free them in rm_destroy below)
     if (!p->ctx.empty()) cudaSetDevice(p->ctx[0]->device);
     if (p->cache) cudaFreeHost(p->cache);
     for (auto& h : p->host_allocs) cudaFreeHost(h.first);
