@@ -76,7 +76,7 @@ class Stats(C.Structure):
                 ("n_hit", C.c_uint64), ("operator_flops", C.c_double), ("algorithmic_flops", C.c_double), ("kernel_ms", C.c_double), ("wall_ms", C.c_double), ("n_launches", C.c_int32),
                 ("device", C.c_int32), ("tc_passes", C.c_uint64), ("tc_requests", C.c_uint64), ("tc_items", C.c_uint64),
                 ("executed_flops", C.c_double), ("fp32_pipe_flops", C.c_double), ("tensor_flops", C.c_double),
-                ("n_devices", C.c_int32), ("pad_", C.c_int32)]
+                ("n_devices", C.c_int32), ("pad_", C.c_int32), ("drain_ms", C.c_double), ("tail_ms", C.c_double)]
 
 
 # every symbol include/rm.h declares

@@ -211,7 +211,11 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     // Operator trees always run the exact (fp64, unfused) kernels: B200 has full-rate-class fp64 and these scenes
     // are a handful of primitives, so there is no reduced-precision variant to disagree with the reference.  A
     // context created without RM_F_VALIDATE_FP64 only swaps V8's compensated hypot for a plain sqrt.
-    if (tree && !(c->flags & RM_F_VALIDATE_FP64)) P.length_sqrt = 1;
+    if (tree && !(c->flags & RM_F_VALIDATE_FP64)) {
+        P.length_sqrt = 1;
+        const char* e = std::getenv("RM_FAST_OBJECTS");  // RM_FAST_OBJECTS=0: measurement knob (fp64 object evaluators everywhere)
+        P.fast_objects = (e && e[0] == '0') ? 0 : 1;
+    }
     if (tree && !c->tree.anims.empty() && (!c->anim_valid || c->anim_time != rq->time)) {
         // Scene.updateTime (raymarcher.ts:59): AnimatedTranslate's offset vector is a per-job constant
         std::vector<float> off;
@@ -260,8 +264,10 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     // cost-ordered queue: hand the tiles out most-expensive-first, by what each tile cost in the previous frame of this geometry
     // (only where tile costs are heavy-tailed: the cooperative-queue kernels of big BVH scenes.  On cheap, uniform frames the
     // reordering loses more in locality than the shorter tail gains: cfg1 +4 %, cfg5 +2 %, profiles/r02g_ab.jsonl)
+    // Measured on cfg4 (profiles/r02k_stripe_time.log): the 1/2, 1/4, 1/8 stripe shares of a multi-GPU frame gain 3-5 %, the whole
+    // frame on one GPU loses 2 % (29.0 -> 29.7 ms): the order is used for striped requests only.
     const bool ordered = P.n_tiles >= kTileOrderMinTiles && tile_order_enabled() && !(c->flags & RM_F_VALIDATE_FP64) && !tree &&
-                         c->scene.accel_kind == RM_ACCEL_BVH && c->scene.n_prims >= 256;
+                         c->scene.accel_kind == RM_ACCEL_BVH && c->scene.n_prims >= 256 && rq->stripe_count > 1;
     if (ordered) {
         const int key[8] = {rq->width, rq->height, rq->y_start, bandH, P.stripe_rows, P.stripe_count, P.stripe_index, P.n_tiles};
         const size_t bytes = (size_t)P.n_tiles * sizeof(unsigned int);
@@ -288,6 +294,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     DevStats init{};
     init.min_sdf = 0xffffffffu;
     init.min_iters = 0xffffffffu;
+    init.t_enter_min = init.t_drain_min = init.t_exit_min = ~0ull;
     *c->h_stats = init;
     CU(c, cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(DevStats), cudaMemcpyHostToDevice, stream));
     int launches = 0;
@@ -367,6 +374,11 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     }
     L.executed_flops = L.fp32_pipe_flops + L.tensor_flops;
     L.n_devices = 1;
+    if (s.t_exit_max && s.t_enter_min != ~0ull && s.t_drain_min != ~0ull) {
+        // frame anatomy: first CTA in -> first warp finds the tile queue empty (steady state) -> last warp out (tail)
+        L.drain_ms = (double)(s.t_drain_min - s.t_enter_min) * 1e-6;
+        L.tail_ms = (double)(s.t_exit_max - s.t_drain_min) * 1e-6;
+    }
     L.kernel_ms = ms;
     L.n_launches = launches;
     L.device = c->device;

@@ -56,6 +56,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RM_VEC_EPILOGUE
 #define RM_VEC_EPILOGUE 0  // 1: retired pixels are held in registers and written per whole tile with 16-byte vector stores (shuffle transpose).  Parity-green (profiles/r02c_gpu_tests_vec_epilogue.log) but SLOWER on every config (cfg4 +2 %, cfg5 +14 %, profiles/r02c_ab.jsonl): the scalar stores at retirement are fire-and-forget, the tile write sits on the refill path.  Default 0.
 #endif
+#ifndef RM_RESIDENT_B
+#define RM_RESIDENT_B 1  // cluster-screen B tiles resident in shared memory when they fit the ring (0: always streamed; A/B switch)
+#endif
 #ifndef RM_SMEM_STATS
 #define RM_SMEM_STATS 1  // diagnostics accumulators per warp in shared memory (0: per-lane registers; A/B switch)
 #endif
@@ -231,6 +234,131 @@ RM_DEV double prim_sdf_exact(const DevScene& sc, int j, double x, double y, doub
     return leaf_sdf_exact(sc, j, x, y, z, length_sqrt);
 }
 
+// ---- fp32 evaluators of scene objects (operator trees, Mandelbulb) for default contexts (round 2) --------------------------
+// The exact kernels serve these scenes in every context; without RM_F_VALIDATE_FP64 the MARCH-STEP queries evaluate the object
+// programs in fp32 (same stack machine, float arithmetic, CUDA's single-precision libm) while the four normal taps — whose
+// differences of nearly equal distances set the normal bytes — and any query that lands within 2e-5 of the hit threshold are
+// evaluated exactly.  Bar: >= 99.9 % of pixels agree (hit mask, RGB within 1/255, depth rel. err <= 1e-4).
+RM_DEV float leaf_sdf_f32(const DevScene& sc, int j, float x, float y, float z, float time_scale) {
+    const float* m = sc.w2l + 16 * (size_t)j;
+    float w = fmaf(m[3], x, fmaf(m[7], y, fmaf(m[11], z, m[15])));
+    if (w == 0.f || w != w) w = 1.f;
+    const float iw = 1.f / w;
+    const float lx = fmaf(m[0], x, fmaf(m[4], y, fmaf(m[8], z, m[12]))) * iw;
+    const float ly = fmaf(m[1], x, fmaf(m[5], y, fmaf(m[9], z, m[13]))) * iw;
+    const float lz = fmaf(m[2], x, fmaf(m[6], y, fmaf(m[10], z, m[14]))) * iw;
+    const double* prm = sc.params + 4 * (size_t)j;
+    const int type = sc.type[j];
+    if (type == RM_PRIM_SPHERE) {
+        return sqrtf(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - (float)prm[0];
+    } else if (type == RM_PRIM_BOX) {
+        const float q0 = fabsf(lx) - (float)prm[0], q1 = fabsf(ly) - (float)prm[1], q2 = fabsf(lz) - (float)prm[2];
+        const float o0 = fmaxf(q0, 0.f), o1 = fmaxf(q1, 0.f), o2 = fmaxf(q2, 0.f);
+        return sqrtf(fmaf(o0, o0, fmaf(o1, o1, o2 * o2))) + fminf(fmaxf(q0, fmaxf(q1, q2)), 0.f);
+    } else if (type == RM_PRIM_MANDELBULB) {  // mandelbulb.ts:38-78 in float
+        const float px = lx, py = lz, pz = ly;
+        float zx = px, zy = py, zz = pz, dr = 1.f, r = 0.f;
+        const float power = (float)prm[0], dphi = (prm[2] != 0.0) ? (float)((sc.time * (double)time_scale) * prm[3]) : 0.f;
+        const int iterations = (int)prm[1];
+        for (int i = 0; i < iterations; ++i) {
+            r = sqrtf(fmaf(zx, zx, fmaf(zy, zy, zz * zz)));
+            if (r > 2.f) break;
+            float theta = atan2f(zy, zx), phi = asinf(zz / r) + dphi;
+            const float rp1 = powf(r, power - 1.f);
+            dr = fmaf(rp1 * dr, power, 1.f);
+            r = rp1 * r;  // r^power: what the return reads after the last pass
+            theta *= power;
+            phi *= power;
+            float st, ct, sp, cp;
+            sincosf(theta, &st, &ct);
+            sincosf(phi, &sp, &cp);
+            zx = fmaf(r * ct, cp, px);
+            zy = fmaf(r * st, cp, py);
+            zz = fmaf(r, sp, pz);
+        }
+        return 0.5f * logf(r) * r / dr;
+    } else {
+        const float qx = sqrtf(fmaf(lx, lx, lz * lz)) - (float)prm[0];
+        return sqrtf(fmaf(qx, qx, ly * ly)) - (float)prm[1];
+    }
+}
+
+static __device__ __noinline__ float object_sdf_f32(const DevScene& sc, int j, float x, float y, float z) {
+    float px[kMaxPointStack], py[kMaxPointStack], pz[kMaxPointStack];
+    float ds[kMaxDistStack];
+    int sp = 0, dp = 0;
+    px[0] = x;
+    py[0] = y;
+    pz[0] = z;
+    ds[0] = 10.f;
+    const int end = sc.obj_first[j + 1];
+    for (int pc = sc.obj_first[j]; pc < end; ++pc) {
+        const DevInstr in = sc.instrs[pc];
+        const float X = px[sp], Y = py[sp], Z = pz[sp];
+        switch (in.op) {
+            case I_PRIM: ds[dp++] = leaf_sdf_f32(sc, in.a, X, Y, Z, (float)in.c); break;
+            case I_XFORM: {
+                const float* m = sc.mats + 16 * (size_t)in.a;
+                float w = fmaf(m[3], X, fmaf(m[7], Y, fmaf(m[11], Z, m[15])));
+                if (w == 0.f || w != w) w = 1.f;
+                const float iw = 1.f / w;
+                ++sp;
+                px[sp] = fmaf(m[0], X, fmaf(m[4], Y, fmaf(m[8], Z, m[12]))) * iw;
+                py[sp] = fmaf(m[1], X, fmaf(m[5], Y, fmaf(m[9], Z, m[13]))) * iw;
+                pz[sp] = fmaf(m[2], X, fmaf(m[6], Y, fmaf(m[10], Z, m[14]))) * iw;
+                break;
+            }
+            case I_POP: sp -= in.a; break;
+            case I_TWIST: {
+                float sn, c;
+                sincosf((float)in.c * Y, &sn, &c);
+                ++sp;
+                px[sp] = c * X - sn * Z;
+                py[sp] = Y;
+                pz[sp] = sn * X + c * Z;
+                break;
+            }
+            case I_REPEAT: {  // Math.round: ties toward +Infinity
+                const float s0 = in.v[0], s1 = in.v[1], s2 = in.v[2];
+                ++sp;
+                px[sp] = X - s0 * floorf(X / s0 + 0.5f);
+                py[sp] = Y - s1 * floorf(Y / s1 + 0.5f);
+                pz[sp] = Z - s2 * floorf(Z / s2 + 0.5f);
+                break;
+            }
+            case I_SUBV: {
+                const float* o = sc.anim + 4 * (size_t)in.a;
+                ++sp;
+                px[sp] = X - o[0];
+                py[sp] = Y - o[1];
+                pz[sp] = Z - o[2];
+                break;
+            }
+            case I_SUBC: ds[dp - 1] = ds[dp - 1] - (float)in.c; break;
+            case I_SUNION: {
+                const float d1 = ds[dp - 2], d2 = ds[dp - 1], k = (float)in.c * 4.f;
+                const float h = fmaxf(k - fabsf(d1 - d2), 0.f);
+                ds[dp - 2] = fminf(d1, d2) - h * h * 0.25f / k;
+                --dp;
+                break;
+            }
+            default: {  // I_SSUB
+                const float d1 = ds[dp - 2], d2 = ds[dp - 1], k = (float)in.c * 4.f;
+                const float h = fmaxf(k - fabsf(d1 + d2), 0.f);
+                ds[dp - 2] = fmaxf(d1, -d2) + h * h * 0.25f / k;
+                --dp;
+                break;
+            }
+        }
+    }
+    return ds[0];
+}
+// Scene object j in fp32: a primitive, or an operator tree over primitives.
+RM_DEV float prim_sdf_f32_object(const DevScene& sc, int j, float x, float y, float z) {
+    if (sc.n_instrs > 0) return object_sdf_f32(sc, j, x, y, z);
+    return leaf_sdf_f32(sc, j, x, y, z, 1.f);
+}
+
 // Fast model, general affine record: rows of the 3x4 world->local + (p0,p1,p2,type).
 RM_DEV float prim_sdf_fast_general(const float4* __restrict__ rec, int j, float x, float y, float z, int& type) {
     const float4 r0 = __ldg(rec + 4 * (size_t)j + 0);
@@ -270,6 +398,8 @@ struct EvalExtra {};
 template <>
 struct EvalExtra<true> {
     unsigned nTorus, opFlops;
+    bool fastq;       // this query is evaluated by the fp32 object evaluators (default contexts, march steps)
+    bool forceExact;  // ... unless its fp32 result landed next to the hit threshold: the same query is repeated exactly
 };
 
 // One scene-object evaluation at the f32 sample point q; r.nSphere / r.nBox (/ r.ex) count primitive evaluations by type.
@@ -290,6 +420,7 @@ RM_DEV typename NP::F prim_sdf(const RenderParams& P, int j, const float q[3], R
             nBox += (type == RM_PRIM_BOX);
             r.ex.nTorus += (type == RM_PRIM_TORUS);
         }
+        if (r.ex.fastq) return (double)prim_sdf_f32_object(P.scene, j, q[0], q[1], q[2]);
         return prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt);
     } else if constexpr (PK == PK_TSPHERE) {
         nSphere += 1;
@@ -338,6 +469,11 @@ constexpr int kWarpsPerCtaMax = 16;  // fast BVH kernels: 16 warps per CTA for t
                                      // 8 for general primitives (64-request batches, 2 per lane); all other kernels 4
 constexpr int kChunk = 32;         // argmin granularity of the fp32 search
 
+RM_DEV unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 RM_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 RM_DEV void mbar_init(uint32_t bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -792,15 +928,20 @@ static __device__ __noinline__ void tc_pass(const RenderParams& P, TcCtx& tcRef,
     const char* tiles = reinterpret_cast<const char*>(P.scene.tc_tiles);
     const float2* __restrict__ bound = P.scene.cl_bound;
     unsigned gBase = tc.g;  // global block counter at the start of the current sweep (fixes all mbarrier parities)
+    // Scenes of <= kTcStages cluster blocks (128 x 128 x 8 = 131 072 spheres): every B tile has its own stage, loaded once at
+    // kernel start and resident for the whole frame — a pass then starts its sweeps without a TMA round trip (~2.5 us under load,
+    // twice per pass).  Bigger scenes stream the tiles through the ring as before.
+    const bool resB = RM_RESIDENT_B && nB <= kTcStages;
     auto tma = [&](int b) {  // B tile b -> its ring stage
+        if (resB) return;
         const unsigned sidx = (gBase + (unsigned)b) % kTcStages;
         mbar_expect_tx(tc.barFull + 8u * sidx, kTcTileBytes);
         bulk_g2s(tc.sB + sidx * kTcTileBytes, tiles + (size_t)b * kTcTileBytes, kTcTileBytes, tc.barFull + 8u * sidx);
     };
     auto mma = [&](int b) {  // S[128 x 128] of block b -> the accumulator buffer of its group
-        const unsigned g = gBase + (unsigned)b, sidx = g % kTcStages;
+        const unsigned g = gBase + (unsigned)b, sidx = resB ? (unsigned)b : g % kTcStages;
         // (the accumulator buffer is free: the caller is the last of the group's warps to have drained block g - 4)
-        mbar_wait(tc.barFull + 8u * sidx, (g / kTcStages) & 1u);
+        if (!resB) mbar_wait(tc.barFull + 8u * sidx, (g / kTcStages) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tc.tmem + (g % kTcGroups) * (uint32_t)kTcBlock;
         const uint64_t db = umma_desc(tc.sB + sidx * kTcTileBytes);
@@ -1146,13 +1287,20 @@ RM_DEV double finish_search(const RenderParams& P, const float q[3], int code) {
 //                32-primitive chunk (FMNMX); the winner is re-scanned once for its index and that ONE
 //                primitive is evaluated in fp64.
 template <class NP, int PK>
-RM_DEV double scene_all_prims(const RenderParams& P, const float q[3], WarpStage& ws, bool active, int lane) {
+RM_DEV double scene_all_prims(const RenderParams& P, const float q[3], WarpStage& ws, bool active, int lane, bool fastq = false) {
     if constexpr (NP::kExact) {
         const int n = P.scene.n_prims;
         double closest = 10.0;
-        if (active)
-            for (int j = 0; j < n; ++j)
-                closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
+        if (active) {
+            if (fastq) {  // default contexts, march steps: fp32 object evaluators
+                float cf = 10.f;
+                for (int j = 0; j < n; ++j) cf = fminf(cf, prim_sdf_f32_object(P.scene, j, q[0], q[1], q[2]));
+                closest = (double)cf;
+            } else {
+                for (int j = 0; j < n; ++j)
+                    closest = jsmin(prim_sdf_exact(P.scene, j, (double)q[0], (double)q[1], (double)q[2], P.length_sqrt), closest);
+            }
+        }
         return closest;
     } else {
         float best;
@@ -1835,9 +1983,20 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             __syncthreads();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tc.tmem = *(volatile uint32_t*)&shTmemBase;
+            if (RM_RESIDENT_B && P.scene.n_tc_blocks <= kTcStages) {  // resident B tiles (see tc_pass): one TMA bulk copy per block, once
+                if (threadIdx.x == 0) {
+                    for (int b = 0; b < P.scene.n_tc_blocks; ++b) {
+                        mbar_expect_tx(tc.barFull + 8u * (unsigned)b, kTcTileBytes);
+                        bulk_g2s(tc.sB + (unsigned)b * kTcTileBytes, reinterpret_cast<const char*>(P.scene.tc_tiles) + (size_t)b * kTcTileBytes, kTcTileBytes,
+                                 tc.barFull + 8u * (unsigned)b);
+                    }
+                }
+                for (int b = 0; b < P.scene.n_tc_blocks; ++b) mbar_wait(tc.barFull + 8u * (unsigned)b, 0u);
+            }
         }
     }
 
+    if (threadIdx.x == 0) atomicMin(&P.stats->t_enter_min, globaltimer_ns());
     // warp-uniform work-queue cursor
     int tile = -1, tilePos = kTileW * kTileH;
     unsigned tileT0 = 0u;  // clock() at the fetch of the current tile (cost-ordered queue)
@@ -2088,6 +2247,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 t = __shfl_sync(kFull, t, 0);
                 if ((int)t >= P.n_tiles) {
                     queueEmpty = true;
+                    if (lane == 0) atomicMin(&P.stats->t_drain_min, globaltimer_ns());
                     break;
                 }
                 // cost-ordered queue: ticket t -> the t-th most expensive tile of the previous frame of this geometry (so the frame ends
@@ -2147,6 +2307,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             if constexpr (NP::kExact) {
                 r.ex.nTorus = 0;
                 r.ex.opFlops = 0;
+                r.ex.forceExact = false;
             }
             r.i = 0;
             r.done = false;
@@ -2233,6 +2394,14 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
 
         // ---- (d) resolve the pending scene-distance query (scene.ts:144-190) ----
         const bool waiting = (r.phase >= PH_WAIT_MARCH && r.phase <= PH_WAIT_N3);
+        unsigned svSphere = 0u, svBox = 0u, svTorus = 0u, svOp = 0u;  // exact kernels: counters before this query (fp32 object mode may repeat it)
+        if constexpr (NP::kExact) {
+            r.ex.fastq = P.fast_objects != 0 && !r.ex.forceExact && (r.phase == PH_WAIT_MARCH || r.phase == PH_WAIT_V3B);
+            svSphere = r.nSphere;
+            svBox = r.nBox;
+            svTorus = r.ex.nTorus;
+            svOp = r.ex.opFlops;
+        }
         double dd = 10.0;      // the query result handed to the control logic
         float distF = 10.f;    // fast model: running fp32 min over the candidate primitives
         int argmin = -1;       // fast model: its primitive
@@ -2345,7 +2514,9 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
             // small scenes / no acceleration structure: the warp serves its own lanes right away
             const unsigned need = __ballot_sync(kFull, needAll);
             if (need) {
-                double v = scene_all_prims<NP, PK>(P, r.q, ws, needAll, lane);
+                bool fq = false;
+                if constexpr (NP::kExact) fq = r.ex.fastq;
+                double v = scene_all_prims<NP, PK>(P, r.q, ws, needAll, lane, fq);
                 if (needAll) {
                     dd = v;
                     cnt = (unsigned)P.scene.n_prims;
@@ -2390,7 +2561,22 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
 
         // ---- (e) consume the query result ----
-        if (waiting && !r.pending) {
+        bool repeatExact = false;
+        if constexpr (NP::kExact) {
+            // fp32 object mode: a distance within 2e-5 of the hit threshold decides nothing — the same query runs again, exactly,
+            // in the next trip through the loop (its evaluations are not counted twice)
+            if (waiting && r.ex.fastq && fabs(dd - EPSILON) < 2.0e-5) {
+                repeatExact = true;
+                r.ex.forceExact = true;
+                r.nSphere = svSphere;
+                r.nBox = svBox;
+                r.ex.nTorus = svTorus;
+                r.ex.opFlops = svOp;
+            } else if (waiting) {
+                r.ex.forceExact = false;
+            }
+        }
+        if (waiting && !r.pending && !repeatExact) {
             r.sdf += cnt;
             switch (r.phase) {
                 case PH_WAIT_MARCH: {
@@ -2647,6 +2833,11 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         if (heldM) flush_held(heldM);
     }
     if (P.tile_cost && tile >= 0 && lane == 0) P.tile_cost[tile] = (unsigned)clock() - tileT0;  // the warp's last tile
+    if (lane == 0) {  // frame anatomy (rm_stats: ramp / drain / tail): a handful of atomics per warp per frame
+        const unsigned long long now = globaltimer_ns();
+        atomicMin(&P.stats->t_exit_min, now);
+        atomicMax(&P.stats->t_exit_max, now);
+    }
     publish_bands();  // pixels finalised since the warp's last tile fetch
     // ---- epilogue: diagnostics (main.ts:527-548) — warp reduce, one atomic set per warp ----
     unsigned long long s0, s1, s2, s3, s4, s5, s6, s7, s8 = 0;

@@ -24,7 +24,7 @@ using namespace rm;
 
 namespace {
 thread_local std::string g_pool_create_error;
-constexpr int kPoolStripeRows = 8;  // rows per interleaved stripe (a multiple of the 4-row tile)
+constexpr int kPoolStripeRows = 8;  // rows per interleaved stripe (a multiple of the 4-row tile); 4-row stripes measured 2 % slower (profiles/r02k_stripe_time.log)
 
 // One persistent host thread per device: CUDA calls for device i are always issued from thread i.
 struct DeviceThread {
@@ -160,7 +160,11 @@ void reduce_stats(const std::vector<rm_stats_t>& d, rm_stats_t& out) {
         out.min_sdf = std::min(out.min_sdf, s.min_sdf);
         out.max_iters = std::max(out.max_iters, s.max_iters);
         out.min_iters = std::min(out.min_iters, s.min_iters);
-        out.kernel_ms = std::max(out.kernel_ms, s.kernel_ms);  // the devices run concurrently: the slowest one is the frame
+        if (s.kernel_ms >= out.kernel_ms) {  // the devices run concurrently: the slowest one is the frame
+            out.kernel_ms = s.kernel_ms;
+            out.drain_ms = s.drain_ms;
+            out.tail_ms = s.tail_ms;
+        }
     }
     out.device = -1;
     out.n_devices = (int32_t)d.size();

@@ -130,6 +130,7 @@ struct DevStats {
     unsigned long long t_total, t_search, t_barrier, t_stuck;  // RM_PHASE_TIMING builds: warp-cycles by phase
     unsigned long long n_pass, n_req, n_rearm, t_tc[4];        // RM_PHASE_TIMING builds: cooperative passes, requests served, buffer re-arms and
                                                                // tc_pass cycles by step as seen by thread 0
+    unsigned long long t_enter_min, t_drain_min, t_exit_min, t_exit_max;  // globaltimer ns: first CTA in, first empty-queue ticket, first / last warp out
     unsigned int band_done[kMaxBands];  // rm_render with page-locked planes: pixels finalised per row band (early D2H)
     unsigned int pad_;
 };
@@ -143,6 +144,7 @@ struct RenderParams {
     double step_size, overshoot;
     int32_t shader, shader2;
     int32_t length_sqrt;  // validation: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot
+    int32_t fast_objects;  // exact kernels in a default context (operator trees / Mandelbulb): march-step queries in fp32
     int32_t n_tiles, tiles_x;
     // cost-ordered tile queue (both optional): tile_order[t] = tile handed out with ticket t; tile_cost[tile] = cycles it took
     const unsigned int* tile_order;

@@ -35,7 +35,7 @@ import numpy as np
 from . import _lib
 from .renderer import Context
 
-STRIPE_ROWS = 8
+STRIPE_ROWS = 8  # measured against 4-row stripes on the 1/8 share of cfg4: 8 rows 0.774, 4 rows 0.756 (profiles/r02k_stripe_time.log)
 
 
 def stripe_rows_of(rank: int, world: int, height: int, stripe_rows: int = STRIPE_ROWS):

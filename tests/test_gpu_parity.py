@@ -831,9 +831,10 @@ def test_cost_ordered_tile_queue_does_not_change_the_frame(monkeypatch):
     t, m, q = sm.synthetic_spheres(10000).arrays()
     W, H = 1920, 1080
     cam = Camera()
-    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap")
+    # (the order is used for striped requests — the shares of a multi-GPU frame; here: GPU 0 of 2)
+    rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap", stripes=(8, 2, 0))
     cam.set_angles(0.1, 0.3)
-    rq2 = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap")
+    rq2 = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap", stripes=(8, 2, 0))
     ctx = rb.Context(0)
     ctx.upload_scene(t, m, q, "BVH")
     frames = [ctx.render(rq) for _ in range(3)]
@@ -851,3 +852,6 @@ def test_cost_ordered_tile_queue_does_not_change_the_frame(monkeypatch):
         for f in frames:
             assert np.array_equal(getattr(f, k), getattr(plain, k)), k
         assert np.array_equal(getattr(moved, k), getattr(plain_moved, k)), k
+    assert int(plain.iters.astype(np.int64).sum()) > 0
+    # and the frame-anatomy timers of rm_stats are filled
+    assert st["drain_ms"] > 0 and st["tail_ms"] >= 0 and st["drain_ms"] + st["tail_ms"] <= st["kernel_ms"] * 1.05 + 0.05
