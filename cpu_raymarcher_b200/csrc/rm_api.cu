@@ -156,6 +156,11 @@ bool tile_order_enabled() {  // RM_TILE_ORDER=0: measurement knob (identity queu
     const char* e = std::getenv("RM_TILE_ORDER");
     return !(e && e[0] == '0');
 }
+bool tile_order_forced() {  // RM_TILE_ORDER=2: measurement knob (ordered queue for unstriped requests too)
+    const char* e = std::getenv("RM_TILE_ORDER");
+    return e && e[0] == '2';
+}
+constexpr int kTailTriggerWarps = 4;  // end of the frame: a cooperative pass as soon as this many warps are parked (RM_TAIL_TRIGGER overrides)
 constexpr int kTileOrderMinTiles = 8192;  // smaller frames finish in a handful of tile rounds: nothing to order
 
 bool is_translation_sphere(uint8_t type, const float* m) {
@@ -206,6 +211,10 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.shader = rq->shader;
     P.shader2 = rq->shader_analytics;
     P.length_sqrt = (c->flags & RM_F_LENGTH_SQRT) ? 1 : 0;
+    {
+        const char* e = std::getenv("RM_TAIL_TRIGGER");  // measurement knob, read per call
+        P.tail_trigger = e ? std::max(1, std::atoi(e)) : kTailTriggerWarps;
+    }
     const bool tree = c->exact_only;
     P.scene.time = rq->time;
     // Operator trees always run the exact (fp64, unfused) kernels: B200 has full-rate-class fp64 and these scenes
@@ -267,7 +276,7 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     // Measured on cfg4 (profiles/r02k_stripe_time.log): the 1/2, 1/4, 1/8 stripe shares of a multi-GPU frame gain 3-5 %, the whole
     // frame on one GPU loses 2 % (29.0 -> 29.7 ms): the order is used for striped requests only.
     const bool ordered = P.n_tiles >= kTileOrderMinTiles && tile_order_enabled() && !(c->flags & RM_F_VALIDATE_FP64) && !tree &&
-                         c->scene.accel_kind == RM_ACCEL_BVH && c->scene.n_prims >= 256 && rq->stripe_count > 1;
+                         c->scene.accel_kind == RM_ACCEL_BVH && c->scene.n_prims >= 256 && (rq->stripe_count > 1 || tile_order_forced());
     if (ordered) {
         const int key[8] = {rq->width, rq->height, rq->y_start, bandH, P.stripe_rows, P.stripe_count, P.stripe_index, P.n_tiles};
         const size_t bytes = (size_t)P.n_tiles * sizeof(unsigned int);

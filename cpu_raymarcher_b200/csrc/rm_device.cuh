@@ -2801,8 +2801,11 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 if (finishedNow != wasFinished) atomicAdd(&shFinished, finishedNow ? 1u : 0xffffffffu);
                 if (stuckNow != wasStuck) {
                     const unsigned prev = atomicAdd(&shStuck, stuckNow ? 1u : 0xffffffffu);
-                    // last warp to get stuck: nobody can progress any more -> serve whatever is queued
-                    if (stuckNow && prev + 1u == (unsigned)kWarpsPerCta) {
+                    // last warp to get stuck: nobody can progress any more -> serve whatever is queued.  End of the frame (this
+                    // warp's tile queue is empty): the SM is no longer throughput-bound, the rays still in flight are a chain of
+                    // dependent passes — serve the queue as soon as P.tail_trigger warps are parked instead of all of them.
+                    const unsigned needStuck = queueEmpty ? min((unsigned)kWarpsPerCta, (unsigned)P.tail_trigger) : (unsigned)kWarpsPerCta;
+                    if (stuckNow && prev + 1u >= needStuck) {
                         __threadfence_block();
                         if (*(volatile unsigned*)&shTail != *(volatile unsigned*)&shHead) *(volatile unsigned*)&shGo = 1u;
                     }

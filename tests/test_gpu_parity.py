@@ -336,7 +336,8 @@ def test_fast_path_cluster_screen_sizes(fast_worker, oracle, n):
     st = fast_worker.stats()
     if (ref.sdf_full >= n).any():  # at least one full-scene fallback happened: it went through the screen
         assert st["tc_passes"] > 0 and st["tc_requests"] > 0 and st["tc_items"] >= st["tc_requests"]
-        if n >= 12800:  # (tiny scenes pay a whole 128 x 128 MMA block for a couple of clusters)
+        if n >= 33000:  # (small scenes pay a whole 128 x 128 MMA block for a couple of clusters, and on a 96 x 54 frame nearly
+                        #  every pass is an end-of-frame pass that serves a handful of requests)
             assert st["executed_flops"] < st["algorithmic_flops"]
 
 
