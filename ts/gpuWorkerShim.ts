@@ -6,7 +6,10 @@
 //     w.postMessage(job);                       // Job of raymarchWorker.ts:10-22
 // Install this class as globalThis.Worker (Electron preload / node + jsdom harness) before main.ts loads.
 // The reference keeps scene / camera / shader selection (SceneManager, Camera are imported unchanged);
-// only the march moves to the GPU.  NOT executed in the build container (no Node.js there).
+// only the march moves to the GPU.  The addon owns every GPU of the box (rm_pool_*): all NUM_WORKERS GpuWorker objects talk to
+// that one pool, and the row-band Jobs of a frame share ONE render (the pool's frame cache).  Not executed in the build container
+// (no Node.js there): tests/addon_harness.cc drives the same addon calls under a mock N-API runtime; tools/node_harness.mjs is
+// the one-command check under real Node.
 import { mat3, mat4, vec3 } from 'gl-matrix';
 import { SceneManager } from '../../reference/src/util/sceneManager';
 import { Camera } from '../../reference/src/util/camera';
