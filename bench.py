@@ -66,6 +66,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def config_of(wl, n_prims, parallelism):
+    """The `config` object of the JSON line — identical keys and values on the b200 arm and on the reference arm."""
+    return {"workload": wl["desc"], "n_prims": n_prims, "width": wl["W"], "height": wl["H"], "accel": wl["accel"],
+            "algorithm": wl["algorithm"], "shader": wl["shader"], "l2": "flushed between steps (256 MiB write per device)",
+            "parallelism": parallelism,
+            "field_math": "fp32 (SDF evaluations)", "control_math": "fp64, unfused (JS-exact ray/interval logic)"}
+
+
 def workload(args):
     desc, preset, syn, accel, alg, shader, W, H = WORKLOADS[args.workload]
     if syn is not None and args.prims:
@@ -247,7 +255,9 @@ def reference_arm(args, wl, rank):
     line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "n_prims": wl["n_prims"], "width": wl["W"], "height": wl["H"]},
+            "config": config_of(wl, s.n_prims, "single GPU" if args.gpus <= 1 else f"row-stripe x{args.gpus}"),
+            "config_note": "same workload as the b200 arm (its config keys are repeated verbatim); this arm runs the CPU restatement of the "
+                           "reference path in f64 on the host cores, on a bounded row sample",
             "sdf_evals_per_s": evals / t_all,
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
                              "accel_build_ms": t_accel},
@@ -451,10 +461,8 @@ def main():
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "n_prims": last["n_prims"], "width": W, "height": H, "accel": wl["accel"],
-                   "algorithm": wl["algorithm"], "shader": wl["shader"], "l2": "flushed between steps (256 MiB write per device)",
-                   "parallelism": eng.mode,
-                   "field_math": "fp32 (SDF evaluations)", "control_math": "fp64, unfused (JS-exact ray/interval logic)"},
+        "config": config_of(wl, last["n_prims"], "single GPU" if n_gpus == 1 else f"row-stripe x{n_gpus}"),
+        "route": eng.mode,
         "value_timing": "device-resident: max over GPUs of the CUDA-event kernel time per step (the tile gather is fused into the kernel); "
                         "the stats reduction and host time are in wall_ms_per_step and in e2e, which is the headline",
         "kernel_ms_per_gpu": per_rank_ms,

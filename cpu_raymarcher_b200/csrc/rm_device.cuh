@@ -56,6 +56,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RM_VEC_EPILOGUE
 #define RM_VEC_EPILOGUE 0  // 1: retired pixels are held in registers and written per whole tile with 16-byte vector stores (shuffle transpose).  Parity-green (profiles/r02c_gpu_tests_vec_epilogue.log) but SLOWER on every config (cfg4 +2 %, cfg5 +14 %, profiles/r02c_ab.jsonl): the scalar stores at retirement are fire-and-forget, the tile write sits on the refill path.  Default 0.
 #endif
+#ifndef RM_INLINE_WALK
+#define RM_INLINE_WALK 0  // 1: the grid-walk cell step inlined into the state machine instead of an out-of-line call (A/B switch)
+#endif
 #ifndef RM_RESIDENT_B
 #define RM_RESIDENT_B 1  // cluster-screen B tiles resident in shared memory when they fit the ring (0: always streamed; A/B switch)
 #endif
@@ -1575,7 +1578,12 @@ static __device__ __noinline__ bool lazy_init(const DevScene& sc, const float* _
 }
 
 // examine the current cell, then step to the next one
-static __device__ __noinline__ void lazy_advance_cell(const DevScene& sc, const float* __restrict__ of, float dx, float dy, float dz, LazyIv& lz) {
+#if RM_INLINE_WALK
+static __device__ __forceinline__
+#else
+static __device__ __noinline__
+#endif
+void lazy_advance_cell(const DevScene& sc, const float* __restrict__ of, float dx, float dy, float dz, LazyIv& lz) {
     const double o[3] = {(double)of[0], (double)of[1], (double)of[2]};
     const float d[3] = {dx, dy, dz};
     const double invD[3] = {lz.invD[0], lz.invD[1], lz.invD[2]};
