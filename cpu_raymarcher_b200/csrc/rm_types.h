@@ -186,6 +186,6 @@ int launch_render_fast(const RenderParams& p, int n_sms, void* stream);
 int launch_shade_val(const ShadeParams& p, void* stream);
 int launch_shade_fast(const ShadeParams& p, void* stream);
 int probe_fp32_peak(int n_sms, void* stream, float* scratch, double* tflops);
-int launch_order_tiles(const unsigned int* cost, unsigned int* order, int n_tiles, void* stream);  // rm_kernels_fast.cu
+int launch_order_tiles(const unsigned int* cost, unsigned int* order, int n_tiles, int n_runs, void* stream);  // rm_kernels_fast.cu
 
 }  // namespace rm
