@@ -317,7 +317,8 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     CU(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, stream));
     if (ordered && launches) {  // next frame's order from this frame's per-tile costs (one small CTA, after the timed kernel)
         // spatial runs of >= 4 tiles per resident warp (16 warps per SM on the kernels that use the order), at most 16
-        const int runs = std::max(1, std::min(16, P.n_tiles / (4 * 16 * c->n_sms)));
+        // (frames whose bands are not downloaded during the render need no spatial order: 0 = every tile by cost)
+        const int runs = early ? std::max(1, std::min(16, P.n_tiles / (4 * 16 * c->n_sms))) : 0;
         int e = launch_order_tiles((const unsigned int*)c->d_tile_cost.p, (unsigned int*)c->d_tile_order.p, P.n_tiles, runs, stream);
         if (e != 0) return fail(c, RM_ERR_CUDA, "tile-order launch: %s", cudaGetErrorString((cudaError_t)e));
         c->order_valid = true;

@@ -2902,6 +2902,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
 // schedule.
 constexpr int kOrderBands = 16;
 constexpr int kOrderKeys = 256 + kOrderBands * 256;
+// nRuns == 0: no spatial constraint at all (frames that stay on the device: nothing downloads bands) — every tile by cost.
 static __global__ void __launch_bounds__(1024) order_tiles_kernel(const unsigned* __restrict__ cost, unsigned* __restrict__ order, int n, int nRuns) {
     __shared__ unsigned shMax, shCut, hist[kOrderKeys], cursor[kOrderKeys];
     const int tid = threadIdx.x;
@@ -2921,7 +2922,7 @@ static __global__ void __launch_bounds__(1024) order_tiles_kernel(const unsigned
     if (tid == 0) {
         unsigned acc = 0u, cut = 0u;
         for (unsigned b = 0; b < 256u; ++b) {
-            if (acc + hist[b] > (unsigned)n / 4u) break;
+            if (nRuns > 0 && acc + hist[b] > (unsigned)n / 4u) break;
             acc += hist[b];
             cut = b + 1u;  // buckets [0, cut) go first
         }
@@ -2932,7 +2933,7 @@ static __global__ void __launch_bounds__(1024) order_tiles_kernel(const unsigned
     for (int i = tid; i < 256; i += blockDim.x)
         if ((unsigned)i >= cut) hist[i] = 0u;  // (their tiles are counted again under their run's keys)
     __syncthreads();
-    const int perRun = (n + nRuns - 1) / nRuns;  // nRuns <= kOrderBands
+    const int perRun = nRuns > 0 ? (n + nRuns - 1) / nRuns : n;  // nRuns <= kOrderBands
     auto key = [&](int i) {
         const unsigned b = bucket(i);
         return b < cut ? b : 256u + (unsigned)(i / perRun) * 256u + b;
