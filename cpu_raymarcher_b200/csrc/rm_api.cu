@@ -212,6 +212,8 @@ int render_device_locked(rm_ctx* c, const rm_request* rq, const rm_result* out, 
     P.shader2 = rq->shader_analytics;
     P.length_sqrt = (c->flags & RM_F_LENGTH_SQRT) ? 1 : 0;
     {
+        const char* a = std::getenv("RM_ANATOMY");  // measurement knob: drain_ms / tail_ms of rm_stats (off: no timestamps taken)
+        P.anatomy = (a && a[0] == '1') ? 1 : 0;
         const char* e = std::getenv("RM_TAIL_TRIGGER");  // measurement knob, read per call
         P.tail_trigger = e ? std::max(1, std::atoi(e)) : kTailTriggerWarps;
     }

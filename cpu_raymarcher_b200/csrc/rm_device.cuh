@@ -2004,7 +2004,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         }
     }
 
-    if (threadIdx.x == 0) atomicMin(&P.stats->t_enter_min, globaltimer_ns());
+    if (P.anatomy && threadIdx.x == 0) atomicMin(&P.stats->t_enter_min, globaltimer_ns());
     // warp-uniform work-queue cursor
     int tile = -1, tilePos = kTileW * kTileH;
     unsigned tileT0 = 0u;  // clock() at the fetch of the current tile (cost-ordered queue)
@@ -2255,7 +2255,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
                 t = __shfl_sync(kFull, t, 0);
                 if ((int)t >= P.n_tiles) {
                     queueEmpty = true;
-                    if (lane == 0) atomicMin(&P.stats->t_drain_min, globaltimer_ns());
+                    if (P.anatomy && lane == 0) atomicMin(&P.stats->t_drain_min, globaltimer_ns());
                     break;
                 }
                 // cost-ordered queue: ticket t -> the t-th most expensive tile of the previous frame of this geometry (so the frame ends
@@ -2844,7 +2844,7 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         if (heldM) flush_held(heldM);
     }
     if (P.tile_cost && tile >= 0 && lane == 0) P.tile_cost[tile] = (unsigned)clock() - tileT0;  // the warp's last tile
-    if (lane == 0) {  // frame anatomy (rm_stats: ramp / drain / tail): a handful of atomics per warp per frame
+    if (P.anatomy && lane == 0) {  // frame anatomy (rm_stats: drain / tail), RM_ANATOMY=1: three same-address atomics per warp
         const unsigned long long now = globaltimer_ns();
         atomicMin(&P.stats->t_exit_min, now);
         atomicMax(&P.stats->t_exit_max, now);

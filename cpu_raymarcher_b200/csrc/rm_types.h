@@ -144,6 +144,7 @@ struct RenderParams {
     double step_size, overshoot;
     int32_t shader, shader2;
     int32_t length_sqrt;  // validation: vec3.length = sqrt(x*x+y*y+z*z) instead of Math.hypot
+    int32_t anatomy;       // RM_ANATOMY=1: record the frame-anatomy timestamps (rm_stats.drain_ms / tail_ms)
     int32_t tail_trigger;  // cooperative pass at the end of the frame: parked warps that trigger it (kWarpsPerCta = only when all are)
     int32_t fast_objects;  // exact kernels in a default context (operator trees / Mandelbulb): march-step queries in fp32
     int32_t n_tiles, tiles_x;

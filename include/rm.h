@@ -198,7 +198,8 @@ typedef struct rm_stats_t {
     double tensor_flops;       /* tcgen05 tf32 MMAs of the cluster screen: 2 sweeps x 128 x 128 x 16 MACs per cluster block  */
     int32_t n_devices;         /* 1, or the number of GPUs a pool call used (rm_pool_stats)                               */
     int32_t pad_;
-    /* frame anatomy of the render kernel, from %globaltimer: how long the tile queue lasted, and the end-of-frame tail */
+    /* frame anatomy of the render kernel, from %globaltimer: how long the tile queue lasted, and the end-of-frame tail.
+     * Only recorded when the environment has RM_ANATOMY=1 (three contended atomics per warp); 0 otherwise. */
     double drain_ms;           /* first CTA in -> the first warp finds the tile queue empty                               */
     double tail_ms;            /* ... -> the last warp leaves (pool: the slowest device's)                                */
 } rm_stats_t;

@@ -832,6 +832,7 @@ def test_cost_ordered_tile_queue_does_not_change_the_frame(monkeypatch):
     t, m, q = sm.synthetic_spheres(10000).arrays()
     W, H = 1920, 1080
     cam = Camera()
+    monkeypatch.setenv("RM_ANATOMY", "1")
     # (the order is used for striped requests — the shares of a multi-GPU frame; here: GPU 0 of 2)
     rq = rb.Context.make_request(W, H, cam.get_rotation_matrix3(), cam.get_position(), shader="iteration-heatmap", stripes=(8, 2, 0))
     cam.set_angles(0.1, 0.3)

@@ -5,6 +5,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["RM_ANATOMY"] = "1"
 import cpu_raymarcher_b200 as rb  # noqa: E402
 
 w = rb.RaymarchWorker(0)
