@@ -361,7 +361,7 @@ class FrameSharder:
         return st, planes
 
     # ------------------------------------------------------------------ end-to-end frames (host buffers)
-    def e2e_frames(self, job: dict, shader, steps: int = 3) -> dict:
+    def e2e_frames(self, job: dict, shader, steps: int = 3, between=None) -> dict:
         """The same frame through the reference-facing call with HOST buffers: request in, planes out.
         world == 1: RaymarchWorker.on_message (rm_render).  world > 1: render_frame_host (every rank downloads its own stripes into one shared host frame)."""
         W, H = int(job["width"]), int(job["height"])
@@ -370,10 +370,14 @@ class FrameSharder:
         h2d = C.sizeof(_lib.Request)
         if self.world == 1:
             self.worker.on_message(job, shader=shader, pinned=True)  # warm-up (allocates the page-locked planes)
-            t0 = time.perf_counter()
+            t_all = 0.0
             for _ in range(steps):
+                if between:
+                    between()  # e.g. an L2 flush, not timed
+                t0 = time.perf_counter()
                 self.worker.on_message(job, shader=shader, pinned=True)
-            ms = (time.perf_counter() - t0) * 1e3 / steps
+                t_all += time.perf_counter() - t0
+            ms = t_all * 1e3 / steps
             return {"ms_per_frame": ms, "h2d_bytes": h2d, "d2h_bytes": d2h,
                     "path": "RaymarchWorker.on_message -> rm_render into page-locked planes (row bands downloaded during the render)"}
         import torch.distributed as dist
@@ -393,10 +397,14 @@ class FrameSharder:
                 if self.rank == 0:
                     self.download_frame(shader)
             path = "fused peer-store gather into rank 0's HBM, then rank 0 downloads the frame"
-        dist.barrier()
-        t0 = time.perf_counter()
+        t_all = 0.0
         for _ in range(steps):
+            if between:
+                between()
+            dist.barrier()
+            t0 = time.perf_counter()
             frame()
-        dist.barrier()
-        ms = (time.perf_counter() - t0) * 1e3 / steps
+            dist.barrier()  # the frame is complete on every rank
+            t_all += time.perf_counter() - t0
+        ms = t_all * 1e3 / steps
         return {"ms_per_frame": ms, "h2d_bytes": h2d * self.world, "d2h_bytes": d2h, "path": path}

@@ -14,7 +14,9 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-PRESETS = ((4, "Atom"), (5, "Torus"), (7, "Cube"), (0, "Sphere"), (9, "Pyramid of Boxes"))
+# BASELINE config 5 / SURVEY.md §8d: presets 4, 5, 7, 8, 9 (sceneManager.ts:159-207).  (Round 1 had preset 0 "Sphere" in place of
+# 8 "Sphere and Cube".)  The measured workload is `bench.py --workload cfg5sweep`; this script is the standalone per-preset view.
+PRESETS = ((4, "Atom"), (5, "Torus"), (7, "Cube"), (8, "Sphere and Cube"), (9, "Pyramid of Boxes"))
 
 
 def main():
