@@ -3,6 +3,8 @@ mirrors of sceneManager.ts / camera.ts against the oracle (independent implement
 import ctypes as C
 import os
 import re
+import shutil
+import subprocess
 
 import numpy as np
 import pytest
@@ -235,3 +237,25 @@ def test_header_is_plain_c(tmp_path):
     src = tmp_path / "t.c"
     src.write_text('#include "rm.h"\nint main(void) { rm_scene s; rm_op_node n; (void)s; (void)n; return sizeof(rm_stats_t) > 0 ? 0 : 1; }\n')
     subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="only meaningful on a machine without a GPU")
+def test_pool_without_gpu_fails_loudly_and_addon_harness_reports_it(tmp_path):
+    """rm_pool_create has no CPU fallback either; and the N-API addon (run here under the mock runtime of tests/napi_mock.cc)
+    turns that failure into a thrown JS error instead of a hang or a silent empty frame."""
+    with pytest.raises(rb.RmError) as ei:
+        rb.RaymarchPool()
+    assert ei.value.code == _lib.RM_ERR_CUDA and "no CPU fallback" in str(ei.value)
+    cxx = shutil.which(os.environ.get("CXX", "g++"))
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    exe = tmp_path / "addon_harness"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-Wall", "-pthread", os.path.join(ROOT, "tests", "addon_harness.cc"),
+                           os.path.join(ROOT, "tests", "napi_mock.cc"), os.path.join(ROOT, "addon", "rm_napi.cc"), "-o", str(exe),
+                           "-L" + os.path.join(ROOT, "cpu_raymarcher_b200"), "-lrm_b200", "-Wl,-rpath," + os.path.join(ROOT, "cpu_raymarcher_b200")])
+    import struct
+    scene = tmp_path / "scene.bin"
+    scene.write_bytes(struct.pack("4i", 1, 0, 0, 0) + bytes([0]) + np.eye(4, dtype=np.float32).tobytes() + np.array([1.5, 0, 0, 0]).tobytes() +
+                      np.eye(3, dtype=np.float32).tobytes() + np.array([0, 0, 3], np.float32).tobytes())
+    r = subprocess.run([str(exe), str(scene), str(tmp_path / "out.bin"), "32", "32", "sphere-tracer", "None", "4"], capture_output=True, text=True)
+    assert r.returncode == 1 and "uploadScene threw: RM_ERR_CUDA" in r.stderr and "no CPU fallback" in r.stderr
