@@ -759,7 +759,11 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float (&q)[NQ][3], War
 // ------------------------------------------------------------------------------------------
 constexpr int kTcGroups = 4;            // warpgroups of the CTA = TMEM accumulator buffers (4 x 128 columns = all of TMEM)
 constexpr int kTcStages = 8;            // B-tile ring (4 KB each)
-constexpr unsigned kTcItemCap = 10240;  // work items of one pass (40 KB of the dynamic shared memory)
+#ifndef RM_TC_ITEM_CAP
+#define RM_TC_ITEM_CAP 7168  // 28 KB: with the static cooperative queue the tensor-core instance then needs 68 KB of dynamic + 25 KB of
+                             // static shared memory — under the 100 KB carve-out step, which leaves the SM 156 KB of L1 instead of 124
+#endif
+constexpr unsigned kTcItemCap = RM_TC_ITEM_CAP;  // work items of one pass (a typical pass lists ~550; overflow falls back to a per-lane scan)
 constexpr int kTcBlock = 128;           // spheres per MMA (N) = query rows per batch (M)
 constexpr uint32_t kTcTileBytes = 4096;  // B tile: 128 rows x 8 tf32
 constexpr uint32_t kTcATileBytes = 8192;  // A tile: 128 rows x 16 tf32

@@ -13,7 +13,10 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     auto kern = render_kernel<NP, ACCEL, PK, TCK, ALGT>;
     constexpr int kWarps = CtaShape<NP, ACCEL, PK>::kWarps;
     constexpr int kThreads = 32 * kWarps;
-    constexpr size_t kDynSmem = (size_t)kWarps * 2 * kStageBytes;  // per-warp double-buffered TMA stages
+    // per-warp double-buffered TMA stages; the tensor-core instance with the static cooperative queue never streams primitives
+    // through them and only needs its A tile + B ring + work-item list
+    constexpr size_t kDynSmem = (TCK && RM_TC_STATIC_QUEUE) ? (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes + 4u * (size_t)kTcItemCap
+                                                            : (size_t)kWarps * 2 * kStageBytes;
     // per instantiation; function attributes are PER DEVICE, and several devices launch from several host threads (rm_pool)
     static std::mutex mu;
     static int blocksPerSM = 0;
