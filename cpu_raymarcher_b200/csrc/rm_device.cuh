@@ -1897,8 +1897,10 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     // ---- shared memory: per-warp TMA stages for the primitive stream, and the CTA-wide request queue of
     //      the all-primitives service (requests are just a point, so they can move between warps even
     //      though ray state cannot: any warp that finds 32 of them serves them at full lane occupancy) ----
-    extern __shared__ __align__(128) float4 shStageDyn[];  // [kWarpsPerCta][2][kStageBytes / 16], sized at launch
-    float4 (*shStage)[2][kStageBytes / 16] = reinterpret_cast<float4 (*)[2][kStageBytes / 16]>(shStageDyn);
+    // [2][kWarpsPerCta][kStageBytes / 16], stage-major and sized at launch: scenes small enough to stay resident in stage 0 get
+    // only the first half (and the exact kernels none at all) — every KB of shared memory a CTA does not ask for is L1
+    extern __shared__ __align__(128) float4 shStageDyn[];
+    float4 (*shStage)[kWarpsPerCta][kStageBytes / 16] = reinterpret_cast<float4 (*)[kWarpsPerCta][kStageBytes / 16]>(shStageDyn);
     __shared__ __align__(8) unsigned long long shBar[kWarpsPerCta][2];
     __shared__ float4 shReq[kQueueCap];               // ring of requests: x, y, z, owner thread
     __shared__ double shRes[kWarpsPerCta * 32];        // results by owner thread
@@ -1926,8 +1928,8 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
     ws.phase = 0u;
 #pragma unroll
     for (int sgi = 0; sgi < 2; ++sgi) {
-        ws.buf[sgi] = shStage[warpId][sgi];
-        ws.bufAddr[sgi] = smem_u32(shStage[warpId][sgi]);
+        ws.buf[sgi] = shStage[sgi][warpId];
+        ws.bufAddr[sgi] = smem_u32(shStage[sgi][warpId]);
         ws.bar[sgi] = smem_u32(&shBar[warpId][sgi]);
     }
     ws.resident = false;

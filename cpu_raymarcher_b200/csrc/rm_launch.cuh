@@ -15,8 +15,18 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     constexpr int kThreads = 32 * kWarps;
     // per-warp double-buffered TMA stages; the tensor-core instance with the static cooperative queue never streams primitives
     // through them and only needs its A tile + B ring + work-item list
-    constexpr size_t kDynSmem = (TCK && RM_TC_STATIC_QUEUE) ? (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes + 4u * (size_t)kTcItemCap
-                                                            : (size_t)kWarps * 2 * kStageBytes;
+    constexpr size_t kDynSmem = NP::kExact ? 0
+                                : (TCK && RM_TC_STATIC_QUEUE) ? (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes + 4u * (size_t)kTcItemCap
+                                                              : (size_t)kWarps * 2 * kStageBytes;
+    // a scene that stays resident in stage 0 (the kernel's own rule) only needs the first, stage-major half of the stages
+    constexpr int kPerStage0 = kStageBytes / (16 * ((PK == PK_TSPHERE) ? 1 : 4));
+    const bool resident = !NP::kExact && !(TCK && RM_TC_STATIC_QUEUE) && p.scene.n_prims > 0 &&
+                          ((PK == PK_TSPHERE) ? p.scene.n_chunks <= 4 : p.scene.n_prims <= kPerStage0);
+#ifdef RM_FULL_STAGES  // A/B switch: always the full double-buffered allocation
+    const size_t dynSmem = NP::kExact ? (size_t)kWarps * 2 * kStageBytes : ((void)resident, kDynSmem);
+#else
+    const size_t dynSmem = resident ? kDynSmem / 2 : kDynSmem;
+#endif
     // per instantiation; function attributes are PER DEVICE, and several devices launch from several host threads (rm_pool)
     static std::mutex mu;
     static int blocksPerSM = 0;
@@ -27,7 +37,7 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
         if (e != cudaSuccess) return (int)e;
         std::lock_guard<std::mutex> lk(mu);
         if (!((devDone >> (dev & 63)) & 1ull)) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(kDynSmem, (size_t)kWarps * 2 * kStageBytes));
             if (e != cudaSuccess) return (int)e;
             int b = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, kDynSmem);
@@ -44,7 +54,7 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     int blocks = (int)std::min<long long>(maxBlocks, (warpsWanted + kWarps - 1) / kWarps);
     if (blocks < 1) blocks = 1;
     (void)cudaGetLastError();  // a stale error of an unrelated earlier call on this thread must not be blamed on this launch
-    kern<<<blocks, kThreads, kDynSmem, stream>>>(p);
+    kern<<<blocks, kThreads, dynSmem, stream>>>(p);
     return (int)cudaGetLastError();
 }
 
