@@ -1943,14 +1943,20 @@ __global__ void __launch_bounds__(32 * CtaShape<NP, ACCEL, PK>::kWarps,
         // small scenes: stage the whole primitive array once and keep it resident in shared memory
         constexpr int kPerStage0 = kStageBytes / (16 * ((PK == PK_TSPHERE) ? 1 : 4));
         if (P.scene.n_prims > 0 && ((PK == PK_TSPHERE) ? P.scene.n_chunks <= 4 : P.scene.n_prims <= kPerStage0)) {
+            // ONE copy per CTA, in the first stage of the dynamic shared memory (the launcher allocates just that: 2.5 KB instead of
+            // 20-80 KB, the difference is L1); warp 0 brings it in, the __syncthreads() below publishes it to the other warps
             const unsigned bytes = (PK == PK_TSPHERE) ? (unsigned)(P.scene.n_chunks * kChunkBytes) : (unsigned)(P.scene.n_prims * 64);
-            if (lane == 0) {
-                mbar_expect_tx(ws.bar[0], bytes);
-                bulk_g2s(ws.bufAddr[0], P.scene.rec, bytes, ws.bar[0]);
+            ws.buf[0] = shStage[0][0];
+            ws.bufAddr[0] = smem_u32(shStage[0][0]);
+            if (warpId == 0) {
+                if (lane == 0) {
+                    mbar_expect_tx(ws.bar[0], bytes);
+                    bulk_g2s(ws.bufAddr[0], P.scene.rec, bytes, ws.bar[0]);
+                }
+                mbar_wait(ws.bar[0], 0u);
+                ws.phase ^= 1u;
             }
-            mbar_wait(ws.bar[0], 0u);
-            ws.phase ^= 1u;
-            ws.resident = true;
+            ws.resident = true;  // (never streamed through again: the cooperative queue needs >= 256 primitives)
         }
     }
     shReady[threadIdx.x] = 0u;

@@ -18,14 +18,14 @@ static int launch_one(const RenderParams& p, int n_sms, cudaStream_t stream) {
     constexpr size_t kDynSmem = NP::kExact ? 0
                                 : (TCK && RM_TC_STATIC_QUEUE) ? (size_t)kTcATileBytes + (size_t)kTcStages * kTcTileBytes + 4u * (size_t)kTcItemCap
                                                               : (size_t)kWarps * 2 * kStageBytes;
-    // a scene that stays resident in stage 0 (the kernel's own rule) only needs the first, stage-major half of the stages
+    // a scene that stays resident in shared memory (the kernel's own rule) only needs the first stage: one copy per CTA
     constexpr int kPerStage0 = kStageBytes / (16 * ((PK == PK_TSPHERE) ? 1 : 4));
     const bool resident = !NP::kExact && !(TCK && RM_TC_STATIC_QUEUE) && p.scene.n_prims > 0 &&
                           ((PK == PK_TSPHERE) ? p.scene.n_chunks <= 4 : p.scene.n_prims <= kPerStage0);
 #ifdef RM_FULL_STAGES  // A/B switch: always the full double-buffered allocation
     const size_t dynSmem = NP::kExact ? (size_t)kWarps * 2 * kStageBytes : ((void)resident, kDynSmem);
 #else
-    const size_t dynSmem = resident ? kDynSmem / 2 : kDynSmem;
+    const size_t dynSmem = resident ? (size_t)kStageBytes : kDynSmem;  // resident: one copy of the scene per CTA
 #endif
     // per instantiation; function attributes are PER DEVICE, and several devices launch from several host threads (rm_pool)
     static std::mutex mu;
