@@ -602,7 +602,6 @@ def sweep_main(args, rank, local_rank, world):
     worker = None if pool_mode else rb.RaymarchWorker(device=local_rank)
     sharder = None if pool_mode else multigpu.FrameSharder(worker, rank, world, local_rank)
     local_sharder = None if pool_mode else multigpu.FrameSharder(worker, 0, 1, local_rank)  # whole frames on this GPU, no collective per frame
-    SUMK, MAXK = ("n_pixels", "sum_sdf", "sum_iters", "n_hit"), ("max_sdf", "max_iters")
 
     def run_sweep(nframes):
         """-> per preset: list of per-frame diagnostics (identical on every rank), kernel ms summed on the busiest GPU, launches"""
@@ -625,23 +624,19 @@ def sweep_main(args, rank, local_rank, world):
                         launches += st["n_launches"]
             elif args.sweep_mode == "frames" or world == 1:
                 worker._ensure_scene(preset, "None")
-                table = torch.zeros((nframes, len(SUMK) + 2 * len(MAXK) + 1), dtype=torch.int64)
-                my_ms = 0.0
+                mine, my_ms = {}, 0.0
                 for k in range(rank, nframes, world):
                     st = local_sharder.render_frame(jobs[k], shader="normal")
-                    table[k] = torch.tensor([st[q] for q in SUMK] + [st[q] for q in MAXK] + [st["min_sdf"], st["min_iters"], 1])
+                    mine[k] = st
                     my_ms += st["kernel_ms"]
                     launches += st["n_launches"]
-                if world > 1:  # disjoint rows: one SUM all-reduce per preset carries every frame's diagnostics to every rank
-                    table = table.to(dev)
-                    dist.all_reduce(table, op=dist.ReduceOp.SUM)
+                # disjoint rows: one SUM all-reduce per preset carries every frame's diagnostics to every rank
+                sts = multigpu.allreduce_frame_table(mine, nframes, dev)
+                if world > 1:
                     ms_t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
                     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
                     my_ms = float(ms_t.item())
-                    table = table.cpu()
                 kms += my_ms
-                cols = list(SUMK) + list(MAXK) + ["min_sdf", "min_iters", "_n"]
-                sts = [dict(zip(cols, [int(v) for v in row])) for row in table.tolist()]
             else:
                 sharder.setup_scene(jobs[0])
                 sts = []

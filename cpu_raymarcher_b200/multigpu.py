@@ -75,6 +75,33 @@ def reduce_stats(stats_list):
     return out
 
 
+SWEEP_SUM_KEYS = ("n_pixels", "sum_sdf", "sum_iters", "n_hit")
+SWEEP_MAX_KEYS = ("max_sdf", "max_iters")
+SWEEP_COLS = SWEEP_SUM_KEYS + SWEEP_MAX_KEYS + ("min_sdf", "min_iters", "_n")
+
+
+def allreduce_frame_table(my_stats: dict, n_frames: int, device=None) -> list:
+    """Frame-parallel sweeps (config 5): every frame is rendered whole by ONE rank, so the per-frame diagnostics of main.ts:527-548
+    are complete on that rank and zero everywhere else — one SUM all-reduce of the [frames x columns] table carries every frame's
+    row to every rank (the `_n` column counts the contributions: exactly 1 per frame).  `my_stats` maps frame index -> stats dict of
+    the frames this rank rendered.  Returns one dict per frame, identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    table = torch.zeros((n_frames, len(SWEEP_COLS)), dtype=torch.int64)
+    for k, st in my_stats.items():
+        table[k] = torch.tensor([int(st[q]) for q in SWEEP_SUM_KEYS + SWEEP_MAX_KEYS] + [int(st["min_sdf"]), int(st["min_iters"]), 1])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if device is not None:
+            table = table.to(device)
+        dist.all_reduce(table, op=dist.ReduceOp.SUM)
+        table = table.cpu()
+    rows = [dict(zip(SWEEP_COLS, [int(v) for v in row])) for row in table.tolist()]
+    missing = [k for k, r in enumerate(rows) if r["_n"] != 1]
+    if missing:
+        raise RuntimeError(f"frames {missing[:8]} were rendered by {rows[missing[0]]['_n']} ranks instead of exactly one")
+    return rows
+
+
 class HostFrameUnavailable(RuntimeError):
     """The shared host frame could not be created (raised on every rank alike)."""
 

@@ -112,6 +112,22 @@ def _worker(rank, world, port, q):
             nodes, nn, leaf = build(t, m, q_, ops, roots, 0)
             assert got["n_nodes"] == nn and got["nodes"] == bytes(nodes)[: len(got["nodes"])] and np.array_equal(got["leaf"], leaf), (preset, accel)
         assert cw._scene_key == (preset, None, accel)
+    # frame-parallel sweep (config 5): frames dealt round robin, one SUM all-reduce of the per-frame table; every rank ends up with
+    # every frame's diagnostics, and a frame rendered by nobody (or twice) is an error, not a silent zero
+    n_frames = 7
+    mine = {k: dict(n_pixels=100 + k, sum_sdf=1000 * k + 7, sum_iters=10 * k, n_hit=k, max_sdf=50 + k, max_iters=5 + k, min_sdf=k, min_iters=1)
+            for k in range(rank, n_frames, world)}
+    rows = multigpu.allreduce_frame_table(mine, n_frames)
+    assert len(rows) == n_frames
+    for k, r in enumerate(rows):
+        assert (r["n_pixels"], r["sum_sdf"], r["sum_iters"], r["n_hit"], r["max_sdf"], r["max_iters"], r["min_sdf"], r["min_iters"]) == \
+            (100 + k, 1000 * k + 7, 10 * k, k, 50 + k, 5 + k, k, 1), (k, r)
+    try:
+        multigpu.allreduce_frame_table({k: v for k, v in mine.items() if k != 1}, n_frames)  # frame 1 rendered by nobody
+        lost = False
+    except RuntimeError:
+        lost = True
+    assert lost
     if rank == 0:
         q.put(({k: v.numpy() for k, v in frame.items()}, want))
     dist.barrier()
