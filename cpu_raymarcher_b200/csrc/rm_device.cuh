@@ -758,7 +758,10 @@ RM_DEV void search_stages_ts(const RenderParams& P, const float (&q)[NQ][3], War
 // candidates are still resolved with the plain fp32 SDF and the winner polished in fp64.
 // ------------------------------------------------------------------------------------------
 constexpr int kTcGroups = 4;            // warpgroups of the CTA = TMEM accumulator buffers (4 x 128 columns = all of TMEM)
-constexpr int kTcStages = 8;            // B-tile ring (4 KB each)
+#ifndef RM_TC_STAGES
+#define RM_TC_STAGES 8
+#endif
+constexpr int kTcStages = RM_TC_STAGES;  // B-tile ring (4 KB each)
 #ifndef RM_TC_ITEM_CAP
 #define RM_TC_ITEM_CAP 7168  // 28 KB: with the static cooperative queue the tensor-core instance then needs 68 KB of dynamic + 25 KB of
                              // static shared memory — under the 100 KB carve-out step, which leaves the SM 156 KB of L1 instead of 124

@@ -43,6 +43,7 @@ def main():
                 res[name].append(round(line["ms_per_step"], 3))
             except Exception:
                 res[name].append("FAILED: " + (out.stderr.strip().splitlines() or ["?"])[-1][:200])
+            print(json.dumps({"variant": name, "ms_per_step": res[name][-1]}), flush=True)  # per run: a call cut off by its time limit still reports
     print(json.dumps({"args": extra, "ms_per_step": res}), flush=True)
 
 
