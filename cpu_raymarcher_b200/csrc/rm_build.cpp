@@ -120,47 +120,66 @@ void compute_prim_geometry(int32_t n, const uint8_t* type, const float* w2l, con
 
 // ------------------------------------------------------------------------------------------ BVH
 namespace {
+// Median-split BVH, built in place.  Every split of bvh.ts is by COUNT (mid = floor(n / 2)) and every object ends up in exactly
+// one leaf, so the shape of the tree — hence every node's index in the reference's pre-order numbering and every leaf's range in
+// the leaf-index array — follows from n and the depth alone: a subtree over n objects at depth d has count_nodes(n, d) nodes and
+// its leaves cover a contiguous run of n entries.  That makes the two children independent jobs (the top levels are handed to
+// threads) and lets all nodes share one permutation array, sorted a segment at a time on (key, index) pairs instead of through a
+// comparator that chases indices into the geometry.
 struct BvhBuilder {
-    const std::vector<PrimGeom>& geom;
-    std::vector<rm_bvh_node>& nodes;
-    std::vector<int32_t>& leafPrims;
-    const int maxDepth = 20, maxPrimsPerNode = 2;  // bvh.ts:32-33
+    const PrimGeom* geom;
+    rm_bvh_node* nodes;
+    int32_t* perm;  // becomes leafPrims
+    static constexpr int kMaxDepth = 20, kMaxPrimsPerNode = 2;  // bvh.ts:32-33
+    static constexpr size_t kParallelMin = 8192;                // segments at least this long fork while depth < kForkDepth
+    static constexpr int kForkDepth = 4;
 
-    void bounds_of(const std::vector<int32_t>& prims, float* bmin, float* bmax) const {  // computeBounds
-        if (prims.empty()) {
-            for (int k = 0; k < 3; ++k) bmin[k] = bmax[k] = 0.f;
-            return;
+    static bool is_leaf(size_t n, int depth) { return depth >= kMaxDepth || n <= (size_t)kMaxPrimsPerNode; }
+    // a subtree's node count depends on (n, depth) only; per depth at most two distinct n occur (floor / ceil halves)
+    struct CountMemo {
+        size_t n[kMaxDepth + 1][2];
+        int32_t c[kMaxDepth + 1][2];
+        int used[kMaxDepth + 1];
+        CountMemo() { std::memset(used, 0, sizeof(used)); }
+    };
+    static int32_t count_nodes(size_t n, int depth, CountMemo& m) {
+        if (is_leaf(n, depth)) return 1;
+        for (int i = 0; i < m.used[depth]; ++i)
+            if (m.n[depth][i] == n) return m.c[depth][i];
+        const int32_t c = 1 + count_nodes(n / 2, depth + 1, m) + count_nodes(n - n / 2, depth + 1, m);
+        if (m.used[depth] < 2) {
+            m.n[depth][m.used[depth]] = n;
+            m.c[depth][m.used[depth]++] = c;
         }
-        for (int k = 0; k < 3; ++k) {
-            bmin[k] = geom[(size_t)prims[0]].bmin[k];
-            bmax[k] = geom[(size_t)prims[0]].bmax[k];
-        }
-        for (size_t i = 1; i < prims.size(); ++i)
-            for (int k = 0; k < 3; ++k) {
-                bmin[k] = std::min(bmin[k], geom[(size_t)prims[i]].bmin[k]);
-                bmax[k] = std::max(bmax[k], geom[(size_t)prims[i]].bmax[k]);
-            }
+        return c;
     }
-    int32_t build(std::vector<int32_t>& prims, const float* bmin, const float* bmax, int depth) {
-        int32_t me = (int32_t)nodes.size();
-        nodes.emplace_back();
-        {
-            rm_bvh_node& nd = nodes[(size_t)me];
-            for (int k = 0; k < 3; ++k) {
-                nd.bmin[k] = bmin[k];
-                nd.bmax[k] = bmax[k];
-            }
-            nd.left = nd.right = -1;
-            nd.prim_first = (int32_t)leafPrims.size();
-            nd.prim_count = 0;
+    void bounds_of(size_t lo, size_t hi, float* bmin, float* bmax) const {  // computeBounds, folded in array order
+        for (int k = 0; k < 3; ++k) {
+            bmin[k] = geom[(size_t)perm[lo]].bmin[k];
+            bmax[k] = geom[(size_t)perm[lo]].bmax[k];
         }
-        auto make_leaf = [&]() {
-            nodes[(size_t)me].prim_count = (int32_t)prims.size();
-            leafPrims.insert(leafPrims.end(), prims.begin(), prims.end());
-        };
-        if (depth >= maxDepth || (int)prims.size() <= maxPrimsPerNode) {
-            make_leaf();
-            return me;
+        for (size_t i = lo + 1; i < hi; ++i) {
+            const PrimGeom& g = geom[(size_t)perm[i]];
+            for (int k = 0; k < 3; ++k) {
+                bmin[k] = std::min(bmin[k], g.bmin[k]);
+                bmax[k] = std::max(bmax[k], g.bmax[k]);
+            }
+        }
+    }
+    void build(size_t lo, size_t hi, const float* bmin, const float* bmax, int depth, int32_t me, CountMemo& memo,
+               std::vector<std::pair<float, int32_t>>& keys) {
+        rm_bvh_node& nd = nodes[(size_t)me];
+        for (int k = 0; k < 3; ++k) {
+            nd.bmin[k] = bmin[k];
+            nd.bmax[k] = bmax[k];
+        }
+        nd.left = nd.right = -1;
+        nd.prim_first = (int32_t)lo;  // = leafPrims.length when the reference creates this node
+        nd.prim_count = 0;
+        const size_t n = hi - lo;
+        if (is_leaf(n, depth)) {
+            nd.prim_count = (int32_t)n;
+            return;
         }
         // longest axis of the f32 size vector (bvh.ts:57-63)
         float size[3];
@@ -168,39 +187,45 @@ struct BvhBuilder {
         int axis = 0;
         if (size[1] > size[0]) axis = 1;
         if (size[2] > size[axis]) axis = 2;
-        std::vector<int32_t> sorted(prims);
-        std::stable_sort(sorted.begin(), sorted.end(), [&](int32_t a, int32_t b) {
-            return geom[(size_t)a].world[axis] < geom[(size_t)b].world[axis];
-        });
-        size_t mid = sorted.size() / 2;
-        std::vector<int32_t> leftStuff(sorted.begin(), sorted.begin() + (long)mid);
-        std::vector<int32_t> rightStuff(sorted.begin() + (long)mid, sorted.end());
-        if (leftStuff.empty() || rightStuff.empty()) {
-            make_leaf();
-            return me;
-        }
+        // Array.prototype.sort is stable (bvh.ts:66-70)
+        keys.resize(n);
+        for (size_t i = 0; i < n; ++i) keys[i] = {geom[(size_t)perm[lo + i]].world[axis], perm[lo + i]};
+        std::stable_sort(keys.begin(), keys.end(), [](const std::pair<float, int32_t>& a, const std::pair<float, int32_t>& b) { return a.first < b.first; });
+        for (size_t i = 0; i < n; ++i) perm[lo + i] = keys[i].second;
+        const size_t mid = lo + n / 2;
         float lmin[3], lmax[3], rmin[3], rmax[3];
-        bounds_of(leftStuff, lmin, lmax);
-        bounds_of(rightStuff, rmin, rmax);
-        std::vector<int32_t>().swap(sorted);
-        int32_t l = build(leftStuff, lmin, lmax, depth + 1);
-        nodes[(size_t)me].left = l;
-        int32_t r = build(rightStuff, rmin, rmax, depth + 1);
-        nodes[(size_t)me].right = r;
-        return me;
+        bounds_of(lo, mid, lmin, lmax);
+        bounds_of(mid, hi, rmin, rmax);
+        const int32_t l = me + 1, r = l + count_nodes(mid - lo, depth + 1, memo);
+        nd.left = l;
+        nd.right = r;
+        if (depth < kForkDepth && n >= kParallelMin) {
+            std::thread t([&, l] {
+                CountMemo m2;
+                std::vector<std::pair<float, int32_t>> k2;
+                build(lo, mid, lmin, lmax, depth + 1, l, m2, k2);
+            });
+            build(mid, hi, rmin, rmax, depth + 1, r, memo, keys);
+            t.join();
+        } else {
+            build(lo, mid, lmin, lmax, depth + 1, l, memo, keys);
+            build(mid, hi, rmin, rmax, depth + 1, r, memo, keys);
+        }
     }
 };
 }  // namespace
 
 void build_bvh(const std::vector<PrimGeom>& geom, std::vector<rm_bvh_node>& nodes, std::vector<int32_t>& leafPrims) {
-    nodes.clear();
-    leafPrims.clear();
-    std::vector<int32_t> all(geom.size());
-    for (size_t i = 0; i < geom.size(); ++i) all[i] = (int32_t)i;
-    BvhBuilder b{geom, nodes, leafPrims};
-    float bmin[3], bmax[3];
-    b.bounds_of(all, bmin, bmax);
-    b.build(all, bmin, bmax, 0);
+    const size_t n = geom.size();
+    leafPrims.resize(n);
+    for (size_t i = 0; i < n; ++i) leafPrims[i] = (int32_t)i;
+    BvhBuilder::CountMemo memo;
+    nodes.assign((size_t)BvhBuilder::count_nodes(n, 0, memo), rm_bvh_node{});
+    BvhBuilder b{geom.data(), nodes.data(), leafPrims.data()};
+    float bmin[3] = {0.f, 0.f, 0.f}, bmax[3] = {0.f, 0.f, 0.f};  // computeBounds of an empty scene
+    if (n > 0) b.bounds_of(0, n, bmin, bmax);
+    std::vector<std::pair<float, int32_t>> keys;
+    b.build(0, n, bmin, bmax, 0, 0, memo, keys);
 }
 
 // ------------------------------------------------------------------------------------ leaf grid
@@ -244,7 +269,6 @@ void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
     };
     const size_t nCells = (size_t)g.dims[0] * g.dims[1] * g.dims[2];
     g.leaves.resize(leafNodes.size());
-    std::vector<uint32_t> count(nCells + 1, 0u);
     for (size_t li = 0; li < leafNodes.size(); ++li) {
         const rm_bvh_node& nd = nodes[(size_t)leafNodes[li]];
         int lo[3], hi[3];
@@ -253,37 +277,54 @@ void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
             hi[k] = hi_idx(nd.bmax[k], k);
         }
         g.leaves[li] = {leafNodes[li], (uint32_t)(lo[0] | (lo[1] << 8) | (lo[2] << 16)), (uint32_t)(hi[0] | (hi[1] << 8) | (hi[2] << 16))};
-        for (int z = lo[2]; z <= hi[2]; ++z)
-            for (int y = lo[1]; y <= hi[1]; ++y)
-                for (int x = lo[0]; x <= hi[0]; ++x) count[((size_t)z * g.dims[1] + y) * g.dims[0] + x + 1]++;
     }
+    // Every pass below scatters leaf references into per-cell lists in ascending leaf order.  The grid is cut into slabs of z
+    // layers, one per thread: a thread walks ALL leaves but touches only the cells of its slab, so no two threads share a cell
+    // (no atomics) and the order within a cell is the serial one.
+    const int nSlabs = leafNodes.size() >= 4096 ? std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, g.dims[2]})) : 1;
+    auto slabs = [&](auto&& fn) {  // fn(z0, z1): layers [z0, z1)
+        if (nSlabs <= 1) return fn(0, g.dims[2]);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nSlabs; ++t) {
+            const int z0 = (int)((int64_t)g.dims[2] * t / nSlabs), z1 = (int)((int64_t)g.dims[2] * (t + 1) / nSlabs);
+            if (z0 < z1) th.emplace_back([&fn, z0, z1] { fn(z0, z1); });
+        }
+        for (auto& t : th) t.join();
+    };
+    // cells of leaf `lr` inside layers [z0, z1); k < 0: its whole range, else only the face it is entered through by a step
+    // along axis k >> 1 (k & 1: in the negative direction, i.e. the range's hi face)
+    auto for_cells = [&](const LeafRef& lr, int k, int z0, int z1, auto&& fn) {
+        int lo[3] = {(int)(lr.lo & 255), (int)((lr.lo >> 8) & 255), (int)((lr.lo >> 16) & 255)};
+        int hi[3] = {(int)(lr.hi & 255), (int)((lr.hi >> 8) & 255), (int)((lr.hi >> 16) & 255)};
+        if (k >= 0) {
+            const int a = k >> 1;
+            if (k & 1) lo[a] = hi[a];
+            else hi[a] = lo[a];
+        }
+        const int zb = std::max(lo[2], z0), ze = std::min(hi[2], z1 - 1);
+        for (int z = zb; z <= ze; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) fn(((size_t)z * g.dims[1] + y) * g.dims[0] + x);
+    };
+    std::vector<uint32_t> count(nCells + 1, 0u);
+    slabs([&](int z0, int z1) {
+        for (const LeafRef& lr : g.leaves) for_cells(lr, -1, z0, z1, [&](size_t c) { count[c + 1]++; });
+    });
     for (size_t c = 0; c < nCells; ++c) count[c + 1] += count[c];
     g.cell_start = count;
     g.cell_leaf.assign(g.cell_start[nCells], 0);
     std::vector<uint32_t> fill(g.cell_start.begin(), g.cell_start.end() - 1);
-    for (size_t li = 0; li < g.leaves.size(); ++li) {  // ascending leaf ordinal within each cell
-        const LeafRef& lr = g.leaves[li];
-        int lo[3] = {(int)(lr.lo & 255), (int)((lr.lo >> 8) & 255), (int)((lr.lo >> 16) & 255)};
-        int hi[3] = {(int)(lr.hi & 255), (int)((lr.hi >> 8) & 255), (int)((lr.hi >> 16) & 255)};
-        for (int z = lo[2]; z <= hi[2]; ++z)
-            for (int y = lo[1]; y <= hi[1]; ++y)
-                for (int x = lo[0]; x <= hi[0]; ++x) g.cell_leaf[fill[((size_t)z * g.dims[1] + y) * g.dims[0] + x]++] = (int32_t)li;
-    }
+    slabs([&](int z0, int z1) {
+        for (size_t li = 0; li < g.leaves.size(); ++li)  // ascending leaf ordinal within each cell
+            for_cells(g.leaves[li], -1, z0, z1, [&](size_t c) { g.cell_leaf[fill[c]++] = (int32_t)li; });
+    });
     // ---- direction lists
     static_assert(sizeof(LeafGrid::CellDir) == 16, "CellDir is one 16-byte load");
-    auto for_face = [&](const LeafRef& lr, int k, auto&& fn) {
-        int lo[3] = {(int)(lr.lo & 255), (int)((lr.lo >> 8) & 255), (int)((lr.lo >> 16) & 255)};
-        int hi[3] = {(int)(lr.hi & 255), (int)((lr.hi >> 8) & 255), (int)((lr.hi >> 16) & 255)};
-        const int a = k >> 1;
-        if (k & 1) lo[a] = hi[a];  // step in -a: the range starts at its hi face
-        else hi[a] = lo[a];        // step in +a: at its lo face
-        for (int z = lo[2]; z <= hi[2]; ++z)
-            for (int y = lo[1]; y <= hi[1]; ++y)
-                for (int x = lo[0]; x <= hi[0]; ++x) fn(((size_t)z * g.dims[1] + y) * g.dims[0] + x);
-    };
     std::vector<uint32_t> dcount(nCells * 6, 0u);
-    for (size_t li = 0; li < g.leaves.size(); ++li)
-        for (int k = 0; k < 6; ++k) for_face(g.leaves[li], k, [&](size_t c) { dcount[c * 6 + k]++; });
+    slabs([&](int z0, int z1) {
+        for (const LeafRef& lr : g.leaves)
+            for (int k = 0; k < 6; ++k) for_cells(lr, k, z0, z1, [&](size_t c) { dcount[c * 6 + k]++; });
+    });
     g.cell_dir.resize(nCells);
     std::vector<uint32_t> dfill(nCells * 6, 0u);
     uint64_t total = 0;
@@ -299,8 +340,10 @@ void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
     if (total > 0xFFFFFFFFull) g.dir_ok = false;
     if (g.dir_ok) {
         g.dir_node.assign((size_t)total, 0u);
-        for (size_t li = 0; li < g.leaves.size(); ++li)  // ascending leaf ordinal within every list
-            for (int k = 0; k < 6; ++k) for_face(g.leaves[li], k, [&](size_t c) { g.dir_node[dfill[c * 6 + k]++] = (uint32_t)g.leaves[li].node; });
+        slabs([&](int z0, int z1) {
+            for (const LeafRef& lr : g.leaves)  // ascending leaf ordinal within every list
+                for (int k = 0; k < 6; ++k) for_cells(lr, k, z0, z1, [&](size_t c) { g.dir_node[dfill[c * 6 + k]++] = (uint32_t)lr.node; });
+        });
     } else {
         g.cell_dir.clear();
     }
@@ -316,6 +359,161 @@ static double box_distance(const float* amin, const float* amax, const float* bm
     }
     return hypot3(d[0], d[1], d[2]);
 }
+
+// min over every primitive box of box_distance(node box, primitive box) — what computeMinDistances (octree.ts:149-191) finds by
+// trying them all, once per empty node.  A minimum does not depend on the order of its candidates, so the same double comes out
+// of a pruned search: the boxes are sorted along a Morton curve and covered by an implicit binary tree of ranges; a range is
+// skipped when a LOWER BOUND of the distance to its covering box already exceeds the best candidate, and every candidate that is
+// looked at goes through the very same box_distance (V8's compensated hypot included).  The bound is the plain Euclidean
+// gap of the covering box shrunk by 1e-9: a member box is inside the covering box, so each of its axis gaps is at least the
+// cover's, and hypot3 is within a few ulp of the true norm.  Boxes with a NaN bound compare false everywhere and yield distance 0
+// in the reference arithmetic; a scene that has one takes the exhaustive loop.
+namespace {
+class NearestBox {
+public:
+    explicit NearestBox(const std::vector<PrimGeom>& geom) : geom_(geom) {
+        const size_t n = geom.size();
+        for (const PrimGeom& g : geom)
+            for (int k = 0; k < 3; ++k)
+                if (std::isnan(g.bmin[k]) || std::isnan(g.bmax[k])) exhaustive_ = true;
+        if (n <= 2 * kLeaf) exhaustive_ = true;
+        if (exhaustive_) return;
+        // Morton order of the box centres (10 bits per axis over the finite centres; infinite boxes — Repetition — sort first)
+        std::vector<double> ctr(3 * n);
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) ctr[3 * i + (size_t)k] = 0.5 * ((double)geom[i].bmin[k] + (double)geom[i].bmax[k]);
+        double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int k = 0; k < 3; ++k) {
+            bool seeded = false;
+            for (size_t i = 0; i < n; ++i) {
+                const double c = ctr[3 * i + (size_t)k];
+                if (!std::isfinite(c)) continue;
+                lo[k] = seeded ? std::min(lo[k], c) : c;
+                hi[k] = seeded ? std::max(hi[k], c) : c;
+                seeded = true;
+            }
+        }
+        std::vector<std::pair<uint32_t, int32_t>> code(n);
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t m = 0;
+            for (int k = 0; k < 3; ++k) {
+                const double c = ctr[3 * i + (size_t)k], ext = hi[k] - lo[k];
+                uint32_t q = 0;
+                if (std::isfinite(c) && ext > 0) q = (uint32_t)std::min(1023.0, std::max(0.0, (c - lo[k]) / ext * 1024.0));
+                m |= spread(q) << k;
+            }
+            code[i] = {m, (int32_t)i};
+        }
+        std::sort(code.begin(), code.end());
+        order_.resize(n);
+        for (size_t i = 0; i < n; ++i) order_[i] = code[i].second;
+        // implicit tree over [0, n): node k covers a range, children split it in half, ranges of <= kLeaf boxes are leaves
+        cover_.reserve(2 * (n / kLeaf + 1));
+        build(0, n);
+    }
+    double min_distance(const float* amin, const float* amax) const {
+        double best = std::numeric_limits<double>::infinity();
+        if (exhaustive_) {
+            for (const PrimGeom& g : geom_) {
+                const double d = box_distance(amin, amax, g.bmin, g.bmax);
+                if (d < best) best = d;
+            }
+            return best;
+        }
+        struct Item {
+            uint32_t node;
+            double lb;
+        };
+        Item stack[64];
+        int sp = 0;
+        stack[sp++] = {0u, 0.0};
+        while (sp > 0) {
+            const Item it = stack[--sp];
+            if (it.lb > best) continue;
+            const Cover& c = cover_[it.node];
+            if (c.left == 0u) {  // leaf range
+                for (uint32_t i = c.lo; i < c.hi; ++i) {
+                    const PrimGeom& g = geom_[(size_t)order_[i]];
+                    const double d = box_distance(amin, amax, g.bmin, g.bmax);
+                    if (d < best) best = d;
+                }
+                continue;
+            }
+            const double l = lower_bound(amin, amax, cover_[c.left]), r = lower_bound(amin, amax, cover_[c.right]);
+            // nearer child on top of the stack
+            if (l <= r) {
+                if (r <= best) stack[sp++] = {c.right, r};
+                if (l <= best) stack[sp++] = {c.left, l};
+            } else {
+                if (l <= best) stack[sp++] = {c.left, l};
+                if (r <= best) stack[sp++] = {c.right, r};
+            }
+        }
+        return best;
+    }
+
+private:
+    static constexpr size_t kLeaf = 8;
+    struct Cover {
+        float bmin[3], bmax[3];
+        uint32_t lo, hi, left, right;  // left == 0: leaf (node 0 is the root and nobody's child)
+    };
+    static uint32_t spread(uint32_t v) {  // 10 bits -> every third bit
+        v &= 1023u;
+        v = (v | (v << 16)) & 0x030000FFu;
+        v = (v | (v << 8)) & 0x0300F00Fu;
+        v = (v | (v << 4)) & 0x030C30C3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    }
+    static double lower_bound(const float* amin, const float* amax, const Cover& c) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) {
+            double d = 0;
+            if (amax[k] < c.bmin[k]) d = (double)c.bmin[k] - (double)amax[k];
+            else if (c.bmax[k] < amin[k]) d = (double)amin[k] - (double)c.bmax[k];
+            s += d * d;
+        }
+        return std::sqrt(s) * (1.0 - 1e-9);
+    }
+    uint32_t build(size_t lo, size_t hi) {
+        const uint32_t me = (uint32_t)cover_.size();
+        cover_.emplace_back();
+        cover_[me].lo = (uint32_t)lo;
+        cover_[me].hi = (uint32_t)hi;
+        cover_[me].left = cover_[me].right = 0u;
+        if (hi - lo <= kLeaf) {
+            Cover& c = cover_[me];
+            for (int k = 0; k < 3; ++k) {
+                c.bmin[k] = std::numeric_limits<float>::infinity();
+                c.bmax[k] = -std::numeric_limits<float>::infinity();
+            }
+            for (size_t i = lo; i < hi; ++i) {
+                const PrimGeom& g = geom_[(size_t)order_[i]];
+                for (int k = 0; k < 3; ++k) {
+                    c.bmin[k] = std::min(c.bmin[k], g.bmin[k]);
+                    c.bmax[k] = std::max(c.bmax[k], g.bmax[k]);
+                }
+            }
+            return me;
+        }
+        const size_t mid = lo + (hi - lo) / 2;
+        const uint32_t l = build(lo, mid), r = build(mid, hi);
+        Cover& c = cover_[me];
+        c.left = l;
+        c.right = r;
+        for (int k = 0; k < 3; ++k) {
+            c.bmin[k] = std::min(cover_[l].bmin[k], cover_[r].bmin[k]);
+            c.bmax[k] = std::max(cover_[l].bmax[k], cover_[r].bmax[k]);
+        }
+        return me;
+    }
+    const std::vector<PrimGeom>& geom_;
+    bool exhaustive_ = false;
+    std::vector<int32_t> order_;
+    std::vector<Cover> cover_;
+};
+}  // namespace
 
 void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>& nodes, std::vector<int32_t>& leafPrims) {
     const int maxDepth = 6, maxPrimsPerNode = 4;  // octree.ts:39-40
@@ -405,19 +603,15 @@ void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>
     std::vector<size_t> empties;
     for (size_t i = 0; i < nn; ++i)
         if (nodes[i].is_empty) empties.push_back(i);
+    NearestBox nearest(geom);
     auto work = [&](size_t lo, size_t hi) {
         for (size_t e = lo; e < hi; ++e) {
             rm_octree_node& nd = nodes[empties[e]];
-            double minD = std::numeric_limits<double>::infinity();
-            for (const PrimGeom& g : geom) {
-                double d = box_distance(nd.bmin, nd.bmax, g.bmin, g.bmax);
-                if (d < minD) minD = d;
-            }
+            const double minD = nearest.min_distance(nd.bmin, nd.bmax);
             nd.min_distance = (minD != std::numeric_limits<double>::infinity()) ? std::max(0.0, minD) : 0.0;
         }
     };
-    const size_t total = empties.size() * geom.size();
-    unsigned nt = total > (1u << 22) ? std::max(1u, std::thread::hardware_concurrency()) : 1u;
+    const unsigned nt = empties.size() >= 4096 ? std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1u;
     if (nt <= 1) {
         work(0, empties.size());
     } else {

@@ -124,11 +124,13 @@ OCT_DT = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("fc", "<i4"), ("pf",
                    ("pad", "u1", 2), ("md", "<f8")])
 
 
-def _scene_cases():
-    return [("preset", i) for i in sm.SUPPORTED_PRESETS] + [("synthetic", 300), ("synthetic", 3000)]
+def _scene_cases(big=()):
+    # 20 000 and 100 000 objects: past the sizes where the builders fork threads (BVH subtrees, leaf-grid slabs, octree
+    # minDistance queries) and where the octree's nearest-box search prunes instead of trying every box
+    return [("preset", i) for i in sm.SUPPORTED_PRESETS] + [("synthetic", n) for n in (300, 3000, 20000) + tuple(big)]
 
 
-@pytest.mark.parametrize("kind,arg", _scene_cases())
+@pytest.mark.parametrize("kind,arg", _scene_cases(big=(100000,)))
 def test_native_bvh_builder_matches_oracle(oracle, kind, arg):
     if kind == "preset":
         pl = sm.get_preset(arg)
@@ -173,6 +175,22 @@ def test_native_octree_builder_matches_oracle(oracle, kind, arg):
     assert np.array_equal(a["lvl"], lvl) and np.array_equal(a["emp"], emp)
     assert np.array_equal(bits(a["md"]), bits(mind))
     assert np.array_equal(leaf, oleaf)
+
+
+def test_leaf_grid_lists_equal_brute_force(tmp_path):
+    """The leaf grid of the fast BVH path (csrc/rm_build.cpp build_leaf_grid: per-cell leaf lists + the six direction lists of the
+    DDA walk, filled by z-slab threads) against a brute-force rebuild of every list, in a C++ harness linked with the product's
+    builder source: above and below the size where the threads start, a flat scene (one z layer), one sphere, no sphere."""
+    cxx = shutil.which(os.environ.get("CXX", "g++"))
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    exe = tmp_path / "leafgrid_harness"
+    inc = [p for p in ("/usr/local/cuda/include",) if os.path.isdir(p)]
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-pthread"] + ["-I" + p for p in inc] +
+                          [os.path.join(ROOT, "tests", "leafgrid_harness.cc"), os.path.join(ROOT, "cpu_raymarcher_b200", "csrc", "rm_build.cpp"), "-o", str(exe)])
+    for args in (["9000", "0.01", "0.05", "5"], ["9000", "0.01", "0.05", "6", "flat"], ["500", "0.1", "0.6", "7"], ["1", "0.1", "0.6", "8"], ["0", "0.1", "0.6", "9"]):
+        r = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("OK"), (args, r.stdout, r.stderr)
 
 
 def test_builders_handle_empty_and_rotated_scenes(oracle):
