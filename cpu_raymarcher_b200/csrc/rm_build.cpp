@@ -16,6 +16,7 @@
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -199,12 +200,18 @@ struct BvhBuilder {
         const int32_t l = me + 1, r = l + count_nodes(mid - lo, depth + 1, memo);
         nd.left = l;
         nd.right = r;
+        std::thread t;
         if (depth < kForkDepth && n >= kParallelMin) {
-            std::thread t([&, l] {
-                CountMemo m2;
-                std::vector<std::pair<float, int32_t>> k2;
-                build(lo, mid, lmin, lmax, depth + 1, l, m2, k2);
-            });
+            try {
+                t = std::thread([&, l] {
+                    CountMemo m2;
+                    std::vector<std::pair<float, int32_t>> k2;
+                    build(lo, mid, lmin, lmax, depth + 1, l, m2, k2);
+                });
+            } catch (const std::system_error&) {  // no thread to be had: build the left subtree here as well
+            }
+        }
+        if (t.joinable()) {
             build(mid, hi, rmin, rmax, depth + 1, r, memo, keys);
             t.join();
         } else {
@@ -287,7 +294,12 @@ void build_leaf_grid(const std::vector<rm_bvh_node>& nodes, LeafGrid& g) {
         std::vector<std::thread> th;
         for (int t = 0; t < nSlabs; ++t) {
             const int z0 = (int)((int64_t)g.dims[2] * t / nSlabs), z1 = (int)((int64_t)g.dims[2] * (t + 1) / nSlabs);
-            if (z0 < z1) th.emplace_back([&fn, z0, z1] { fn(z0, z1); });
+            if (z0 >= z1) continue;
+            try {
+                th.emplace_back([&fn, z0, z1] { fn(z0, z1); });
+            } catch (const std::system_error&) {  // no thread to be had: this slab runs here
+                fn(z0, z1);
+            }
         }
         for (auto& t : th) t.join();
     };
@@ -619,7 +631,12 @@ void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>
         size_t per = (empties.size() + nt - 1) / nt;
         for (unsigned t = 0; t < nt; ++t) {
             size_t lo = std::min(empties.size(), t * per), hi = std::min(empties.size(), lo + per);
-            if (lo < hi) th.emplace_back(work, lo, hi);
+            if (lo >= hi) continue;
+            try {
+                th.emplace_back(work, lo, hi);
+            } catch (const std::system_error&) {
+                work(lo, hi);
+            }
         }
         for (auto& t : th) t.join();
     }

@@ -36,13 +36,12 @@ def build_bvh(types, w2l, params, flags: int = 0):
     types = np.ascontiguousarray(types, np.uint8)
     w2l = np.ascontiguousarray(w2l, np.float32)
     params = np.ascontiguousarray(params, np.float64)
-    nn, nl = C.c_int32(0), C.c_int32(0)
-    rc = L.rm_build_bvh(len(types), _ptr(types), _ptr(w2l), _ptr(params), flags, None, C.byref(nn), None, C.byref(nl))
-    if rc:
-        raise RmError(rc, "rm_build_bvh")
-    nodes = (_lib.BvhNode * max(nn.value, 1))()
-    leaf = np.zeros(max(nl.value, 1), np.int32)
-    rc = L.rm_build_bvh(len(types), _ptr(types), _ptr(w2l), _ptr(params), flags, nodes, C.byref(nn), _ptr(leaf), C.byref(nl))
+    # one call: a median-split BVH whose leaves are never empty has at most 2n - 1 nodes and exactly n leaf entries
+    n = len(types)
+    nn, nl = C.c_int32(2 * n + 1), C.c_int32(n + 1)
+    nodes = (_lib.BvhNode * nn.value)()
+    leaf = np.zeros(nl.value, np.int32)
+    rc = L.rm_build_bvh(n, _ptr(types), _ptr(w2l), _ptr(params), flags, nodes, C.byref(nn), _ptr(leaf), C.byref(nl))
     if rc:
         raise RmError(rc, "rm_build_bvh")
     return nodes, nn.value, leaf[: nl.value]
@@ -94,10 +93,14 @@ def _build_scene(fn_name, node_type, types, w2l, params, op_nodes, object_root, 
     L = _lib.lib()
     s, keep = _fill_scene(types, w2l, params, op_nodes, object_root)
     fn = getattr(L, fn_name)
-    nn, nl = C.c_int32(0), C.c_int32(0)
-    rc = fn(C.byref(s), flags, None, C.byref(nn), None, C.byref(nl))
-    if rc:
-        raise RmError(rc, fn_name)
+    if node_type is _lib.BvhNode:  # sizes known up front (see build_bvh): one build instead of a sizing call plus a build
+        n_obj = int(s.n_objects) if s.n_objects > 0 else int(s.n_prims)
+        nn, nl = C.c_int32(2 * n_obj + 1), C.c_int32(n_obj + 1)
+    else:
+        nn, nl = C.c_int32(0), C.c_int32(0)
+        rc = fn(C.byref(s), flags, None, C.byref(nn), None, C.byref(nl))
+        if rc:
+            raise RmError(rc, fn_name)
     nodes = (node_type * max(nn.value, 1))()
     leaf = np.zeros(max(nl.value, 1), np.int32)
     rc = fn(C.byref(s), flags, nodes, C.byref(nn), _ptr(leaf), C.byref(nl))
