@@ -588,14 +588,17 @@ void build_octree(const std::vector<PrimGeom>& geom, std::vector<rm_octree_node>
             ch.first_child = -1;
             ch.is_empty = 1;
         }
+        // closed-interval overlap of the primitive's box with every child (octree.ts:91-103).  The eight tests share their
+        // per-axis halves: the low child spans [bmin, c], the high child [c, bmax] on each axis.
         for (int32_t p : cur.prims) {
             const PrimGeom& g = geom[(size_t)p];
-            for (int i = 0; i < 8; ++i) {
-                const rm_octree_node& ch = nodes[(size_t)(first + i)];
-                bool hit = ch.bmin[0] <= g.bmax[0] && ch.bmax[0] >= g.bmin[0] && ch.bmin[1] <= g.bmax[1] &&
-                           ch.bmax[1] >= g.bmin[1] && ch.bmin[2] <= g.bmax[2] && ch.bmax[2] >= g.bmin[2];
-                if (hit) childPrims[i].push_back(p);
+            bool half[3][2];
+            for (int k = 0; k < 3; ++k) {
+                half[k][0] = bmin[k] <= g.bmax[k] && c[k] >= g.bmin[k];
+                half[k][1] = c[k] <= g.bmax[k] && bmax[k] >= g.bmin[k];
             }
+            for (int i = 0; i < 8; ++i)
+                if (half[0][i & 1] && half[1][(i >> 1) & 1] && half[2][(i >> 2) & 1]) childPrims[i].push_back(p);
         }
         for (int i = 0; i < 8; ++i) q.push_back({first + i, std::move(childPrims[i])});
     }
