@@ -177,6 +177,35 @@ def test_native_octree_builder_matches_oracle(oracle, kind, arg):
     assert np.array_equal(leaf, oleaf)
 
 
+def test_builder_entry_points_reject_bad_arguments():
+    """rm_build_bvh / rm_build_octree: the sizing call (nodes == NULL) reports the counts, a too-small capacity and missing
+    arrays are RM_ERR_ARG — never a partial write."""
+    L = _lib.lib()
+    t, m, q = sm.synthetic_spheres(50).arrays()
+    t, m, q = np.ascontiguousarray(t, np.uint8), np.ascontiguousarray(m, np.float32), np.ascontiguousarray(q, np.float64)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for fn, node_t in ((L.rm_build_bvh, _lib.BvhNode), (L.rm_build_octree, _lib.OctreeNode)):
+        nn, nl = C.c_int32(0), C.c_int32(0)
+        assert fn(50, ptr(t), ptr(m), ptr(q), 0, None, C.byref(nn), None, C.byref(nl)) == 0
+        assert nn.value > 0 and nl.value >= 50
+        need_n, need_l = nn.value, nl.value
+        nodes = (node_t * need_n)()
+        leaf = np.full(need_l, -7, np.int32)
+        small = C.c_int32(need_n - 1)
+        assert fn(50, ptr(t), ptr(m), ptr(q), 0, nodes, C.byref(small), ptr(leaf), C.byref(nl)) == _lib.RM_ERR_ARG
+        assert (leaf == -7).all(), "nothing may be written when the capacity is too small"
+        small_l = C.c_int32(need_l - 1)
+        nn.value = need_n
+        assert fn(50, ptr(t), ptr(m), ptr(q), 0, nodes, C.byref(nn), ptr(leaf), C.byref(small_l)) == _lib.RM_ERR_ARG
+        assert fn(50, ptr(t), ptr(m), ptr(q), 0, nodes, C.byref(nn), None, C.byref(nl)) == _lib.RM_ERR_ARG  # leaf array missing
+        assert fn(50, None, ptr(m), ptr(q), 0, None, C.byref(nn), None, C.byref(nl)) == _lib.RM_ERR_ARG
+        assert fn(-1, ptr(t), ptr(m), ptr(q), 0, None, C.byref(nn), None, C.byref(nl)) == _lib.RM_ERR_ARG
+        assert fn(50, ptr(t), ptr(m), ptr(q), 0, None, None, None, C.byref(nl)) == _lib.RM_ERR_ARG
+        nn.value, nl.value = need_n, need_l
+        assert fn(50, ptr(t), ptr(m), ptr(q), 0, nodes, C.byref(nn), ptr(leaf), C.byref(nl)) == 0
+        assert (nn.value, nl.value) == (need_n, need_l) and (leaf >= 0).all() and (leaf < 50).all()
+
+
 def test_leaf_grid_lists_equal_brute_force(tmp_path):
     """The leaf grid of the fast BVH path (csrc/rm_build.cpp build_leaf_grid: per-cell leaf lists + the six direction lists of the
     DDA walk, filled by z-slab threads) against a brute-force rebuild of every list, in a C++ harness linked with the product's
